@@ -1,0 +1,76 @@
+"""ctypes binding of libbuddy_b200.so (the C ABI declared in include/buddy_b200.h).
+
+There is no CPU fallback: if the library is missing, or a call fails, this raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libbuddy_b200.so")
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_float = ctypes.c_float
+
+
+class BuddyError(RuntimeError):
+    pass
+
+
+class GemmDesc(ctypes.Structure):
+    """Mirror of `buddy_gemm_desc` (include/buddy_b200.h)."""
+    _fields_ = [
+        ("a", c_void_p), ("a_c", c_int), ("a_stride_w", c_i64), ("a_stride_h", c_i64), ("a_stride_b", c_i64),
+        ("a2", c_void_p), ("a2_c", c_int), ("a2_stride_w", c_i64), ("a2_stride_h", c_i64), ("a2_stride_b", c_i64),
+        ("b", c_void_p), ("b_rows", c_int), ("b_t", c_int), ("b_stride_n", c_i64), ("b_stride_t", c_i64),
+        ("b2", c_void_p), ("b2_rows", c_int), ("b2_stride_n", c_i64),
+        ("batch", c_int), ("H", c_int), ("W", c_int),
+        ("taps", c_int), ("b_batched", c_int), ("n_total", c_int), ("n_tile", c_int),
+        ("out", c_void_p), ("out_fp16", c_int), ("ldc", c_i64), ("col_off", c_int),
+        ("bias", c_void_p), ("bias_b", c_void_p), ("resid", c_void_p), ("ld_res", c_i64),
+        ("scale", c_float), ("stats", c_void_p), ("max_ctas", c_int),
+    ]
+
+
+def lib():
+    """Load the shared library once.  Raises BuddyError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise BuddyError(
+                f"{_LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(buddy_b200 has no CPU fallback)")
+        l = ctypes.CDLL(_LIB_PATH)
+        l.buddy_last_error.restype = ctypes.c_char_p
+        l.buddy_launch_count.restype = c_i64
+        _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().buddy_last_error().decode("utf-8", "replace")
+        raise BuddyError(f"{what} failed (rc={rc}): {msg}")
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "buddy_b200 kernels take CUDA tensors only (no CPU fallback)"
+    return c_void_p(t.data_ptr())
+
+
+def launch_count():
+    return int(lib().buddy_launch_count())
+
+
+def reset_launch_count():
+    lib().buddy_reset_launch_count()

@@ -1,0 +1,515 @@
+// Implicit-GEMM 3x3 / 1x1 convolution and batched GEMM for sm_100a.
+//
+//   * operands: fp16, channels-last; fp32 accumulation in TMEM (tcgen05.mma kind::f16, M=128, N<=256, K=16)
+//   * A tile  : TMA 4-D tiled load of a (bh x bw) pixel patch x 64 channels, shifted by the filter tap;
+//               out-of-image coordinates are zero-filled by TMA == the conv's "same" padding, so no im2col
+//               buffer and no halo logic exist anywhere.
+//   * B tile  : TMA 3-D load of [n_tile rows][64 k] of the packed weights for (tap, k-chunk)
+//   * both land in SWIZZLE_128B K-major layout, exactly what the UMMA shared-memory descriptors expect
+//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue
+//   * persistent CTAs (one per SM), double-buffered TMEM accumulator so the epilogue of tile i overlaps
+//     the mainloop of tile i+1
+//   * epilogue: TMEM -> registers -> (+bias, +per-image bias, +residual) * scale -> fp32/fp16 global,
+//               optional fused GroupNorm partial statistics (fp64 atomics per 4-channel bundle)
+//
+// Replaces nn.Conv2d / NIN / attention einsums of the reference network
+// (networks/ncsnpp_utils/layers.py:100-126,548-557; layerspp.py:75-91) and their data-gradients.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/buddy_b200.h"
+#include "common.cuh"
+
+namespace buddy {
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;            // fp16 elements per k-block = 128 bytes = one swizzle row
+constexpr int kStageA = kTileM * 128;  // bytes
+constexpr int kMaxStages = 8;
+constexpr int kAccStride = 256;        // TMEM columns per accumulator stage
+constexpr int kThreads = 192;
+
+struct GemmParams {
+  int batch, H, W;
+  int bh, bw, tiles_h, tiles_w;
+  int n_tiles, n_tile, n_total;
+  int taps, kchunks1, kchunks2, b_batched;
+  int stages;
+  float* out32;
+  __half* out16;
+  long long ldc;
+  int col_off;
+  const float* bias;
+  const float* bias_b;
+  const float* resid;
+  long long ld_res;
+  float scale;
+  double* stats;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                 const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16B aligned by the runtime: round up to 1024 (swizzle-128B atoms)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = kStageA + p.n_tile * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* full_bar = bars;                     // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
+  uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.kchunks2 > 0) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int total_tiles = p.batch * tiles_per_img * p.n_tiles;
+  const int kb_phase1 = p.taps * p.kchunks1;
+  const int num_kb = kb_phase1 + p.kchunks2;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles;
+        const int pt = t / p.n_tiles;
+        const int b = pt / tiles_per_img;
+        const int r = pt - b * tiles_per_img;
+        const int h0 = (r / p.tiles_w) * p.bh;
+        const int w0 = (r % p.tiles_w) * p.bw;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + kStageA;
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          if (kb < kb_phase1) {
+            const int tap = kb / p.kchunks1;
+            const int kc = kb - tap * p.kchunks1;
+            int dy = 0, dx = 0;
+            if (p.taps == 9) {
+              dy = tap / 3 - 1;
+              dx = tap % 3 - 1;
+            }
+            tma_load_4d(&tmA, sa, &full_bar[stage], kc * kBlockK, w0 + dx, h0 + dy, b);
+            tma_load_3d(&tmB, sb, &full_bar[stage], kc * kBlockK, nt * p.n_tile, p.b_batched ? b : tap);
+          } else {
+            const int kc = kb - kb_phase1;
+            tma_load_4d(&tmA2, sa, &full_bar[stage], kc * kBlockK, w0, h0, b);
+            tma_load_3d(&tmB2, sb, &full_bar[stage], kc * kBlockK, nt * p.n_tile, 0);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (single thread)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kTileM, p.n_tile);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint64_t da = make_sw128_kmajor_desc(sa);
+          const uint64_t db = make_sw128_kmajor_desc(sa + kStageA);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the 128B swizzle row: +2 in (addr >> 4) units
+            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue (4 warps, 128 threads)
+    const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = wq * 32 + lane;
+    const int hl = m / p.bw;
+    const int wl = m - hl * p.bw;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % p.n_tiles;
+      const int pt = t / p.n_tiles;
+      const int b = pt / tiles_per_img;
+      const int r = pt - b * tiles_per_img;
+      const int h = (r / p.tiles_w) * p.bh + hl;
+      const int w = (r % p.tiles_w) * p.bw + wl;
+      const bool valid = (h < p.H) && (w < p.W);
+      const long long pix = (static_cast<long long>(b) * p.H + h) * p.W + w;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * kAccStride;
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+        uint32_t rr[32];
+        tmem_ld_32x32(taddr + c0, rr);
+        tmem_ld_wait();
+        const int ncol0 = nt * p.n_tile + c0;  // first global output column of this chunk
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+        const int nvalid = min(32, min(p.n_tile - c0, p.n_total - ncol0));
+        if (nvalid <= 0) continue;
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) v[j] += __ldg(p.bias + ncol0 + j);
+        }
+        if (p.bias_b) {
+          const float* bb = p.bias_b + static_cast<long long>(b) * p.n_total + ncol0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) v[j] += __ldg(bb + j);
+        }
+        if (p.resid && valid) {
+          const float* rp = p.resid + pix * p.ld_res + ncol0;
+          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(rp + j));
+              v[j] += q.x;
+              v[j + 1] += q.y;
+              v[j + 2] += q.z;
+              v[j + 3] += q.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) v[j] += __ldg(rp + j);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+
+        if (valid) {
+          if (p.out16) {
+            __half* op = p.out16 + pix * p.ldc + p.col_off + ncol0;
+            if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                __half2 h0 = __floats2half2_rn(v[j], v[j + 1]);
+                __half2 h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]);
+                __half2 h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                uint4 q;
+                q.x = *reinterpret_cast<uint32_t*>(&h0);
+                q.y = *reinterpret_cast<uint32_t*>(&h1);
+                q.z = *reinterpret_cast<uint32_t*>(&h2);
+                q.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(op + j) = q;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) op[j] = __float2half_rn(v[j]);
+            }
+          } else {
+            float* op = p.out32 + pix * p.ldc + p.col_off + ncol0;
+            if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) op[j] = v[j];
+            }
+          }
+        }
+        if (p.stats) {
+          // GroupNorm partial statistics of what was just written: per 4-channel bundle, over this warp's
+          // 32 pixels, then one fp64 atomic pair per bundle per warp.
+          double* sp = p.stats + (static_cast<long long>(b) * (p.n_total >> 2) + (ncol0 >> 2)) * 2;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float s = 0.f, q = 0.f;
+            if (valid && g * 4 < nvalid) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float x = v[g * 4 + j];
+                s += x;
+                q += x * x;
+              }
+            }
+            s = warp_sum(s);
+            q = warp_sum(q);
+            if (lane == 0 && g * 4 < nvalid) {
+              atomicAdd(sp + g * 2, static_cast<double>(s));
+              atomicAdd(sp + g * 2 + 1, static_cast<double>(q));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// fp16 tensor map with `rank` dims (dim 0 contiguous), 128B swizzle, zero OOB fill.
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                      const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return BUDDY_ERR_CUDA;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_el[i] * 2;  // bytes
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_last_error("tensor map base not 16B aligned");
+    return BUDDY_ERR_INVALID;
+  }
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gstr[i] % 16 != 0) {
+      set_last_error("tensor map stride %d (%llu bytes) not a multiple of 16", i + 1, (unsigned long long)gstr[i]);
+      return BUDDY_ERR_INVALID;
+    }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return BUDDY_ERR_CUDA;
+  }
+  return 0;
+}
+
+static void choose_patch(int H, int W, int* bh, int* bw) {
+  long best = -1;
+  for (int w = 128; w >= 1; w >>= 1) {
+    const int h = 128 / w;
+    const long tiles = static_cast<long>((H + h - 1) / h) * ((W + w - 1) / w);
+    if (best < 0 || tiles < best) {
+      best = tiles;
+      *bh = h;
+      *bw = w;
+    }
+  }
+}
+
+std::atomic<long long> g_launches{0};
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+}  // namespace buddy
+
+using namespace buddy;
+
+extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!d || !d->a || !d->b || !d->out) {
+    set_last_error("buddy_conv_gemm: null pointer");
+    return BUDDY_ERR_INVALID;
+  }
+  if (d->a_c <= 0 || d->a_c % kBlockK != 0 || (d->a2 && (d->a2_c <= 0 || d->a2_c % kBlockK != 0))) {
+    set_last_error("buddy_conv_gemm: channel count must be a positive multiple of 64 (got %d / %d)", d->a_c,
+                   d->a2_c);
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  if (d->n_tile < 16 || d->n_tile > 256 || d->n_tile % 16 != 0) {
+    set_last_error("buddy_conv_gemm: n_tile must be a multiple of 16 in [16,256] (got %d)", d->n_tile);
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  if (d->taps != 1 && d->taps != 9) {
+    set_last_error("buddy_conv_gemm: taps must be 1 or 9 (got %d)", d->taps);
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  if (d->batch <= 0 || d->H <= 0 || d->W <= 0 || d->n_total <= 0) {
+    set_last_error("buddy_conv_gemm: empty problem (batch %d H %d W %d n %d)", d->batch, d->H, d->W, d->n_total);
+    return BUDDY_ERR_INVALID;
+  }
+  if (d->stats && (d->n_total % 4 != 0 || d->out_fp16)) {
+    set_last_error("buddy_conv_gemm: fused stats need fp32 output and n_total %% 4 == 0");
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  if ((d->a2 != nullptr) != (d->b2 != nullptr)) {
+    set_last_error("buddy_conv_gemm: a2 and b2 must be given together");
+    return BUDDY_ERR_INVALID;
+  }
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.batch = d->batch;
+  p.H = d->H;
+  p.W = d->W;
+  choose_patch(d->H, d->W, &p.bh, &p.bw);
+  p.tiles_h = (d->H + p.bh - 1) / p.bh;
+  p.tiles_w = (d->W + p.bw - 1) / p.bw;
+  p.n_tile = d->n_tile;
+  p.n_total = d->n_total;
+  p.n_tiles = (d->n_total + d->n_tile - 1) / d->n_tile;
+  p.taps = d->taps;
+  p.kchunks1 = d->a_c / kBlockK;
+  p.kchunks2 = d->a2 ? d->a2_c / kBlockK : 0;
+  p.b_batched = d->b_batched;
+  const int stage_bytes = kStageA + d->n_tile * 128;
+  int stages = (227 * 1024 - 2048) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) {
+    set_last_error("buddy_conv_gemm: not enough shared memory for 2 stages");
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  p.stages = stages;
+  p.out32 = d->out_fp16 ? nullptr : static_cast<float*>(d->out);
+  p.out16 = d->out_fp16 ? static_cast<__half*>(d->out) : nullptr;
+  p.ldc = d->ldc;
+  p.col_off = d->col_off;
+  p.bias = d->bias;
+  p.bias_b = d->bias_b;
+  p.resid = d->resid;
+  p.ld_res = d->ld_res;
+  p.scale = d->scale;
+  p.stats = d->stats;
+
+  CUtensorMap tmA, tmB, tmA2, tmB2;
+  {
+    uint64_t dims[4] = {(uint64_t)d->a_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
+    uint64_t str[4] = {1, (uint64_t)d->a_stride_w, (uint64_t)d->a_stride_h, (uint64_t)d->a_stride_b};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    int e = encode_map(&tmA, d->a, 4, dims, str, box);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)(d->a_c), (uint64_t)d->b_rows, (uint64_t)d->b_t};
+    uint64_t str[3] = {1, (uint64_t)d->b_stride_n, (uint64_t)d->b_stride_t};
+    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)d->n_tile, 1};
+    int e = encode_map(&tmB, d->b, 3, dims, str, box);
+    if (e) return e;
+  }
+  if (d->a2) {
+    uint64_t dims[4] = {(uint64_t)d->a2_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
+    uint64_t str[4] = {1, (uint64_t)d->a2_stride_w, (uint64_t)d->a2_stride_h, (uint64_t)d->a2_stride_b};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    int e = encode_map(&tmA2, d->a2, 4, dims, str, box);
+    if (e) return e;
+    uint64_t dimsb[3] = {(uint64_t)(d->a2_c), (uint64_t)d->b2_rows, 1};
+    uint64_t strb[3] = {1, (uint64_t)d->b2_stride_n, (uint64_t)d->b2_stride_n * (uint64_t)d->b2_rows};
+    uint32_t boxb[3] = {(uint32_t)kBlockK, (uint32_t)d->n_tile, 1};
+    e = encode_map(&tmB2, d->b2, 3, dimsb, strb, boxb);
+    if (e) return e;
+  } else {
+    tmA2 = tmA;
+    tmB2 = tmB;
+  }
+
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int e = check_cuda(
+        cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+        "cudaFuncSetAttribute(conv_gemm_kernel)");
+    if (e) return e;
+    attr_set = true;
+  }
+  const long long total_tiles = (long long)p.batch * p.tiles_h * p.tiles_w * p.n_tiles;
+  int grid = num_sms();
+  if (d->max_ctas > 0 && d->max_ctas < grid) grid = d->max_ctas;
+  if (total_tiles < grid) grid = (int)total_tiles;
+  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  BUDDY_CHECK_LAUNCH("conv_gemm_kernel");
+  return 0;
+}

@@ -1,0 +1,131 @@
+"""Parity of the tcgen05 implicit-GEMM conv / batched GEMM kernel against plain PyTorch fp32
+(the same op the reference runs: nn.Conv2d, networks/ncsnpp_utils/layers.py:100-126)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from buddy_b200 import ops
+    return ops
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def ref_conv(a16, w16, taps):
+    """a16: [B,H,W,C] fp16, w16: [T,N,K] fp16 -> [B,H,W,N] fp32 (exact products of the fp16 operands)."""
+    x = a16.float().permute(0, 3, 1, 2).double()
+    T, N, K = w16.shape
+    if taps == 9:
+        w = w16.double().view(3, 3, N, K).permute(2, 3, 0, 1)
+        y = F.conv2d(x, w, padding=1)
+    else:
+        w = w16.double().view(N, K, 1, 1)
+        y = F.conv2d(x, w)
+    return y.permute(0, 2, 3, 1).float()
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 16), (1000, 128, 256), (2112, 256, 768), (4096, 512, 384)])
+def test_plain_gemm(M, K, N):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(1, 1, M, K, device="cuda", generator=g).half()
+    w = torch.randn(1, N, K, device="cuda", generator=g).half()
+    out = torch.full((1, 1, M, N), float("nan"), device="cuda")
+    ops.conv_gemm(a, w, out, taps=1, n_total=N)
+    torch.cuda.synchronize()
+    ref = ref_conv(a, w, 1)
+    assert rel(out, ref) < 2e-6, rel(out, ref)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 64, 16), (2, 32, 66, 64, 128), (1, 64, 132, 128, 256),
+                                            (2, 16, 40, 256, 2), (1, 24, 24, 64, 384)])
+def test_conv3x3(B, H, W, Cin, Cout):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    a = torch.randn(B, H, W, Cin, device="cuda", generator=g).half()
+    rows = max(Cout, 16)
+    w = torch.zeros(9, rows, Cin, device="cuda", dtype=torch.float16)
+    w[:, :Cout] = (torch.randn(9, Cout, Cin, device="cuda", generator=g) * 0.1).half()
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda")
+    ops.conv_gemm(a, w, out, taps=9, n_total=Cout)
+    torch.cuda.synchronize()
+    ref = ref_conv(a, w[:, :Cout].contiguous(), 9)
+    assert rel(out, ref) < 2e-6, rel(out, ref)
+
+
+def test_fused_epilogue_and_skip_conv():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, H, W, C1, C2, N = 2, 16, 24, 128, 64, 128
+    a = torch.randn(B, H, W, C1, device="cuda", generator=g).half()
+    a2 = torch.randn(B, H, W, C2, device="cuda", generator=g).half()
+    w = (torch.randn(9, N, C1, device="cuda", generator=g) * 0.05).half()
+    w2 = (torch.randn(N, C2, device="cuda", generator=g) * 0.1).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    bias_b = torch.randn(B, N, device="cuda", generator=g)
+    resid = torch.randn(B, H, W, N, device="cuda", generator=g)
+    out = torch.empty(B, H, W, N, device="cuda")
+    stats = torch.zeros(B, N // 4, 2, device="cuda", dtype=torch.float64)
+    ops.conv_gemm(a, w, out, taps=9, n_total=N, a2=a2, w2=w2, bias=bias, bias_b=bias_b, resid=resid,
+                  scale=0.70710678, stats=stats)
+    torch.cuda.synchronize()
+    ref = ref_conv(a, w, 9) + ref_conv(a2, w2[None], 1) + bias + bias_b[:, None, None, :] + resid
+    ref = ref * 0.70710678
+    assert rel(out, ref) < 2e-6, rel(out, ref)
+    o = out.double().view(B, H * W, N // 4, 4)
+    s_ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
+    assert rel(stats, s_ref) < 1e-6, rel(stats, s_ref)
+
+
+def test_batched_b_fp16_out_strided():
+    """Attention-style: per-image B operand, fp16 output written into a column window of a wider buffer."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    B, M, K, N = 3, 300, 128, 200
+    qkv = torch.randn(B, 1, M, 3 * K, device="cuda", generator=g).half()
+    q = qkv[..., :K]
+    kmat = torch.randn(B, N, K, device="cuda", generator=g).half()
+    out = torch.zeros(B, 1, M, 512, device="cuda", dtype=torch.float16)
+    ops.conv_gemm(q, kmat, out, taps=1, n_total=N, b_batched=True, col_off=64, ldc=512, scale=0.125)
+    torch.cuda.synchronize()
+    ref = torch.einsum("bmk,bnk->bmn", q[:, 0].double(), kmat.double()) * 0.125
+    got = out[:, 0, :, 64:64 + N].double()
+    assert rel(got, ref) < 1e-3
+    assert out[..., :64].abs().max().item() == 0 and out[..., 64 + N:].abs().max().item() == 0
+
+
+def test_big_conv_speed():
+    """256->256 3x3 at the full 256x528 resolution (the single largest layer)."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, H, W, C = 4, 256, 528, 256
+    a = torch.randn(B, H, W, C, device="cuda", generator=g).half()
+    w = (torch.randn(9, C, C, device="cuda", generator=g) * 0.02).half()
+    out = torch.empty(B, H, W, C, device="cuda")
+    for _ in range(2):
+        ops.conv_gemm(a, w, out, taps=9, n_total=C)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    iters = 5
+    for _ in range(iters):
+        ops.conv_gemm(a, w, out, taps=9, n_total=C)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf = 2.0 * B * H * W * C * C * 9 / (ms * 1e-3) / 1e12
+    print(f"\n[conv 256->256 @256x528 B={B}] {ms:.3f} ms  {tf:.1f} TFLOP/s")
+    ref = ref_conv(a[:1, :64], w, 9)
+    # interior rows only (the reference slab was cut at row 64, so its last row sees a different halo)
+    assert rel(out[:1, :63], ref[:, :63]) < 2e-6
