@@ -45,7 +45,7 @@ def test_plain_gemm(M, K, N):
     ops.conv_gemm(a, w, out, taps=1, n_total=N)
     torch.cuda.synchronize()
     ref = ref_conv(a, w, 1)
-    assert rel(out, ref) < 2e-6, rel(out, ref)
+    assert rel(out, ref) < 1e-5, rel(out, ref)
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 64, 16), (2, 32, 66, 64, 128), (1, 64, 132, 128, 256),
@@ -61,7 +61,7 @@ def test_conv3x3(B, H, W, Cin, Cout):
     ops.conv_gemm(a, w, out, taps=9, n_total=Cout)
     torch.cuda.synchronize()
     ref = ref_conv(a, w[:, :Cout].contiguous(), 9)
-    assert rel(out, ref) < 2e-6, rel(out, ref)
+    assert rel(out, ref) < 1e-5, rel(out, ref)
 
 
 def test_fused_epilogue_and_skip_conv():
@@ -82,7 +82,7 @@ def test_fused_epilogue_and_skip_conv():
     torch.cuda.synchronize()
     ref = ref_conv(a, w, 9) + ref_conv(a2, w2[None], 1) + bias + bias_b[:, None, None, :] + resid
     ref = ref * 0.70710678
-    assert rel(out, ref) < 2e-6, rel(out, ref)
+    assert rel(out, ref) < 1e-5, rel(out, ref)
     o = out.double().view(B, H * W, N // 4, 4)
     s_ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
     assert rel(stats, s_ref) < 1e-6, rel(stats, s_ref)
@@ -128,4 +128,4 @@ def test_big_conv_speed():
     print(f"\n[conv 256->256 @256x528 B={B}] {ms:.3f} ms  {tf:.1f} TFLOP/s")
     ref = ref_conv(a[:1, :64], w, 9)
     # interior rows only (the reference slab was cut at row 64, so its last row sees a different halo)
-    assert rel(out[:1, :63], ref[:, :63]) < 2e-6
+    assert rel(out[:1, :63], ref[:, :63]) < 1e-5
