@@ -1,0 +1,153 @@
+"""Loader for the UNMODIFIED reference (sp-uhh/buddy) from /root/reference — build container only.
+
+Used by oracle/make_golden.py to generate the committed fixtures under tests/golden/ and by
+tests/test_oracle_vs_reference.py (skipped where /root/reference does not exist, e.g. on the GPU box).
+Nothing of the reference is copied: it is imported in place, with empty stand-in modules for the
+logging/WPE-only third-party imports it never calls on this path and the
+piecewise-linear stand-in for the absent `torchcde`.
+"""
+import os
+import sys
+import types
+
+import torch
+
+REF_ROOT = os.environ.get("BUDDY_REFERENCE_ROOT", "/root/reference")
+
+NCSNPP_CFG = dict(nonlinearity='swish', nf=128, ch_mult=[1, 2, 2, 2], num_res_blocks=1, attn_resolutions=[0],
+                  resamp_with_conv=True, time_conditional=True, fir=False, fir_kernel=[1, 3, 3, 1], skip_rescale=True,
+                  resblock_type='biggan', progressive='output_skip', progressive_input='input_skip',
+                  progressive_combine='sum', init_scale=0, fourier_scale=16, image_size=256, embedding_type='fourier',
+                  input_channels=2, spatial_channels=1, dropout=0, centered=True, discriminative=False)
+
+EQ_FREQS = [0, 125, 250, 375, 500, 625, 750, 875, 1000, 1250, 1500, 1750, 2000, 2250, 2500, 2750, 3000, 3500, 4000,
+            4500, 5000, 5500, 6000, 6500, 7000, 7500, 8000]
+
+
+class AD(dict):
+    """hydra DictConfig stand-in: attribute access, .get, .keys, AttributeError on miss."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "networks"))
+
+
+class _LinearInterpolation:
+    """Stand-in for torchcde.LinearInterpolation(coeffs, t).evaluate(q) (piecewise linear, no extrapolation clamp)."""
+
+    def __init__(self, coeffs, t):
+        self.c, self.t = coeffs, t
+
+    def evaluate(self, q):
+        t, c = self.t, self.c
+        k = torch.clamp(torch.bucketize(q, t) - 1, 0, len(t) - 2)
+        frac = ((q - t[k]) / (t[k + 1] - t[k]))
+        return c[..., k, :] + frac[..., None] * (c[..., k + 1, :] - c[..., k, :])
+
+
+def install():
+    """Put the reference on sys.path with the stand-in modules.  Idempotent."""
+    if not available():
+        raise RuntimeError(f"reference not found at {REF_ROOT}")
+    sys.dont_write_bytecode = True
+    for n in ["plotly", "plotly.express", "plotly.graph_objects", "soundfile", "matplotlib", "matplotlib.pyplot",
+              "nara_wpe", "nara_wpe.wpe", "nara_wpe.utils", "wandb"]:
+        if n not in sys.modules:
+            try:
+                __import__(n)
+            except Exception:
+                sys.modules[n] = types.ModuleType(n)
+    sys.modules["nara_wpe.wpe"].wpe = None
+    sys.modules["nara_wpe.utils"].stft = None
+    sys.modules["nara_wpe.utils"].istft = None
+    if "torchcde" not in sys.modules:
+        m = types.ModuleType("torchcde")
+        m.linear_interpolation_coeffs = lambda x, t=None: x
+        m.LinearInterpolation = _LinearInterpolation
+        sys.modules["torchcde"] = m
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+
+
+def build_network(state_dict=None):
+    install()
+    from networks.ncsnpp import NCSNppTime
+    net = NCSNppTime(stft=AD(n_fft=510, hop_length=128, center=True), **NCSNPP_CFG)
+    if state_dict is not None:
+        net.load_state_dict(state_dict)
+    return net.eval()
+
+
+def build_edm():
+    install()
+    from diff_params.edm import EDM
+    return EDM(type="ve_karras", sde_hp=AD(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10))
+
+
+def op_hp():
+    return AD(fix_EQ_extremes=True, NFFT=1024, win_length=512, hop=128, window="hann", Nf=100, EQ_freqs=EQ_FREQS,
+              init_single_value=True, init_params=AD(T60_breakpoints=[0.1], multiexp_weighting=[2]),
+              init_phases="random_coherent", minimum_phase=True, fix_direct_path=True, num_GL_iter=1,
+              cumulative_decays=False, decay_scale=1, Amin=0, Amax=40, T60min=0.1, T60max=2, clamp_A=True,
+              clamp_decay=True, strictly_decreasing_decay=False, enforce_long_decay_in_second_exponential=True,
+              n_iter_PR=5)
+
+
+def _loss(weight):
+    return AD(name="l2_comp_stft_summean", weight=weight, frequency_weighting="none", compression_factor=0.667,
+              multiple_compression_factors=False)
+
+
+def make_args(mode, T, audio_len=65536, warm="reverb_scaled"):
+    """Attribute-dict equivalent of conf/tester/{informed_dereverberation_DPS,blind_dereverberation_BUDDy}.yaml."""
+    sde = AD(sigma_data=0.05, sigma_min=1e-4, sigma_max=0.5, rho=10)
+    if mode == "informed":
+        sp = AD(same_as_training=False, sde_hp=sde, Schurn=10, Snoise=1, Stmin=0, Stmax=10, order=2, T=T, schedule="edm")
+        ps = AD(zeta=2.75, rec_loss=_loss(512), normalization_type="grad_norm",
+                warm_initialization=AD(mode=warm, scaling_factor=0.05), constraint_speech_magnitude=AD(use=False))
+    elif mode == "blind":
+        sp = AD(same_as_training=False, sde_hp=sde, Schurn=50, Snoise=1, Stmin=0, Stmax=10, order=1, T=T, schedule="edm")
+        ps = AD(zeta=0.5, rec_loss=_loss(512), rec_loss_params=_loss(512),
+                RIR_noise_regularization=AD(use=True, crop_sigma_max=0.01, crop_sigma_min=5e-4, loss=_loss(2560)),
+                project_parameters=True, normalization_type="grad_norm",
+                blind_hp=AD(optimizer="adam", lr_op=0.1, beta1=0.9, beta2=0.99, noise=0.1, lr_op_phase=1,
+                            weight_decay=0, op_updates_per_step=10, grad_clip=1),
+                warm_initialization=AD(mode=warm, scaling_factor=0.05),
+                constraint_speech_magnitude=AD(use=True, speech_scaling=0.05))
+    elif mode == "unconditional":
+        sp = AD(same_as_training=False, sde_hp=sde, Schurn=10, Snoise=1, Stmin=0, Stmax=10, order=2, T=T, schedule="edm")
+        ps = AD()
+    else:
+        raise ValueError(mode)
+    return AD(exp=AD(audio_len=audio_len, sample_rate=16000),
+              tester=AD(sampling_params=sp, posterior_sampling=ps, informed_dereverberation=AD(op_hp=op_hp())))
+
+
+class injected_noise:
+    """Context manager: make torch.randn / randn_like return pre-drawn tensors in call order, so that the
+    reference sampler and the restatement / CUDA path consume IDENTICAL noise."""
+
+    def __init__(self, draws):
+        self.draws = list(draws)
+        self.i = 0
+
+    def _next(self, shape):
+        t = self.draws[self.i]
+        self.i += 1
+        assert tuple(t.shape) == tuple(shape), (t.shape, shape)
+        return t.clone()
+
+    def __enter__(self):
+        self._randn, self._randn_like = torch.randn, torch.randn_like
+        torch.randn = lambda *s, **kw: self._next(s[0] if len(s) == 1 and not isinstance(s[0], int) else s)
+        torch.randn_like = lambda x, **kw: self._next(x.shape)
+        return self
+
+    def __exit__(self, *a):
+        torch.randn, torch.randn_like = self._randn, self._randn_like

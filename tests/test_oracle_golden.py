@@ -1,0 +1,120 @@
+"""Pins the oracle (oracle/, a PyTorch restatement) to fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py, run in the build container).  CPU only."""
+import os
+
+import pytest
+import torch
+
+from oracle import net as onet
+from oracle import operators as oop
+from oracle import sampler as osm
+from oracle.weights import make_state_dict, param_spec
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gold(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def randn(seed, *shape):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.fixture(scope="module")
+def sd():
+    torch.set_num_threads(os.cpu_count())
+    return make_state_dict(0)
+
+
+def test_state_dict_contract():
+    g = gold("state_dict_spec.pt")
+    assert [(k, tuple(s)) for k, s in g["keys"]] == param_spec()
+
+
+def test_net_stft_istft():
+    g = gold("net_stft.pt")
+    x = randn(g["seed"], *g["shape"])
+    spec = onet.net_stft(x)
+    assert spec.shape == g["spec"].shape == (1, 1, 256, 32)
+    assert rel(torch.view_as_real(spec), torch.view_as_real(g["spec"])) < 1e-6
+    assert rel(onet.net_istft(spec, 3000), g["istft"]) < 1e-6
+    assert g["spec_full_frames"] == 528
+
+
+def test_network_forward_and_vjp(sd):
+    g = gold("net_small.pt")
+    x = (randn(g["x_seed"], 2, 1, 8192) * g["x_scale"]).requires_grad_(True)
+    cot = randn(g["cot_seed"], 2, 1, 8192)
+    out = onet.ncsnpp_time_forward(sd, x, 0.25 * torch.log(g["sigma"]))
+    (vjp,) = torch.autograd.grad((out * cot).sum(), x)
+    assert rel(out.detach(), g["out"]) < 1e-5
+    assert rel(vjp, g["vjp"]) < 1e-5
+
+
+def test_edm_denoiser(sd):
+    g = gold("edm_denoiser.pt")
+    x = randn(g["x_seed"], 1, 8192) * g["x_scale"]
+    with torch.no_grad():
+        out = osm.denoise(sd, x, g["sigma"])
+    assert rel(out, g["out"]) < 1e-5
+
+
+def test_schedule_gamma():
+    g = gold("schedule.pt")
+    for key, schurn in (("informed_35", 10), ("blind_60", 50), ("informed_3", 10), ("blind_2", 50)):
+        T = int(key.split("_")[1])
+        t = osm.create_schedule(T)
+        assert torch.equal(t, g[key]["t"]), key
+        assert torch.equal(osm.get_gamma(t, schurn), g[key]["gamma"]), key
+
+
+def test_operators_and_loss():
+    g = gold("operators.pt")
+    s, h, y = g["s"], g["h"], g["y"]
+    assert rel(oop.fast_apply_rir(s[None], h), y) < 1e-6
+    assert rel(torch.view_as_real(oop.loss_stft(s[None])), torch.view_as_real(g["loss_stft"])) < 1e-6
+    xh = (s + 0.01 * randn(g["pert_seed"], g["n"]))[None].requires_grad_(True)
+    l = oop.comp_loss(y, oop.fast_apply_rir(xh, h), 512.0).sum()
+    (gr,) = torch.autograd.grad(l, xh)
+    assert abs(l.item() - g["loss"].item()) / abs(g["loss"].item()) < 1e-5
+    assert rel(gr, g["loss_grad"]) < 1e-4
+
+
+def test_blind_operator_chain():
+    g = gold("operators.pt")
+    A = oop.design_magnitude(g["blind_decays"], g["blind_weights"])
+    assert rel(A, g["blind_A"]) < 1e-5
+    H = oop.design_H(g["blind_decays"], g["blind_weights"], g["blind_phases"])
+    assert rel(torch.view_as_real(H), torch.view_as_real(g["blind_H"])) < 1e-4
+    assert rel(torch.angle(g["blind_H_init"]), g["blind_phases"]) < 1e-6
+    assert rel(oop.blind_degradation(g["s"][None], g["blind_H"]), g["blind_y"]) < 1e-5
+    assert rel(oop.time_rir(g["blind_H"]), g["blind_rir"]) < 1e-5
+    hin = randn(g["minphase_in_seed"], 640) * torch.exp(-torch.arange(640) / 80.0)
+    assert rel(oop.minimum_phase(hin), g["minphase"]) < 1e-5
+
+
+def test_audio_known_answer():
+    """The reference's only known-answer data: reverberant == gain * (clean (*) rir)."""
+    g = gold("audio_kat_p226.pt")
+    y = oop.fast_apply_rir(g["clean"][None], g["rir"])[0]
+    gain = (y @ g["reverberant"]) / (y @ y)
+    assert rel(gain * y, g["reverberant"]) < 1e-5
+
+
+def test_unconditional_sampler(sd):
+    g = gold("sampler_uncond_T3.pt")
+    noise = [randn(g["noise_seed0"] + i, 1, g["n"]) for i in range(g["T"] + 1)]
+    x = osm.euler_heun(sd, (1, g["n"]), g["T"], noise)
+    assert rel(x, g["x"]) < 1e-4
+
+
+def test_informed_dps_sampler(sd):
+    g = gold("sampler_informed_T3.pt")
+    noise = [randn(g["noise_seed0"] + i, 1, g["n"]) for i in range(g["T"] + 1)]
+    pred = osm.dps_informed(sd, g["y"], g["h"], g["T"], noise)
+    assert rel(pred, g["pred"]) < 1e-3
