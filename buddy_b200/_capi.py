@@ -74,3 +74,25 @@ def launch_count():
 
 def reset_launch_count():
     lib().buddy_reset_launch_count()
+
+
+c_double_p = ctypes.c_void_p
+
+
+class GnDesc(ctypes.Structure):
+    """Mirror of `buddy_gn_desc`."""
+    _fields_ = [
+        ("xa", c_void_p), ("xb", c_void_p), ("Ca", c_int), ("Cb", c_int),
+        ("stats_a", c_void_p), ("stats_b", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+        ("batch", c_int), ("H", c_int), ("W", c_int), ("groups", c_int), ("eps", c_float),
+        ("silu", c_int), ("mode", c_int), ("out", c_void_p), ("out_raw", c_void_p),
+    ]
+
+
+class GnBwdDesc(ctypes.Structure):
+    """Mirror of `buddy_gn_bwd_desc`."""
+    _fields_ = [
+        ("da", c_void_p), ("dskip", c_void_p), ("skip_scale", c_float),
+        ("extra_a", c_void_p), ("extra_b", c_void_p), ("gsum", c_void_p),
+        ("dxa", c_void_p), ("dxb", c_void_p), ("g16a", c_void_p), ("g16b", c_void_p), ("g16_scale", c_float),
+    ]

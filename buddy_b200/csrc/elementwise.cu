@@ -1,0 +1,779 @@
+// HBM-bound glue kernels of the score network (channels-last fp32 activations, fp16 tensor-core operands):
+//   GroupNorm statistics / apply(+SiLU)(+nearest-x2 | 2x2-mean resample)(+virtual channel concat) and their
+//   data-gradients, 2-channel im2col / col2im for the thin convolutions, input/output pyramid helpers,
+//   softmax forward/backward and fp16 transposes for the bottleneck attention.
+// Reference semantics: nn.GroupNorm(eps=1e-6) + SiLU (networks/ncsnpp_utils/layerspp.py:219-263),
+// naive_up/downsample_2d (up_or_down_sampling.py:59-69), Combine (layerspp.py:52-59),
+// AttnBlockpp softmax (layerspp.py:81-85), pyramid up/down (layerspp.py:117,156).
+// All 128-bit loads/stores; one CTA never crosses an image (grid.y = batch index).
+#include <atomic>
+
+#include "../../include/buddy_b200.h"
+#include "common.cuh"
+
+namespace buddy {
+extern std::atomic<long long> g_launches;
+
+#define LAUNCH_END(name)                                  \
+  g_launches.fetch_add(1, std::memory_order_relaxed);     \
+  BUDDY_CHECK_LAUNCH(name);                               \
+  return 0;
+
+__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+__device__ __forceinline__ float dsilu_f(float z) {
+  const float s = 1.f / (1.f + __expf(-z));
+  return s * (1.f + z * (1.f - s));
+}
+
+struct GnSrc {
+  const float* xa;
+  const float* xb;
+  int Ca, Cb;
+  const double* sa;  // bundle sums [B][Ca/4][2]
+  const double* sb;  // bundle sums [B][Cb/4][2]
+};
+
+// per-group mean / rstd of image b from the per-4-channel-bundle (sum, sumsq) accumulators
+__device__ __forceinline__ void group_stats_to_smem(float* s_mean, float* s_rstd, const GnSrc& s, int b, int G,
+                                                     int cpg, double n, float eps) {
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double S = 0.0, Q = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; c += 4) {
+      const double* p = (c < s.Ca) ? s.sa + (static_cast<long long>(b) * (s.Ca >> 2) + (c >> 2)) * 2
+                                   : s.sb + (static_cast<long long>(b) * (s.Cb >> 2) + ((c - s.Ca) >> 2)) * 2;
+      S += p[0];
+      Q += p[1];
+    }
+    const double m = S / n;
+    double var = Q / n - m * m;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = static_cast<float>(m);
+    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
+__device__ __forceinline__ void load8(const GnSrc& s, long long pix, int c, float (&v)[8]) {
+  const float* p = (c < s.Ca) ? s.xa + pix * s.Ca + c : s.xb + pix * s.Cb + (c - s.Ca);
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8h(__half* p, const float (&v)[8]) {
+  __half2 h0 = __floats2half2_rn(v[0], v[1]);
+  __half2 h1 = __floats2half2_rn(v[2], v[3]);
+  __half2 h2 = __floats2half2_rn(v[4], v[5]);
+  __half2 h3 = __floats2half2_rn(v[6], v[7]);
+  uint4 q;
+  q.x = *reinterpret_cast<uint32_t*>(&h0);
+  q.y = *reinterpret_cast<uint32_t*>(&h1);
+  q.z = *reinterpret_cast<uint32_t*>(&h2);
+  q.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm bundle statistics of a plain fp32 [B][P][C] tensor (for tensors no conv epilogue produced)
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const float* __restrict__ x, long long P, int C, double* __restrict__ stats) {
+  const int b = blockIdx.y;
+  const int nb = C >> 2;  // bundles per pixel; blockDim.x is a multiple of nb
+  const int bundle = threadIdx.x % nb;
+  const long long ppb = blockDim.x / nb;  // pixels per block-iteration
+  float s = 0.f, q = 0.f;
+  const float* xb = x + static_cast<long long>(b) * P * C;
+  for (long long pix = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / nb; pix < P;
+       pix += static_cast<long long>(gridDim.x) * ppb) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + pix * C) + bundle);
+    s += v.x + v.y + v.z + v.w;
+    q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  extern __shared__ float sm[];  // [blockDim][2]
+  sm[threadIdx.x * 2] = s;
+  sm[threadIdx.x * 2 + 1] = q;
+  __syncthreads();
+  if (threadIdx.x < nb) {
+    double S = 0.0, Q = 0.0;
+    for (int t = threadIdx.x; t < blockDim.x; t += nb) {
+      S += sm[t * 2];
+      Q += sm[t * 2 + 1];
+    }
+    double* o = stats + (static_cast<long long>(b) * nb + bundle) * 2;
+    atomicAdd(o, S);
+    atomicAdd(o + 1, Q);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm apply (+SiLU) (+resample) -> fp16 operand; optional raw fp16 copy of x for the 1x1 skip conv
+// ------------------------------------------------------------------------------------------------
+struct GnApplyArgs {
+  GnSrc s;
+  const float* gamma;
+  const float* beta;
+  int H, W;  // resolution of x
+  int G, cpg;
+  float eps;
+  int silu;
+  int mode;  // 0 none, 1 nearest x2 up, 2 2x2-mean down
+  __half* out;
+  __half* out_raw;
+};
+
+__device__ __forceinline__ void gn_act8(const float (&x)[8], int c, const float* s_mean, const float* s_rstd,
+                                        const float* gamma, const float* beta, int cpg, int silu, float (&y)[8]) {
+  float g[8], be[8];
+  load8(gamma + c, g);
+  load8(beta + c, be);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int grp = (c + j) / cpg;
+    const float z = (x[j] - s_mean[grp]) * s_rstd[grp] * g[j] + be[j];
+    y[j] = silu ? silu_f(z) : z;
+  }
+}
+
+__global__ void gn_apply_kernel(const GnApplyArgs a) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int b = blockIdx.y;
+  const int C = a.s.Ca + a.s.Cb;
+  group_stats_to_smem(s_mean, s_rstd, a.s, b, a.G, a.cpg, static_cast<double>(a.cpg) * a.H * a.W, a.eps);
+  __syncthreads();
+  const int c8n = C >> 3;
+  const int Ho = (a.mode == 1) ? a.H * 2 : (a.mode == 2 ? a.H / 2 : a.H);
+  const int Wo = (a.mode == 1) ? a.W * 2 : (a.mode == 2 ? a.W / 2 : a.W);
+  const long long Pwork = (a.mode == 2) ? static_cast<long long>(Ho) * Wo : static_cast<long long>(a.H) * a.W;
+  const long long items = Pwork * c8n;
+  const long long in_img = static_cast<long long>(b) * a.H * a.W;
+  const long long out_img = static_cast<long long>(b) * Ho * Wo;
+  for (long long it = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; it < items;
+       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = it / c8n;
+    const int c = static_cast<int>(it - p * c8n) * 8;
+    float x[8], y[8];
+    if (a.mode == 0) {
+      load8(a.s, in_img + p, c, x);
+      gn_act8(x, c, s_mean, s_rstd, a.gamma, a.beta, a.cpg, a.silu, y);
+      store8h(a.out + (out_img + p) * C + c, y);
+      if (a.out_raw) store8h(a.out_raw + (out_img + p) * C + c, x);
+    } else if (a.mode == 1) {
+      const int h = static_cast<int>(p / a.W), w = static_cast<int>(p - static_cast<long long>(h) * a.W);
+      load8(a.s, in_img + p, c, x);
+      gn_act8(x, c, s_mean, s_rstd, a.gamma, a.beta, a.cpg, a.silu, y);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const long long po = out_img + static_cast<long long>(2 * h + (d >> 1)) * Wo + (2 * w + (d & 1));
+        store8h(a.out + po * C + c, y);
+        if (a.out_raw) store8h(a.out_raw + po * C + c, x);
+      }
+    } else {
+      const int ho = static_cast<int>(p / Wo), wo = static_cast<int>(p - static_cast<long long>(ho) * Wo);
+      float ya[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const long long pi = in_img + static_cast<long long>(2 * ho + (d >> 1)) * a.W + (2 * wo + (d & 1));
+        load8(a.s, pi, c, x);
+        gn_act8(x, c, s_mean, s_rstd, a.gamma, a.beta, a.cpg, a.silu, y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          ya[j] += y[j];
+          xa[j] += x[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ya[j] *= 0.25f;
+        xa[j] *= 0.25f;
+      }
+      store8h(a.out + (out_img + p) * C + c, ya);
+      if (a.out_raw) store8h(a.out_raw + (out_img + p) * C + c, xa);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm(+SiLU)(+resample) backward w.r.t. the input.
+//   da : fp32 gradient w.r.t. the activation output, at the conv's resolution, C = Ca + Cb channels
+//   pass 1 (gn_bwd_stats): per (image, group) S1 = sum dxh, S2 = sum dxh*xh   (dxh = dz*gamma)
+//   pass 2 (gn_bwd)      : dx = rstd*(dxh - S1/n - xh*S2/n) + R^T(dskip)*skip_scale + extra
+// ------------------------------------------------------------------------------------------------
+struct GnBwdArgs {
+  GnSrc s;
+  const float* gamma;
+  const float* beta;
+  int H, W;  // resolution of x
+  int G, cpg;
+  float eps;
+  int silu;
+  int mode;
+  const float* da;     // [B][Hc][Wc][C]
+  const float* dskip;  // [B][Hc][Wc][C] or null
+  float skip_scale;
+  const float* extra_a;  // [B][H][W][Ca] or null
+  const float* extra_b;  // [B][H][W][Cb] or null
+  double* gsum;          // [B][G][2]
+  float* dxa;            // [B][H][W][Ca] or null
+  float* dxb;            // [B][H][W][Cb] or null
+  __half* g16a;          // fp16(dx * g16_scale) or null
+  __half* g16b;
+  float g16_scale;
+};
+
+// gradient w.r.t. the activation output pulled back through the resample, for x-pixel (h,w), channels c..c+8
+__device__ __forceinline__ void pull_back8(const float* t, int mode, int b, int h, int w, int H, int W, int C, int c,
+                                           float (&g)[8]) {
+  if (mode == 0) {
+    load8(t + ((static_cast<long long>(b) * H + h) * W + w) * C + c, g);
+  } else if (mode == 1) {  // forward was nearest x2: sum the 4 children
+    const int Wc = 2 * W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      load8(t + ((static_cast<long long>(b) * 2 * H + 2 * h + (d >> 1)) * Wc + 2 * w + (d & 1)) * C + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += v[j];
+    }
+  } else {  // forward was 2x2 mean: a quarter of the parent
+    const int Hc = H / 2, Wc = W / 2;
+    load8(t + ((static_cast<long long>(b) * Hc + (h >> 1)) * Wc + (w >> 1)) * C + c, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
+  }
+}
+
+template <bool kPass2>
+__global__ void gn_bwd_kernel(const GnBwdArgs a) {
+  __shared__ float s_mean[64], s_rstd[64], s_m1[64], s_m2[64];
+  __shared__ float s_acc[64][2];
+  const int b = blockIdx.y;
+  const int C = a.s.Ca + a.s.Cb;
+  const double n = static_cast<double>(a.cpg) * a.H * a.W;
+  group_stats_to_smem(s_mean, s_rstd, a.s, b, a.G, a.cpg, n, a.eps);
+  if (kPass2) {
+    for (int g = threadIdx.x; g < a.G; g += blockDim.x) {
+      s_m1[g] = static_cast<float>(a.gsum[(static_cast<long long>(b) * a.G + g) * 2] / n);
+      s_m2[g] = static_cast<float>(a.gsum[(static_cast<long long>(b) * a.G + g) * 2 + 1] / n);
+    }
+  } else {
+    for (int g = threadIdx.x; g < a.G; g += blockDim.x) s_acc[g][0] = s_acc[g][1] = 0.f;
+  }
+  __syncthreads();
+  const int c8n = C >> 3;  // blockDim.x is a multiple of c8n -> each thread keeps one channel chunk
+  const int c = (threadIdx.x % c8n) * 8;
+  const long long P = static_cast<long long>(a.H) * a.W;
+  const long long ppb = blockDim.x / c8n;
+  float gam[8], bet[8];
+  load8(a.gamma + c, gam);
+  load8(a.beta + c, bet);
+  float p1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, p2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / c8n; p < P;
+       p += static_cast<long long>(gridDim.x) * ppb) {
+    const int h = static_cast<int>(p / a.W), w = static_cast<int>(p - static_cast<long long>(h) * a.W);
+    float x[8], g[8];
+    load8(a.s, static_cast<long long>(b) * P + p, c, x);
+    pull_back8(a.da, a.mode, b, h, w, a.H, a.W, C, c, g);
+    float dxh[8], xh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int grp = (c + j) / a.cpg;
+      xh[j] = (x[j] - s_mean[grp]) * s_rstd[grp];
+      float dz = g[j];
+      if (a.silu) dz *= dsilu_f(xh[j] * gam[j] + bet[j]);
+      dxh[j] = dz * gam[j];
+    }
+    if (!kPass2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        p1[j] += dxh[j];
+        p2[j] += dxh[j] * xh[j];
+      }
+    } else {
+      float dx[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int grp = (c + j) / a.cpg;
+        dx[j] = s_rstd[grp] * (dxh[j] - s_m1[grp] - xh[j] * s_m2[grp]);
+      }
+      if (a.dskip) {
+        float sk[8];
+        pull_back8(a.dskip, a.mode, b, h, w, a.H, a.W, C, c, sk);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dx[j] += sk[j] * a.skip_scale;
+      }
+      const bool in_a = c < a.s.Ca;
+      const int cl = in_a ? c : c - a.s.Ca;
+      const int Cl = in_a ? a.s.Ca : a.s.Cb;
+      const long long off = (static_cast<long long>(b) * P + p) * Cl + cl;
+      const float* ex = in_a ? a.extra_a : a.extra_b;
+      if (ex) {
+        float e[8];
+        load8(ex + off, e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dx[j] += e[j];
+      }
+      float* o32 = in_a ? a.dxa : a.dxb;
+      if (o32) store8(o32 + off, dx);
+      __half* o16 = in_a ? a.g16a : a.g16b;
+      if (o16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dx[j] *= a.g16_scale;
+        store8h(o16 + off, dx);
+      }
+    }
+  }
+  if (!kPass2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int grp = (c + j) / a.cpg;
+      atomicAdd(&s_acc[grp][0], p1[j]);
+      atomicAdd(&s_acc[grp][1], p2[j]);
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < a.G; g += blockDim.x) {
+      atomicAdd(a.gsum + (static_cast<long long>(b) * a.G + g) * 2, static_cast<double>(s_acc[g][0]));
+      atomicAdd(a.gsum + (static_cast<long long>(b) * a.G + g) * 2 + 1, static_cast<double>(s_acc[g][1]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2-channel 3x3 im2col -> fp16 [B][H][W][64] (K index = tap*2 + ci, 18 used, rest zero); and its adjoint
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col_c2_kernel(const float* __restrict__ x, int B, int H, int W, __half* __restrict__ col) {
+  const long long P = static_cast<long long>(B) * H * W;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < P * 8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i >> 3;
+    const int chunk = static_cast<int>(i & 7);  // 8 fp16 = 4 taps x 2 channels
+    const int w = static_cast<int>(p % W);
+    const int h = static_cast<int>((p / W) % H);
+    const long long b = p / (static_cast<long long>(W) * H);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tap = chunk * 4 + j;
+      float v0 = 0.f, v1 = 0.f;
+      if (tap < 9) {
+        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+          const float2 q = __ldg(reinterpret_cast<const float2*>(x) + (b * H + hh) * W + ww);
+          v0 = q.x;
+          v1 = q.y;
+        }
+      }
+      v[2 * j] = v0;
+      v[2 * j + 1] = v1;
+    }
+    store8h(col + p * 64 + chunk * 8, v);
+  }
+}
+
+// dx[b,h,w,ci] (+)= sum_tap dcol[b, h-dy, w-dx, tap*2+ci]   (dcol fp32, row stride ld)
+__global__ void col2im_c2_kernel(const float* __restrict__ dcol, int ld, int B, int H, int W, float* __restrict__ dx,
+                                 int accumulate) {
+  const long long P = static_cast<long long>(B) * H * W;
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(p % W);
+    const int h = static_cast<int>((p / W) % H);
+    const long long b = p / (static_cast<long long>(W) * H);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h - (tap / 3 - 1), ww = w - (tap % 3 - 1);
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+        const float2 q = __ldg(reinterpret_cast<const float2*>(dcol + ((b * H + hh) * W + ww) * ld + tap * 2));
+        a0 += q.x;
+        a1 += q.y;
+      }
+    }
+    float2* o = reinterpret_cast<float2*>(dx) + p;
+    if (accumulate) {
+      const float2 old = *o;
+      a0 += old.x;
+      a1 += old.y;
+    }
+    *o = make_float2(a0, a1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2-channel helpers: 2x2 mean pool (input pyramid), nearest x2 (+add) (output pyramid) and adjoints
+// ------------------------------------------------------------------------------------------------
+// mode 0: out[Ho=H/2] = mean4(in)            mode 1: out[2H] = nearest(in) (+ add)
+// mode 2: out[2H] (+)= in[parent]/4 (adjoint of mode 0)   mode 3: out[H/2] = sum4(in) (adjoint of mode 1)
+__global__ void resample_c2_kernel(const float2* __restrict__ in, int B, int Hin, int Win, int mode,
+                                   const float2* __restrict__ add, float2* __restrict__ out, int accumulate) {
+  const bool shrink = (mode == 0 || mode == 3);
+  const int Ho = shrink ? Hin / 2 : Hin * 2, Wo = shrink ? Win / 2 : Win * 2;
+  const long long P = static_cast<long long>(B) * Ho * Wo;
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(p % Wo);
+    const int h = static_cast<int>((p / Wo) % Ho);
+    const long long b = p / (static_cast<long long>(Wo) * Ho);
+    float2 r;
+    if (shrink) {
+      float sx = 0.f, sy = 0.f;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const float2 q = __ldg(in + (b * Hin + 2 * h + (d >> 1)) * Win + 2 * w + (d & 1));
+        sx += q.x;
+        sy += q.y;
+      }
+      const float sc = (mode == 0) ? 0.25f : 1.f;
+      r = make_float2(sx * sc, sy * sc);
+    } else {
+      const float2 q = __ldg(in + (b * Hin + (h >> 1)) * Win + (w >> 1));
+      const float sc = (mode == 2) ? 0.25f : 1.f;
+      r = make_float2(q.x * sc, q.y * sc);
+    }
+    if (add) {
+      const float2 q = __ldg(add + p);
+      r.x += q.x;
+      r.y += q.y;
+    }
+    if (accumulate) {
+      r.x += out[p].x;
+      r.y += out[p].y;
+    }
+    out[p] = r;
+  }
+}
+
+// Combine (layerspp.py:52-59, method 'sum'): out[p][c] = h[p][c] + w[c][0]*pyr[p][0] + w[c][1]*pyr[p][1] + bias[c]
+__global__ void combine_fwd_kernel(const float* __restrict__ h, const float2* __restrict__ pyr,
+                                   const float* __restrict__ w, const float* __restrict__ bias, long long P, int C,
+                                   float* __restrict__ out) {
+  const int c4n = C >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < P * c4n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / c4n;
+    const int c = static_cast<int>(i - p * c4n) * 4;
+    const float2 q = __ldg(pyr + p);
+    float4 v = __ldg(reinterpret_cast<const float4*>(h + p * C + c));
+    const float4 w01 = __ldg(reinterpret_cast<const float4*>(w + 2 * c));      // w[c][0], w[c][1], w[c+1][0], ...
+    const float4 w23 = __ldg(reinterpret_cast<const float4*>(w + 2 * c + 4));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+    v.x += w01.x * q.x + w01.y * q.y + bb.x;
+    v.y += w01.z * q.x + w01.w * q.y + bb.y;
+    v.z += w23.x * q.x + w23.y * q.y + bb.z;
+    v.w += w23.z * q.x + w23.w * q.y + bb.w;
+    *reinterpret_cast<float4*>(out + p * C + c) = v;
+  }
+}
+// adjoint w.r.t. the pyramid input: dpyr[p][i] = sum_c dout[p][c] * w[c][i]    (one warp per pixel)
+__global__ void combine_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ w, long long P, int C,
+                                   float2* __restrict__ dpyr) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long p = warp; p < P; p += nwarps) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(dout + p * C + c));
+      const float4 w01 = __ldg(reinterpret_cast<const float4*>(w + 2 * c));
+      const float4 w23 = __ldg(reinterpret_cast<const float4*>(w + 2 * c + 4));
+      a0 += v.x * w01.x + v.y * w01.z + v.z * w23.x + v.w * w23.z;
+      a1 += v.x * w01.y + v.y * w01.w + v.z * w23.y + v.w * w23.w;
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) dpyr[p] = make_float2(a0, a1);
+  }
+}
+
+// y[p][:] = M (2x2) x[p][:] + bias   on 2-channel pixels (output_layer 1x1 conv, ncsnpp.py:113,445; and its adjoint)
+__global__ void affine_c2_kernel(const float2* __restrict__ x, long long P, float m00, float m01, float m10, float m11,
+                                 float b0, float b1, float2* __restrict__ y) {
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float2 q = __ldg(x + p);
+    y[p] = make_float2(m00 * q.x + m01 * q.y + b0, m10 * q.x + m11 * q.y + b1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention helpers
+// ------------------------------------------------------------------------------------------------
+// row softmax: logits fp32 [rows][n] -> P fp16 [rows][ldp]   (one block per row)
+__global__ void softmax_fwd_kernel(const float* __restrict__ s, int n, __half* __restrict__ p, int ldp) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const float* sr = s + row * n;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, sr[i]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
+    v = warp_max(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  m = red[0];
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += expf(sr[i] - m);
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  const float inv = 1.f / red[0];
+  __half* pr = p + row * ldp;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) pr[i] = __float2half_rn(expf(sr[i] - m) * inv);
+}
+// dS = P * (dP - sum_j dP*P) * scale   -> fp16 [rows][ld]
+__global__ void softmax_bwd_kernel(const __half* __restrict__ p, int ldp, const float* __restrict__ dp, int n,
+                                   float scale, __half* __restrict__ ds, int ldds) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const __half* pr = p + row * ldp;
+  const float* dr = dp + row * n;
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dot += __half2float(pr[i]) * dr[i];
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  dot = red[0];
+  __half* o = ds + row * ldds;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    o[i] = __float2half_rn(__half2float(pr[i]) * (dr[i] - dot) * scale);
+}
+// batched fp16 transpose: in [batch][R][ld_in] (first Cc columns) -> out [batch][Cc][ld_out] (first R columns)
+__global__ void transpose_h_kernel(const __half* __restrict__ in, int R, int Cc, long long ld_in, long long bs_in,
+                                   __half* __restrict__ out, long long ld_out, long long bs_out) {
+  __shared__ __half tile[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const __half* ip = in + b * bs_in;
+  __half* op = out + b * bs_out;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? ip[r * ld_in + c] : __float2half(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < Cc && r < R) op[c * ld_out + r] = tile[threadIdx.x][i];
+  }
+}
+// fp32 -> fp16 with scale (contiguous)
+__global__ void cast_scale_h_kernel(const float* __restrict__ x, long long n8, float scale, __half* __restrict__ y) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v[8];
+    load8(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= scale;
+    store8h(y + i * 8, v);
+  }
+}
+
+static int grid_for(long long items, int threads, int max_blocks = 148 * 16) {
+  long long g = (items + threads - 1) / threads;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace buddy
+
+using namespace buddy;
+
+#define STREAM static_cast<cudaStream_t>(stream)
+
+extern "C" int buddy_gn_stats(const float* x, int B, int64_t P, int C, double* stats, void* stream) {
+  if (C % 4 || C <= 0 || C > 1024) {
+    set_last_error("buddy_gn_stats: C must be a multiple of 4 (got %d)", C);
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  const int nb = C / 4;
+  int threads = nb * (256 / nb > 0 ? 256 / nb : 1);
+  if (threads > 1024) {
+    set_last_error("buddy_gn_stats: C too large");
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  const long long ppb = threads / nb;
+  long long gx = (P + ppb * 8 - 1) / (ppb * 8);
+  if (gx > 148 * 8) gx = 148 * 8;
+  if (gx < 1) gx = 1;
+  gn_stats_kernel<<<dim3((unsigned)gx, B), threads, threads * 2 * sizeof(float), STREAM>>>(x, P, C, stats);
+  LAUNCH_END("gn_stats_kernel");
+}
+
+static int check_gn(int Ca, int Cb, int G, const char* who) {
+  const int C = Ca + Cb;
+  if (Ca % 8 || Cb % 8 || C <= 0 || G <= 0 || G > 64 || C % G || (C / G) % 4) {
+    set_last_error("%s: unsupported channel/group configuration Ca=%d Cb=%d G=%d", who, Ca, Cb, G);
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  return 0;
+}
+
+extern "C" int buddy_gn_apply(const buddy_gn_desc* d, void* stream) {
+  int e = check_gn(d->Ca, d->Cb, d->groups, "buddy_gn_apply");
+  if (e) return e;
+  if (d->mode == 2 && ((d->H & 1) || (d->W & 1))) {
+    set_last_error("buddy_gn_apply: 2x2-mean needs even H, W");
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  GnApplyArgs a;
+  a.s = {d->xa, d->xb, d->Ca, d->Cb, d->stats_a, d->stats_b};
+  a.gamma = d->gamma;
+  a.beta = d->beta;
+  a.H = d->H;
+  a.W = d->W;
+  a.G = d->groups;
+  a.cpg = (d->Ca + d->Cb) / d->groups;
+  a.eps = d->eps;
+  a.silu = d->silu;
+  a.mode = d->mode;
+  a.out = static_cast<__half*>(d->out);
+  a.out_raw = static_cast<__half*>(d->out_raw);
+  const long long items = static_cast<long long>(d->mode == 2 ? (d->H / 2) * (d->W / 2) : d->H * d->W) *
+                          ((d->Ca + d->Cb) / 8);
+  gn_apply_kernel<<<dim3(grid_for(items, 256, 148 * 8), d->batch), 256, 0, STREAM>>>(a);
+  LAUNCH_END("gn_apply_kernel");
+}
+
+extern "C" int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, void* stream) {
+  int e = check_gn(d->Ca, d->Cb, d->groups, "buddy_gn_bwd");
+  if (e) return e;
+  const int C = d->Ca + d->Cb;
+  GnBwdArgs a;
+  a.s = {d->xa, d->xb, d->Ca, d->Cb, d->stats_a, d->stats_b};
+  a.gamma = d->gamma;
+  a.beta = d->beta;
+  a.H = d->H;
+  a.W = d->W;
+  a.G = d->groups;
+  a.cpg = C / d->groups;
+  a.eps = d->eps;
+  a.silu = d->silu;
+  a.mode = d->mode;
+  a.da = g->da;
+  a.dskip = g->dskip;
+  a.skip_scale = g->skip_scale;
+  a.extra_a = g->extra_a;
+  a.extra_b = g->extra_b;
+  a.gsum = g->gsum;
+  a.dxa = g->dxa;
+  a.dxb = g->dxb;
+  a.g16a = static_cast<__half*>(g->g16a);
+  a.g16b = static_cast<__half*>(g->g16b);
+  a.g16_scale = g->g16_scale;
+  const int c8n = C / 8;
+  const int threads = c8n * (256 / c8n > 0 ? 256 / c8n : 1);
+  const long long ppb = threads / c8n;
+  const long long P = static_cast<long long>(d->H) * d->W;
+  long long gx = (P + ppb * 4 - 1) / (ppb * 4);
+  if (gx > 148 * 8) gx = 148 * 8;
+  if (gx < 1) gx = 1;
+  e = check_cuda(cudaMemsetAsync(g->gsum, 0, sizeof(double) * 2 * d->groups * d->batch, STREAM), "memset gsum");
+  if (e) return e;
+  gn_bwd_kernel<false><<<dim3((unsigned)gx, d->batch), threads, 0, STREAM>>>(a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  BUDDY_CHECK_LAUNCH("gn_bwd_kernel<stats>");
+  gn_bwd_kernel<true><<<dim3((unsigned)gx, d->batch), threads, 0, STREAM>>>(a);
+  LAUNCH_END("gn_bwd_kernel<apply>");
+}
+
+extern "C" int buddy_im2col_c2(const float* x, int B, int H, int W, void* col, void* stream) {
+  const long long items = static_cast<long long>(B) * H * W * 8;
+  im2col_c2_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(x, B, H, W, static_cast<__half*>(col));
+  LAUNCH_END("im2col_c2_kernel");
+}
+extern "C" int buddy_col2im_c2(const float* dcol, int ld, int B, int H, int W, float* dx, int accumulate,
+                               void* stream) {
+  const long long items = static_cast<long long>(B) * H * W;
+  col2im_c2_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(dcol, ld, B, H, W, dx, accumulate);
+  LAUNCH_END("col2im_c2_kernel");
+}
+extern "C" int buddy_resample_c2(const float* in, int B, int Hin, int Win, int mode, const float* add, float* out,
+                                 int accumulate, void* stream) {
+  if (mode < 0 || mode > 3 || ((mode == 0 || mode == 3) && ((Hin & 1) || (Win & 1)))) {
+    set_last_error("buddy_resample_c2: bad mode/shape");
+    return BUDDY_ERR_INVALID;
+  }
+  const bool shrink = (mode == 0 || mode == 3);
+  const long long items = static_cast<long long>(B) * (shrink ? Hin / 2 : Hin * 2) * (shrink ? Win / 2 : Win * 2);
+  resample_c2_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(reinterpret_cast<const float2*>(in), B, Hin, Win, mode,
+                                                               reinterpret_cast<const float2*>(add),
+                                                               reinterpret_cast<float2*>(out), accumulate);
+  LAUNCH_END("resample_c2_kernel");
+}
+extern "C" int buddy_combine_fwd(const float* h, const float* pyr, const float* w, const float* bias, int64_t P, int C,
+                                 float* out, void* stream) {
+  if (C % 4) {
+    set_last_error("buddy_combine_fwd: C %% 4 != 0");
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  combine_fwd_kernel<<<grid_for(P * (C / 4), 256), 256, 0, STREAM>>>(h, reinterpret_cast<const float2*>(pyr), w, bias,
+                                                                      P, C, out);
+  LAUNCH_END("combine_fwd_kernel");
+}
+extern "C" int buddy_combine_bwd(const float* dout, const float* w, int64_t P, int C, float* dpyr, void* stream) {
+  if (C % 128) {
+    set_last_error("buddy_combine_bwd: C %% 128 != 0");
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  combine_bwd_kernel<<<grid_for(P * 32, 256), 256, 0, STREAM>>>(dout, w, P, C, reinterpret_cast<float2*>(dpyr));
+  LAUNCH_END("combine_bwd_kernel");
+}
+extern "C" int buddy_affine_c2(const float* x, int64_t P, const float* m_host, const float* b_host, float* y,
+                               void* stream) {
+  affine_c2_kernel<<<grid_for(P, 256), 256, 0, STREAM>>>(reinterpret_cast<const float2*>(x), P, m_host[0], m_host[1],
+                                                         m_host[2], m_host[3], b_host[0], b_host[1],
+                                                         reinterpret_cast<float2*>(y));
+  LAUNCH_END("affine_c2_kernel");
+}
+extern "C" int buddy_softmax_fwd(const float* s, int64_t rows, int n, void* p, int ldp, void* stream) {
+  softmax_fwd_kernel<<<(unsigned)rows, 256, 0, STREAM>>>(s, n, static_cast<__half*>(p), ldp);
+  LAUNCH_END("softmax_fwd_kernel");
+}
+extern "C" int buddy_softmax_bwd(const void* p, int ldp, const float* dp, int64_t rows, int n, float scale, void* ds,
+                                 int ldds, void* stream) {
+  softmax_bwd_kernel<<<(unsigned)rows, 256, 0, STREAM>>>(static_cast<const __half*>(p), ldp, dp, n, scale,
+                                                         static_cast<__half*>(ds), ldds);
+  LAUNCH_END("softmax_bwd_kernel");
+}
+extern "C" int buddy_transpose_h(const void* in, int batch, int R, int Cc, int64_t ld_in, int64_t bs_in, void* out,
+                                 int64_t ld_out, int64_t bs_out, void* stream) {
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, batch);
+  transpose_h_kernel<<<grid, dim3(32, 8), 0, STREAM>>>(static_cast<const __half*>(in), R, Cc, ld_in, bs_in,
+                                                       static_cast<__half*>(out), ld_out, bs_out);
+  LAUNCH_END("transpose_h_kernel");
+}
+extern "C" int buddy_cast_scale_h(const float* x, int64_t n, float scale, void* y, void* stream) {
+  if (n % 8) {
+    set_last_error("buddy_cast_scale_h: n %% 8 != 0");
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  cast_scale_h_kernel<<<grid_for(n / 8, 256), 256, 0, STREAM>>>(x, n / 8, scale, static_cast<__half*>(y));
+  LAUNCH_END("cast_scale_h_kernel");
+}

@@ -79,3 +79,128 @@ def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=N
         assert stats.dtype == torch.float64
     check(lib().buddy_conv_gemm(ctypes.byref(d), stream_ptr()), "buddy_conv_gemm")
     return out
+
+
+from ._capi import GnBwdDesc, GnDesc, c_float, c_i64, c_int  # noqa: E402
+
+MODE_NONE, MODE_UP, MODE_DOWN = 0, 1, 2
+
+
+def gn_stats(x, stats=None):
+    """Per-4-channel-bundle (sum, sumsq) of x fp32 [B,H,W,C] -> fp64 [B, C/4, 2]."""
+    B, C = x.shape[0], x.shape[-1]
+    P = x.numel() // (B * C)
+    if stats is None:
+        stats = torch.zeros(B, C // 4, 2, device=x.device, dtype=torch.float64)
+    check(lib().buddy_gn_stats(ptr(x), c_int(B), c_i64(P), c_int(C), ptr(stats), stream_ptr()), "buddy_gn_stats")
+    return stats
+
+
+def _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps):
+    B, H, W, Ca = xa.shape
+    d = GnDesc()
+    d.xa, d.Ca, d.stats_a = ptr(xa), Ca, ptr(sa)
+    if xb is not None:
+        assert xb.shape[:3] == xa.shape[:3]
+        d.xb, d.Cb, d.stats_b = ptr(xb), xb.shape[3], ptr(sb)
+    d.gamma, d.beta = ptr(gamma), ptr(beta)
+    d.batch, d.H, d.W = B, H, W
+    d.groups, d.eps, d.silu, d.mode = groups, eps, int(silu), mode
+    return d
+
+
+def gn_apply(xa, sa, gamma, beta, out, *, xb=None, sb=None, groups=32, silu=True, mode=MODE_NONE, out_raw=None,
+             eps=1e-6):
+    """out(fp16) = resample(act(GroupNorm([xa|xb]))); out_raw(fp16) = resample([xa|xb])."""
+    assert xa.dtype == torch.float32 and xa.is_contiguous() and out.dtype == torch.float16
+    d = _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps)
+    d.out, d.out_raw = ptr(out), ptr(out_raw)
+    check(lib().buddy_gn_apply(ctypes.byref(d), stream_ptr()), "buddy_gn_apply")
+    return out
+
+
+def gn_bwd(xa, sa, gamma, beta, da, gsum, *, xb=None, sb=None, groups=32, silu=True, mode=MODE_NONE, dskip=None,
+           skip_scale=1.0, extra_a=None, extra_b=None, dxa=None, dxb=None, g16a=None, g16b=None, g16_scale=1.0,
+           eps=1e-6):
+    d = _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps)
+    g = GnBwdDesc()
+    g.da, g.dskip, g.skip_scale = ptr(da), ptr(dskip), skip_scale
+    g.extra_a, g.extra_b, g.gsum = ptr(extra_a), ptr(extra_b), ptr(gsum)
+    g.dxa, g.dxb, g.g16a, g.g16b, g.g16_scale = ptr(dxa), ptr(dxb), ptr(g16a), ptr(g16b), g16_scale
+    assert da.dtype == torch.float32 and gsum.dtype == torch.float64
+    check(lib().buddy_gn_bwd(ctypes.byref(d), ctypes.byref(g), stream_ptr()), "buddy_gn_bwd")
+
+
+def im2col_c2(x, col):
+    B, H, W, _ = x.shape
+    check(lib().buddy_im2col_c2(ptr(x), c_int(B), c_int(H), c_int(W), ptr(col), stream_ptr()), "buddy_im2col_c2")
+    return col
+
+
+def col2im_c2(dcol, dx, accumulate=False):
+    B, H, W, ld = dcol.shape
+    check(lib().buddy_col2im_c2(ptr(dcol), c_int(ld), c_int(B), c_int(H), c_int(W), ptr(dx), c_int(int(accumulate)),
+                                stream_ptr()), "buddy_col2im_c2")
+    return dx
+
+
+def resample_c2(x, mode, out, add=None, accumulate=False):
+    B, H, W, _ = x.shape
+    check(lib().buddy_resample_c2(ptr(x), c_int(B), c_int(H), c_int(W), c_int(mode), ptr(add), ptr(out),
+                                  c_int(int(accumulate)), stream_ptr()), "buddy_resample_c2")
+    return out
+
+
+def combine_fwd(h, pyr, w, bias, out):
+    C = h.shape[-1]
+    P = h.numel() // C
+    check(lib().buddy_combine_fwd(ptr(h), ptr(pyr), ptr(w), ptr(bias), c_i64(P), c_int(C), ptr(out), stream_ptr()),
+          "buddy_combine_fwd")
+    return out
+
+
+def combine_bwd(dout, w, dpyr):
+    C = dout.shape[-1]
+    P = dout.numel() // C
+    check(lib().buddy_combine_bwd(ptr(dout), ptr(w), c_i64(P), c_int(C), ptr(dpyr), stream_ptr()), "buddy_combine_bwd")
+    return dpyr
+
+
+def affine_c2(x, m4, b2, y):
+    P = x.numel() // 2
+    m = (c_float * 4)(*[float(v) for v in m4])
+    b = (c_float * 2)(*[float(v) for v in b2])
+    check(lib().buddy_affine_c2(ptr(x), c_i64(P), m, b, ptr(y), stream_ptr()), "buddy_affine_c2")
+    return y
+
+
+def softmax_fwd(s, p):
+    n = s.shape[-1]
+    rows = s.numel() // n
+    check(lib().buddy_softmax_fwd(ptr(s), c_i64(rows), c_int(n), ptr(p), c_int(p.shape[-1]), stream_ptr()),
+          "buddy_softmax_fwd")
+    return p
+
+
+def softmax_bwd(p, dp, scale, ds):
+    n = dp.shape[-1]
+    rows = dp.numel() // n
+    check(lib().buddy_softmax_bwd(ptr(p), c_int(p.shape[-1]), ptr(dp), c_i64(rows), c_int(n), c_float(scale), ptr(ds),
+                                  c_int(ds.shape[-1]), stream_ptr()), "buddy_softmax_bwd")
+    return ds
+
+
+def transpose_h(x, out):
+    """x fp16 [batch, R, C] (row stride arbitrary) -> out fp16 [batch, C, R]."""
+    batch, R, C = x.shape
+    assert x.stride(2) == 1 and out.stride(2) == 1 and out.shape == (batch, C, R)
+    check(lib().buddy_transpose_h(ptr(x), c_int(batch), c_int(R), c_int(C), c_i64(x.stride(1)), c_i64(x.stride(0)),
+                                  ptr(out), c_i64(out.stride(1)), c_i64(out.stride(0)), stream_ptr()),
+          "buddy_transpose_h")
+    return out
+
+
+def cast_scale_h(x, scale, y):
+    check(lib().buddy_cast_scale_h(ptr(x), c_i64(x.numel()), c_float(scale), ptr(y), stream_ptr()),
+          "buddy_cast_scale_h")
+    return y

@@ -88,6 +88,80 @@ typedef struct buddy_gemm_desc {
 
 int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm (+SiLU) (+nearest-x2 / 2x2-mean resample) (+virtual channel concat) and its data-gradient.
+ * Replaces nn.GroupNorm(min(C//4,32), C, eps=1e-6) + SiLU + naive_up/downsample_2d + torch.cat of
+ * ResnetBlockBigGANpp.forward / AttnBlockpp.forward / pyramid heads
+ * (networks/ncsnpp_utils/layerspp.py:75-76,242-263; up_or_down_sampling.py:59-69; ncsnpp.py:383,396-412).
+ *
+ * Statistics travel as per-4-channel-bundle fp64 (sum, sum of squares) accumulators [batch][C/4][2], produced
+ * either by buddy_conv_gemm's epilogue (`stats`) or by buddy_gn_stats; any group size that is a multiple of
+ * 4 channels — including groups straddling the concat boundary (384 = 256 + 128 -> 12 per group) — is
+ * assembled from bundles by the consumer.
+ */
+typedef struct buddy_gn_desc {
+  const float* xa; /* fp32 [batch][H][W][Ca] */
+  const float* xb; /* fp32 [batch][H][W][Cb] or NULL (Cb = 0): virtual concat [xa | xb] */
+  int32_t Ca, Cb;
+  const double* stats_a; /* [batch][Ca/4][2] */
+  const double* stats_b; /* [batch][Cb/4][2] or NULL */
+  const float* gamma;    /* [Ca+Cb] */
+  const float* beta;     /* [Ca+Cb] */
+  int32_t batch, H, W;   /* resolution of x */
+  int32_t groups;
+  float eps;
+  int32_t silu; /* 1: SiLU after the affine */
+  int32_t mode; /* 0 none, 1 nearest x2 upsample after the activation, 2 2x2 mean after the activation */
+  void* out;     /* fp16 [batch][H'][W'][Ca+Cb] */
+  void* out_raw; /* optional fp16 copy of the (resampled) input x, operand of the 1x1 skip conv */
+} buddy_gn_desc;
+
+typedef struct buddy_gn_bwd_desc {
+  const float* da;    /* fp32 [batch][H'][W'][C]: gradient w.r.t. `out` (at the resampled resolution) */
+  const float* dskip; /* optional fp32 [batch][H'][W'][C], added as R^T(dskip) * skip_scale */
+  float skip_scale;
+  const float* extra_a; /* optional fp32 [batch][H][W][Ca] added to dxa */
+  const float* extra_b; /* optional fp32 [batch][H][W][Cb] added to dxb */
+  double* gsum;         /* scratch fp64 [batch][groups][2] (zeroed by the call) */
+  float* dxa;           /* optional fp32 out [batch][H][W][Ca] */
+  float* dxb;           /* optional fp32 out [batch][H][W][Cb] */
+  void* g16a;           /* optional fp16 out = dxa * g16_scale (dgrad operand of the producer) */
+  void* g16b;
+  float g16_scale;
+} buddy_gn_bwd_desc;
+
+int buddy_gn_stats(const float* x, int batch, int64_t pixels, int C, double* stats /* += */, void* stream);
+int buddy_gn_apply(const buddy_gn_desc* d, void* stream);
+int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, void* stream);
+
+/* 2-channel (re, im) image helpers — the thin ends of the U-Net.
+ * im2col_c2: x fp32 [B][H][W][2] -> fp16 [B][H][W][64], K index = tap*2 + ci (3x3, zero padded), so the
+ *            2->128 input conv (ncsnpp.py:331) and the dgrad of the 256->2 pyramid heads (:396-412) run as
+ *            plain GEMMs on buddy_conv_gemm.  col2im_c2 is its adjoint (gathers 9 taps).
+ * resample_c2 modes: 0 = 2x2 mean (pyramid_downsample, layerspp.py:156), 1 = nearest x2 (+add)
+ *            (pyramid_upsample, layerspp.py:117), 2 = adjoint of 0, 3 = adjoint of 1.
+ * combine_*: Combine.forward, method 'sum' (layerspp.py:52-59): out = h + Conv1x1(pyr) and d/dpyr.
+ * affine_c2: 2x2 affine map per pixel = output_layer (ncsnpp.py:113,445) and its adjoint. */
+int buddy_im2col_c2(const float* x, int B, int H, int W, void* col, void* stream);
+int buddy_col2im_c2(const float* dcol, int ld, int B, int H, int W, float* dx, int accumulate, void* stream);
+int buddy_resample_c2(const float* in, int B, int Hin, int Win, int mode, const float* add, float* out,
+                      int accumulate, void* stream);
+int buddy_combine_fwd(const float* h, const float* pyr, const float* w, const float* bias, int64_t pixels, int C,
+                      float* out, void* stream);
+int buddy_combine_bwd(const float* dout, const float* w, int64_t pixels, int C, float* dpyr, void* stream);
+int buddy_affine_c2(const float* x, int64_t pixels, const float* m_host /*[4]*/, const float* b_host /*[2]*/,
+                    float* y, void* stream);
+
+/* Attention helpers (AttnBlockpp.forward, layerspp.py:81-85): row softmax fp32 -> fp16 probabilities, its
+ * backward dS = P*(dP - <dP,P>)*scale, batched fp16 transpose, and fp32 -> fp16 cast with scale. */
+int buddy_softmax_fwd(const float* s, int64_t rows, int n, void* p, int ldp, void* stream);
+int buddy_softmax_bwd(const void* p, int ldp, const float* dp, int64_t rows, int n, float scale, void* ds, int ldds,
+                      void* stream);
+int buddy_transpose_h(const void* in, int batch, int R, int C, int64_t ld_in, int64_t bs_in, void* out,
+                      int64_t ld_out, int64_t bs_out, void* stream);
+int buddy_cast_scale_h(const float* x, int64_t n, float scale, void* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
