@@ -1,0 +1,141 @@
+// Small kernels around the network and the sampler loop:
+//   * Gaussian Fourier features + dense layers of the noise-level embedding
+//     (networks/ncsnpp_utils/layerspp.py:39-41; ncsnpp.py:299-318; Dense_0 of every ResBlock, layerspp.py:262-263)
+//   * Philox4x32-10 normal generator with one independent stream per utterance (replaces the CPU
+//     torch.randn(...).to(device) of testing/EulerHeunSampler.py:21,43 — results do not depend on the GPU count)
+//   * per-utterance linear combinations used by the Euler/Heun/DPS update algebra
+//     (testing/EulerHeunSamplerDPS.py:115-157, diff_params/edm.py:83-96, diff_params/shared.py:120)
+#include <atomic>
+
+#include "../../include/buddy_b200.h"
+#include "common.cuh"
+
+namespace buddy {
+extern std::atomic<long long> g_launches;
+#define LAUNCH_END(name)                              \
+  g_launches.fetch_add(1, std::memory_order_relaxed); \
+  BUDDY_CHECK_LAUNCH(name);                           \
+  return 0;
+#define STREAM static_cast<cudaStream_t>(stream)
+
+__global__ void fourier_features_kernel(const float* __restrict__ t, const float* __restrict__ Wf, int B, int E,
+                                        float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * E) return;
+  const int b = i / E, j = i % E;
+  // x_proj = t * W * 2 * pi  (same evaluation order as the reference, fp32)
+  const float xp = t[b] * Wf[j] * 2.f * 3.14159265358979323846f;
+  out[b * 2 * E + j] = sinf(xp);
+  out[b * 2 * E + E + j] = cosf(xp);
+}
+
+// y[b][o] = act_out( sum_i W[o][i] * act_in(x[b][i]) + bias[o] );  one warp per output
+__global__ void dense_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                             int B, int In, int Out, int act_in, int act_out, float* __restrict__ y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * Out) return;
+  const int b = warp / Out, o = warp % Out;
+  float acc = 0.f;
+  for (int i = lane; i < In; i += 32) {
+    float v = x[b * In + i];
+    if (act_in) v = v / (1.f + expf(-v));
+    acc = fmaf(W[static_cast<long long>(o) * In + i], v, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    acc += bias ? bias[o] : 0.f;
+    if (act_out) acc = acc / (1.f + expf(-acc));
+    y[b * Out + o] = acc;
+  }
+}
+
+// ---- Philox4x32-10
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+// out[b][i] ~ N(0,1); key = seeds[b], counter = (i/4, draw index)
+__global__ void philox_normal_kernel(const long long* __restrict__ seeds, unsigned long long draw, int n,
+                                     float* __restrict__ out, long long ld) {
+  const int b = blockIdx.y;
+  const unsigned long long seed = static_cast<unsigned long long>(seeds[b]);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += gridDim.x * blockDim.x) {
+    uint32_t c[4] = {static_cast<uint32_t>(q), 0u, static_cast<uint32_t>(draw), static_cast<uint32_t>(draw >> 32)};
+    philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    float z[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u1 = (static_cast<float>(c[2 * h] >> 8) + 0.5f) * (1.f / 16777216.f);
+      const float u2 = (static_cast<float>(c[2 * h + 1] >> 8) + 0.5f) * (1.f / 16777216.f);
+      const float r = sqrtf(-2.f * logf(u1));
+      float sn, cs;
+      sincospif(2.f * u2, &sn, &cs);
+      z[2 * h] = r * cs;
+      z[2 * h + 1] = r * sn;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q * 4 + j < n) out[b * ld + q * 4 + j] = z[j];
+  }
+}
+
+// out[b][i] = ca[b]*x[b][i] + cb[b]*y[b][i] + cc[b]*z[b][i]   (null coefficient array / tensor => term absent)
+__global__ void lincomb3_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
+                                const float* __restrict__ ca, const float* __restrict__ cb,
+                                const float* __restrict__ cc, int n, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const float a = ca[b], bb = (y && cb) ? cb[b] : 0.f, c = (z && cc) ? cc[b] : 0.f;
+  const long long base = static_cast<long long>(b) * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float v = a * x[base + i];
+    if (y && cb) v = fmaf(bb, y[base + i], v);
+    if (z && cc) v = fmaf(c, z[base + i], v);
+    out[base + i] = v;
+  }
+}
+}  // namespace buddy
+
+using namespace buddy;
+
+extern "C" int buddy_fourier_features(const float* t, const float* Wf, int B, int E, float* out, void* stream) {
+  fourier_features_kernel<<<(B * E + 255) / 256, 256, 0, STREAM>>>(t, Wf, B, E, out);
+  LAUNCH_END("fourier_features_kernel");
+}
+extern "C" int buddy_dense(const float* x, const float* W, const float* bias, int B, int In, int Out, int act_in,
+                           int act_out, float* y, void* stream) {
+  const long long threads = static_cast<long long>(B) * Out * 32;
+  dense_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, STREAM>>>(x, W, bias, B, In, Out, act_in,
+                                                                                act_out, y);
+  LAUNCH_END("dense_kernel");
+}
+extern "C" int buddy_philox_normal(const int64_t* seeds, uint64_t draw, int batch, int n, float* out, int64_t ld,
+                                   void* stream) {
+  int gx = (n / 4 + 255) / 256;
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  philox_normal_kernel<<<dim3(gx, batch), 256, 0, STREAM>>>(reinterpret_cast<const long long*>(seeds), draw, n, out,
+                                                            ld);
+  LAUNCH_END("philox_normal_kernel");
+}
+extern "C" int buddy_lincomb3(const float* x, const float* y, const float* z, const float* ca, const float* cb,
+                              const float* cc, int batch, int n, float* out, void* stream) {
+  if (!x || !ca) {
+    set_last_error("buddy_lincomb3: x and ca are required");
+    return BUDDY_ERR_INVALID;
+  }
+  int gx = (n + 255) / 256;
+  if (gx > 64) gx = 64;
+  lincomb3_kernel<<<dim3(gx, batch), 256, 0, STREAM>>>(x, y, z, ca, cb, cc, n, out);
+  LAUNCH_END("lincomb3_kernel");
+}

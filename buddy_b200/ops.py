@@ -204,3 +204,104 @@ def cast_scale_h(x, scale, y):
     check(lib().buddy_cast_scale_h(ptr(x), c_i64(x.numel()), c_float(scale), ptr(y), stream_ptr()),
           "buddy_cast_scale_h")
     return y
+
+
+c_u64 = ctypes.c_uint64
+
+
+def dft_analysis(sig, mat, hop, frames, Tout, out):
+    """sig fp32 [B, L]; mat fp32 [2*bins, K]; out fp32 [B, bins, Tout, 2]."""
+    B = sig.shape[0]
+    M, K = mat.shape
+    check(lib().buddy_dft_analysis(ptr(sig), c_i64(sig.stride(0)), c_int(B), ptr(mat), c_int(M), c_int(K), c_int(hop),
+                                   c_int(frames), c_int(Tout), ptr(out), stream_ptr()), "buddy_dft_analysis")
+    return out
+
+
+def dft_synthesis(S, mat, frames, fr):
+    """S fp32 [B, bins, Tin, 2]; mat [2*bins, K]; fr fp32 [B, frames, K]."""
+    B, _, Tin, _ = S.shape
+    M, K = mat.shape
+    check(lib().buddy_dft_synthesis(ptr(S), c_int(B), c_int(Tin), ptr(mat), c_int(M), c_int(K), c_int(frames), ptr(fr),
+                                    stream_ptr()), "buddy_dft_synthesis")
+    return fr
+
+
+def ola_gather(fr, hop, off, n_out, out, tab=None, scale_b=None):
+    B, frames, K = fr.shape
+    check(lib().buddy_ola_gather(ptr(fr), c_int(B), c_int(frames), c_int(K), c_int(hop), c_int(off), c_int(n_out),
+                                 ptr(tab), ptr(scale_b), ptr(out), c_i64(out.stride(0)), stream_ptr()),
+          "buddy_ola_gather")
+    return out
+
+
+def pad_signal(x, left, total, mode, out, tab=None, scale_b=None):
+    B, N = x.shape
+    check(lib().buddy_pad_signal(ptr(x), c_i64(x.stride(0)), c_int(B), c_int(N), c_int(left), c_int(total),
+                                 c_int(mode), ptr(tab), ptr(scale_b), ptr(out), stream_ptr()), "buddy_pad_signal")
+    return out
+
+
+def reflect_fold(dxp, N, L, out, scale_b=None):
+    B = dxp.shape[0]
+    check(lib().buddy_reflect_fold(ptr(dxp), c_int(B), c_int(N), c_int(L), ptr(scale_b), ptr(out),
+                                   c_i64(out.stride(0)), stream_ptr()), "buddy_reflect_fold")
+    return out
+
+
+def comp_loss(Y, X, frames, compression, weight, loss, grad=None):
+    B = Y.shape[0]
+    per = Y.numel() // (2 * B)
+    check(lib().buddy_comp_loss(ptr(Y), ptr(X), c_int(B), c_i64(per), c_int(frames), c_float(compression),
+                                c_float(weight), ptr(loss), ptr(grad), stream_ptr()), "buddy_comp_loss")
+    return loss
+
+
+def row_stats(x, out=None):
+    """(sum, sumsq) per row of x fp32 [B, n] -> fp64 [B, 2]."""
+    B, n = x.shape
+    if out is None:
+        out = torch.empty(B, 2, device=x.device, dtype=torch.float64)
+    check(lib().buddy_row_stats(ptr(x), c_i64(x.stride(0)), c_int(B), c_int(n), ptr(out), stream_ptr()),
+          "buddy_row_stats")
+    return out
+
+
+def fftconv(x, n_in, log2_n2, tw512, work, H, h_batch_stride, mode, y, n_out):
+    B = x.shape[0]
+    check(lib().buddy_fftconv(ptr(x), c_i64(x.stride(0)), c_int(B), c_int(n_in), c_int(log2_n2), ptr(tw512), ptr(work),
+                              ptr(H), c_i64(h_batch_stride), c_int(mode), ptr(y),
+                              c_i64(y.stride(0) if y is not None else 0), c_int(n_out), stream_ptr()), "buddy_fftconv")
+    return y
+
+
+def fourier_features(t, W, out):
+    B, E = t.shape[0], W.shape[0]
+    check(lib().buddy_fourier_features(ptr(t), ptr(W), c_int(B), c_int(E), ptr(out), stream_ptr()),
+          "buddy_fourier_features")
+    return out
+
+
+def dense(x, W, bias, out, act_in=False, act_out=False):
+    B, In = x.shape
+    Out = W.shape[0]
+    check(lib().buddy_dense(ptr(x), ptr(W), ptr(bias), c_int(B), c_int(In), c_int(Out), c_int(int(act_in)),
+                            c_int(int(act_out)), ptr(out), stream_ptr()), "buddy_dense")
+    return out
+
+
+def philox_normal(seeds, draw, out):
+    B, n = out.shape
+    assert seeds.dtype == torch.int64
+    check(lib().buddy_philox_normal(ptr(seeds), c_u64(draw), c_int(B), c_int(n), ptr(out), c_i64(out.stride(0)),
+                                    stream_ptr()), "buddy_philox_normal")
+    return out
+
+
+def lincomb3(out, x, ca, y=None, cb=None, z=None, cc=None):
+    B, n = x.shape
+    for t in (x, y, z, out):
+        assert t is None or (t.is_contiguous() and t.dtype == torch.float32)
+    check(lib().buddy_lincomb3(ptr(x), ptr(y), ptr(z), ptr(ca), ptr(cb), ptr(cc), c_int(B), c_int(n), ptr(out),
+                               stream_ptr()), "buddy_lincomb3")
+    return out

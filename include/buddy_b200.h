@@ -162,6 +162,52 @@ int buddy_transpose_h(const void* in, int batch, int R, int C, int64_t ld_in, in
                       int64_t ld_out, int64_t bs_out, void* stream);
 int buddy_cast_scale_h(const float* x, int64_t n, float scale, void* y, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * STFT / iSTFT as fp32 DFT-GEMMs with exact frame indexing (torch.stft / torch.istft semantics of
+ * NCSNppTime.stft/istft, networks/ncsnpp.py:473-496, and of the operators' apply_stft/apply_istft,
+ * testing/operators/subband_filtering.py:41-65).  Spectrograms are [batch][bins][frames][2] (re, im) fp32 —
+ * the channels-last image the network consumes.  `mat` is a host-built [2*bins][K] matrix (window, onesided
+ * weights and normalisation folded in); the adjoints are the same two kernels with the matrices swapped.
+ *   analysis : out[b][f][t][c] = sum_{n<K} mat[2f+c][n] * sig[b][t*hop + n]   (t < frames; zeros up to Tout)
+ *   synthesis: fr[b][t][n]     = sum_{m<M} S[b][m/2][t][m%2] * mat[m][n]
+ *   ola_gather: out[b][s] = tab[s+off] * scale_b[b] * sum_t fr[b][t][s+off-t*hop]   (overlap-add + envelope)
+ *   pad_signal: zero (mode 0) / reflect (mode 1) padding with optional per-sample table and per-utterance scale
+ *   reflect_fold: adjoint of the reflect padding.
+ */
+int buddy_dft_analysis(const float* sig, int64_t sig_ld, int batch, const float* mat, int M, int K, int hop,
+                       int frames, int Tout, float* out, void* stream);
+int buddy_dft_synthesis(const float* S, int batch, int Tin, const float* mat, int M, int K, int frames, float* fr,
+                        void* stream);
+int buddy_ola_gather(const float* fr, int batch, int frames, int K, int hop, int off, int n_out, const float* tab,
+                     const float* scale_b, float* out, int64_t out_ld, void* stream);
+int buddy_pad_signal(const float* x, int64_t x_ld, int batch, int N, int left, int total, int mode, const float* tab,
+                     const float* scale_b, float* out, void* stream);
+int buddy_reflect_fold(const float* dxp, int batch, int N, int L, const float* scale_b, float* dx, int64_t dx_ld,
+                       void* stream);
+
+/* Compressed-spectrum likelihood "l2_comp_stft_summean" (utils/losses.py:59-64,74-76), per utterance:
+ * loss[b] = weight/frames * sum_{f,t} |Yc - Xc|^2, Zc = (|Z|+1e-8)^c e^{j angle Z}; grad = dloss[b]/dX or NULL. */
+int buddy_comp_loss(const float* Y, const float* X, int batch, int64_t bins_times_frames, int frames,
+                    float compression, float weight, double* loss, float* grad, void* stream);
+/* out[b] = (sum, sum of squares) of x[b][:n] in fp64 — .std() / torch.norm of EulerHeunSamplerDPS.py:30,68,129. */
+int buddy_row_stats(const float* x, int64_t ld, int batch, int n, double* out, void* stream);
+
+/* FFT convolution of fast_apply_RIR (utils/reverb_utils.py:25-60), L = 256 * 2^log2_n2 points.
+ * mode 0: work <- spectrum of x (reusable as `H`); mode 1: y = real(ifft(fft(x) H))[:n_out]; mode 2: conj(H)
+ * (the adjoint).  `tw512` = exp(-2 pi i k / 512), k < 256, as float2.  work: complex scratch [batch][L]. */
+int buddy_fftconv(const float* x, int64_t x_ld, int batch, int n_in, int log2_n2, const float* tw512, float* work,
+                  const float* H, int64_t h_batch_stride, int mode, float* y, int64_t y_ld, int n_out, void* stream);
+
+/* Noise-level embedding (GaussianFourierProjection + Linear/SiLU, ncsnpp.py:299-318; Dense_0, layerspp.py:262). */
+int buddy_fourier_features(const float* t, const float* W, int B, int E, float* out, void* stream);
+int buddy_dense(const float* x, const float* W, const float* bias, int B, int In, int Out, int act_in, int act_out,
+                float* y, void* stream);
+/* Philox4x32-10 N(0,1), one stream per utterance (seed[b]), `draw` = running draw index of the sampler. */
+int buddy_philox_normal(const int64_t* seeds, uint64_t draw, int batch, int n, float* out, int64_t ld, void* stream);
+/* out[b][:] = ca[b] x[b][:] + cb[b] y[b][:] + cc[b] z[b][:] — the Euler/Heun/DPS update algebra. */
+int buddy_lincomb3(const float* x, const float* y, const float* z, const float* ca, const float* cb, const float* cc,
+                   int batch, int n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,128 @@
+"""Parity of the spectral kernels against torch.stft/istft/fft (the reference's own ops) and the oracle."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.mark.parametrize("N", [3000, 8192, 65536])
+def test_net_stft_roundtrip_and_adjoints(N):
+    from buddy_b200.spectral import NetSTFT
+    from oracle import net as onet
+    st = NetSTFT("cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B = 2
+    x = torch.randn(B, N, device="cuda", generator=g)
+    sc = torch.tensor([0.5, 2.0], device="cuda")
+    spec = st.forward(x, scale_b=sc)
+    ref = onet.net_stft((x * sc[:, None])[:, None])[:, 0]
+    assert spec.shape == (B, 256, ref.shape[-1], 2)  # exact frame count incl. zero padding
+    assert rel(spec, torch.view_as_real(ref)) < 1e-5
+    assert spec[:, :, 1 + N // 128:].abs().max().item() == 0.0
+    # inverse on an arbitrary (non-consistent) spectrogram incl. non-zero padded frames
+    S = torch.randn(B, 256, spec.shape[2], 2, device="cuda", generator=g)
+    y = st.inverse(S, N)
+    yref = onet.net_istft(torch.view_as_complex(S.contiguous())[:, None], N)[:, 0]
+    assert rel(y, yref) < 1e-5
+    # adjoints: <A x, S> == <x, A^T S>
+    gsig = torch.randn(B, N, device="cuda", generator=g)
+    lhs = (st.inverse(S, N).double() * gsig.double()).sum()
+    rhs = (S.double() * st.inverse_adjoint(gsig).double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+    lhs = (st.forward(x).double() * S.double()).sum()
+    rhs = (x.double() * st.forward_adjoint(S, N).double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+
+
+@pytest.mark.parametrize("N", [4096, 65536])
+def test_loss_stft_and_comp_loss(N):
+    from buddy_b200 import ops
+    from buddy_b200.spectral import LossSTFT
+    from oracle import operators as oop
+    st = LossSTFT("cuda")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    B = 3
+    y = torch.randn(B, N, device="cuda", generator=g) * 0.05
+    x = (y + 0.02 * torch.randn(B, N, device="cuda", generator=g)).requires_grad_(True)
+    Y, X = st.forward(y), st.forward(x.detach())
+    assert X.shape == (B, 513, 1 + (N + 512) // 128, 2)
+    assert rel(X, torch.view_as_real(oop.loss_stft(x.detach()))) < 1e-5
+    loss = torch.empty(B, device="cuda", dtype=torch.float64)
+    G = torch.empty_like(X)
+    ops.comp_loss(Y, X, X.shape[2], 0.667, 512.0, loss, G)
+    gx = st.adjoint(G, N)
+    lref = oop.comp_loss(y, x, 512.0)
+    (gref,) = torch.autograd.grad(lref.sum(), x)
+    assert rel(loss.float(), lref.detach()) < 1e-4
+    assert rel(gx, gref) < 1e-3, rel(gx, gref)
+
+
+@pytest.mark.parametrize("N,M,per_utt", [(8192, 2000, False), (65536, 16000, False), (65536, 40000, True)])
+def test_rir_fftconv(N, M, per_utt):
+    from buddy_b200.spectral import RirConv
+    from oracle import operators as oop
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B = 2
+    x = torch.randn(B, N, device="cuda", generator=g)
+    h = torch.randn((B, M) if per_utt else (M,), device="cuda", generator=g) * torch.exp(
+        -torch.arange(M, device="cuda") / (M / 6))
+    rc = RirConv(h, N, "cuda")
+    y = rc.forward(x)
+    if per_utt:
+        ref = torch.cat([oop.fast_apply_rir(x[i:i + 1].double(), h[i].double()) for i in range(B)])
+    else:
+        ref = oop.fast_apply_rir(x.double(), h.double())
+    assert rel(y, ref) < 1e-5, rel(y, ref)
+    gy = torch.randn(B, N, device="cuda", generator=g)
+    lhs = (y.double() * gy.double()).sum()
+    rhs = (x.double() * rc.adjoint(gy).double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+
+
+def test_temb_philox_lincomb_rowstats():
+    from buddy_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    B = 3
+    t = torch.tensor([-0.3, -1.1, 0.2], device="cuda")
+    Wf = torch.randn(128, device="cuda", generator=g) * 16
+    emb = torch.empty(B, 256, device="cuda")
+    ops.fourier_features(t, Wf, emb)
+    xp = t[:, None] * Wf[None] * 2 * torch.pi
+    assert rel(emb, torch.cat([xp.sin(), xp.cos()], -1)) < 1e-5
+    W = torch.randn(512, 256, device="cuda", generator=g) * 0.05
+    bias = torch.randn(512, device="cuda", generator=g)
+    out = torch.empty(B, 512, device="cuda")
+    ops.dense(emb, W, bias, out, act_in=True, act_out=True)
+    ref = torch.nn.functional.silu(torch.nn.functional.linear(torch.nn.functional.silu(emb), W, bias))
+    assert rel(out, ref) < 1e-5
+    seeds = torch.tensor([3000, 3001, 3000], device="cuda", dtype=torch.int64)
+    z = torch.empty(B, 65536, device="cuda")
+    ops.philox_normal(seeds, 7, z)
+    assert abs(z.mean().item()) < 0.01 and abs(z.std().item() - 1) < 0.01
+    assert torch.equal(z[0], z[2]) and not torch.equal(z[0], z[1])
+    z2 = torch.empty(1, 65536, device="cuda")
+    ops.philox_normal(seeds[1:2], 7, z2)
+    assert torch.equal(z2[0], z[1])  # stream depends only on (seed, draw): invariant to batch sharding
+    ops.philox_normal(seeds[1:2], 8, z2)
+    assert not torch.equal(z2[0], z[1])
+    kurt = ((z - z.mean()) ** 4).mean() / z.var() ** 2
+    assert abs(kurt.item() - 3) < 0.05
+    x, y_, w = (torch.randn(B, 1000, device="cuda", generator=g) for _ in range(3))
+    ca, cb, cc = (torch.randn(B, device="cuda", generator=g) for _ in range(3))
+    o = torch.empty_like(x)
+    ops.lincomb3(o, x, ca, y_, cb, w, cc)
+    assert rel(o, ca[:, None] * x + cb[:, None] * y_ + cc[:, None] * w) < 1e-6
+    ops.lincomb3(o, x, ca, y_, cb)
+    assert rel(o, ca[:, None] * x + cb[:, None] * y_) < 1e-6
+    st = ops.row_stats(x)
+    assert rel(st[:, 0], x.double().sum(1)) < 1e-9 and rel(st[:, 1], (x.double() ** 2).sum(1)) < 1e-9
