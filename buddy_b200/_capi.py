@@ -32,7 +32,7 @@ class GemmDesc(ctypes.Structure):
         ("taps", c_int), ("b_batched", c_int), ("n_total", c_int), ("n_tile", c_int),
         ("out", c_void_p), ("out_fp16", c_int), ("ldc", c_i64), ("col_off", c_int),
         ("bias", c_void_p), ("bias_b", c_void_p), ("resid", c_void_p), ("ld_res", c_i64),
-        ("scale", c_float), ("stats", c_void_p), ("max_ctas", c_int),
+        ("scale", c_float), ("stats", c_void_p), ("max_ctas", c_int), ("k_total", c_int), ("k2_total", c_int),
     ]
 
 
@@ -85,7 +85,7 @@ class GnDesc(ctypes.Structure):
         ("xa", c_void_p), ("xb", c_void_p), ("Ca", c_int), ("Cb", c_int),
         ("stats_a", c_void_p), ("stats_b", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
         ("batch", c_int), ("H", c_int), ("W", c_int), ("groups", c_int), ("eps", c_float),
-        ("silu", c_int), ("mode", c_int), ("out", c_void_p), ("out_raw", c_void_p),
+        ("silu", c_int), ("mode", c_int), ("out", c_void_p), ("out_raw", c_void_p), ("split", c_int),
     ]
 
 

@@ -36,6 +36,7 @@ struct GemmParams {
   int bh, bw, tiles_h, tiles_w;
   int n_tiles, n_tile, n_total;
   int taps, kchunks1, kchunks2, b_batched;
+  int a_wrap1, a_wrap2;  // A-side channel chunk = k-chunk % a_wrap (split-precision operands re-read the hi half)
   int stages;
   float* out32;
   __half* out16;
@@ -123,11 +124,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               dy = tap / 3 - 1;
               dx = tap % 3 - 1;
             }
-            tma_load_4d(&tmA, sa, &full_bar[stage], kc * kBlockK, w0 + dx, h0 + dy, b);
+            tma_load_4d(&tmA, sa, &full_bar[stage], (kc % p.a_wrap1) * kBlockK, w0 + dx, h0 + dy, b);
             tma_load_3d(&tmB, sb, &full_bar[stage], kc * kBlockK, nt * p.n_tile, p.b_batched ? b : tap);
           } else {
             const int kc = kb - kb_phase1;
-            tma_load_4d(&tmA2, sa, &full_bar[stage], kc * kBlockK, w0, h0, b);
+            tma_load_4d(&tmA2, sa, &full_bar[stage], (kc % p.a_wrap2) * kBlockK, w0, h0, b);
             tma_load_3d(&tmB2, sb, &full_bar[stage], kc * kBlockK, nt * p.n_tile, 0);
           }
           if (++stage == p.stages) {
@@ -442,8 +443,16 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   p.n_total = d->n_total;
   p.n_tiles = (d->n_total + d->n_tile - 1) / d->n_tile;
   p.taps = d->taps;
-  p.kchunks1 = d->a_c / kBlockK;
-  p.kchunks2 = d->a2 ? d->a2_c / kBlockK : 0;
+  const int k1 = d->k_total > 0 ? d->k_total : d->a_c;
+  const int k2 = d->a2 ? (d->k2_total > 0 ? d->k2_total : d->a2_c) : 0;
+  if (k1 % kBlockK || k2 % kBlockK) {
+    set_last_error("buddy_conv_gemm: k_total must be a multiple of 64");
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  p.kchunks1 = k1 / kBlockK;
+  p.kchunks2 = k2 / kBlockK;
+  p.a_wrap1 = d->a_c / kBlockK;
+  p.a_wrap2 = d->a2 ? d->a2_c / kBlockK : 1;
   p.b_batched = d->b_batched;
   const int stage_bytes = kStageA + d->n_tile * 128;
   int stages = (227 * 1024 - 2048) / stage_bytes;
@@ -473,7 +482,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     if (e) return e;
   }
   {
-    uint64_t dims[3] = {(uint64_t)(d->a_c), (uint64_t)d->b_rows, (uint64_t)d->b_t};
+    uint64_t dims[3] = {(uint64_t)k1, (uint64_t)d->b_rows, (uint64_t)d->b_t};
     uint64_t str[3] = {1, (uint64_t)d->b_stride_n, (uint64_t)d->b_stride_t};
     uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)d->n_tile, 1};
     int e = encode_map(&tmB, d->b, 3, dims, str, box);
@@ -485,7 +494,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, 1};
     int e = encode_map(&tmA2, d->a2, 4, dims, str, box);
     if (e) return e;
-    uint64_t dimsb[3] = {(uint64_t)(d->a2_c), (uint64_t)d->b2_rows, 1};
+    uint64_t dimsb[3] = {(uint64_t)k2, (uint64_t)d->b2_rows, 1};
     uint64_t strb[3] = {1, (uint64_t)d->b2_stride_n, (uint64_t)d->b2_stride_n * (uint64_t)d->b2_rows};
     uint32_t boxb[3] = {(uint32_t)kBlockK, (uint32_t)d->n_tile, 1};
     e = encode_map(&tmB2, d->b2, 3, dimsb, strb, boxb);

@@ -82,6 +82,22 @@ __device__ __forceinline__ void store8h(__half* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = q;
 }
 
+// fp16 operand store; split: row = [hi (C) | lo (C)], lo = fp16(v - float(hi))
+__device__ __forceinline__ void store_op8(__half* base, long long pix, int C, int c, int split, const float (&v)[8]) {
+  if (!split) {
+    store8h(base + pix * C + c, v);
+    return;
+  }
+  float hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    hi[j] = __half2float(__float2half_rn(v[j]));
+    lo[j] = v[j] - hi[j];
+  }
+  store8h(base + pix * (2 * C) + c, hi);
+  store8h(base + pix * (2 * C) + C + c, lo);
+}
+
 // ------------------------------------------------------------------------------------------------
 // GroupNorm bundle statistics of a plain fp32 [B][P][C] tensor (for tensors no conv epilogue produced)
 // ------------------------------------------------------------------------------------------------
@@ -128,6 +144,7 @@ struct GnApplyArgs {
   int mode;  // 0 none, 1 nearest x2 up, 2 2x2-mean down
   __half* out;
   __half* out_raw;
+  int split;
 };
 
 __device__ __forceinline__ void gn_act8(const float (&x)[8], int c, const float* s_mean, const float* s_rstd,
@@ -164,8 +181,8 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
     if (a.mode == 0) {
       load8(a.s, in_img + p, c, x);
       gn_act8(x, c, s_mean, s_rstd, a.gamma, a.beta, a.cpg, a.silu, y);
-      store8h(a.out + (out_img + p) * C + c, y);
-      if (a.out_raw) store8h(a.out_raw + (out_img + p) * C + c, x);
+      store_op8(a.out, out_img + p, C, c, a.split, y);
+      if (a.out_raw) store_op8(a.out_raw, out_img + p, C, c, a.split, x);
     } else if (a.mode == 1) {
       const int h = static_cast<int>(p / a.W), w = static_cast<int>(p - static_cast<long long>(h) * a.W);
       load8(a.s, in_img + p, c, x);
@@ -173,8 +190,8 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         const long long po = out_img + static_cast<long long>(2 * h + (d >> 1)) * Wo + (2 * w + (d & 1));
-        store8h(a.out + po * C + c, y);
-        if (a.out_raw) store8h(a.out_raw + po * C + c, x);
+        store_op8(a.out, po, C, c, a.split, y);
+        if (a.out_raw) store_op8(a.out_raw, po, C, c, a.split, x);
       }
     } else {
       const int ho = static_cast<int>(p / Wo), wo = static_cast<int>(p - static_cast<long long>(ho) * Wo);
@@ -195,8 +212,8 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
         ya[j] *= 0.25f;
         xa[j] *= 0.25f;
       }
-      store8h(a.out + (out_img + p) * C + c, ya);
-      if (a.out_raw) store8h(a.out_raw + (out_img + p) * C + c, xa);
+      store_op8(a.out, out_img + p, C, c, a.split, ya);
+      if (a.out_raw) store_op8(a.out_raw, out_img + p, C, c, a.split, xa);
     }
   }
 }
@@ -227,6 +244,7 @@ struct GnBwdArgs {
   __half* g16a;          // fp16(dx * g16_scale) or null
   __half* g16b;
   float g16_scale;
+  int split;
 };
 
 // gradient w.r.t. the activation output pulled back through the resample, for x-pixel (h,w), channels c..c+8
@@ -329,7 +347,7 @@ __global__ void gn_bwd_kernel(const GnBwdArgs a) {
       if (o16) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) dx[j] *= a.g16_scale;
-        store8h(o16 + off, dx);
+        store_op8(o16, static_cast<long long>(b) * P + p, Cl, cl, a.split, dx);
       }
     }
   }
@@ -351,7 +369,8 @@ __global__ void gn_bwd_kernel(const GnBwdArgs a) {
 // ------------------------------------------------------------------------------------------------
 // 2-channel 3x3 im2col -> fp16 [B][H][W][64] (K index = tap*2 + ci, 18 used, rest zero); and its adjoint
 // ------------------------------------------------------------------------------------------------
-__global__ void im2col_c2_kernel(const float* __restrict__ x, int B, int H, int W, __half* __restrict__ col) {
+__global__ void im2col_c2_kernel(const float* __restrict__ x, int B, int H, int W, __half* __restrict__ col,
+                                 int split) {
   const long long P = static_cast<long long>(B) * H * W;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < P * 8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -376,7 +395,7 @@ __global__ void im2col_c2_kernel(const float* __restrict__ x, int B, int H, int 
       v[2 * j] = v0;
       v[2 * j + 1] = v1;
     }
-    store8h(col + p * 64 + chunk * 8, v);
+    store_op8(col, p, 64, chunk * 8, split, v);
   }
 }
 
@@ -655,6 +674,7 @@ extern "C" int buddy_gn_apply(const buddy_gn_desc* d, void* stream) {
   a.mode = d->mode;
   a.out = static_cast<__half*>(d->out);
   a.out_raw = static_cast<__half*>(d->out_raw);
+  a.split = d->split;
   const long long items = static_cast<long long>(d->mode == 2 ? (d->H / 2) * (d->W / 2) : d->H * d->W) *
                           ((d->Ca + d->Cb) / 8);
   gn_apply_kernel<<<dim3(grid_for(items, 256, 148 * 8), d->batch), 256, 0, STREAM>>>(a);
@@ -687,6 +707,7 @@ extern "C" int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, 
   a.g16a = static_cast<__half*>(g->g16a);
   a.g16b = static_cast<__half*>(g->g16b);
   a.g16_scale = g->g16_scale;
+  a.split = d->split;
   const int c8n = C / 8;
   const int threads = c8n * (256 / c8n > 0 ? 256 / c8n : 1);
   const long long ppb = threads / c8n;
@@ -703,9 +724,9 @@ extern "C" int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, 
   LAUNCH_END("gn_bwd_kernel<apply>");
 }
 
-extern "C" int buddy_im2col_c2(const float* x, int B, int H, int W, void* col, void* stream) {
+extern "C" int buddy_im2col_c2(const float* x, int B, int H, int W, void* col, int split, void* stream) {
   const long long items = static_cast<long long>(B) * H * W * 8;
-  im2col_c2_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(x, B, H, W, static_cast<__half*>(col));
+  im2col_c2_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(x, B, H, W, static_cast<__half*>(col), split);
   LAUNCH_END("im2col_c2_kernel");
 }
 extern "C" int buddy_col2im_c2(const float* dcol, int ld, int B, int H, int W, float* dx, int accumulate,

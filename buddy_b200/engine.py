@@ -1,0 +1,478 @@
+"""NCSN++ score-network engine: forward and data-gradient (VJP) as a sequence of buddy_b200 kernels.
+
+Graph = the shipped configuration of the reference (conf/network/ncsnpp.yaml; networks/ncsnpp.py:281-449,
+module map in SURVEY.md App. B): 20 BigGAN ResBlocks, one bottleneck attention block, input pyramid (Combine),
+output pyramid heads.  Activations are channels-last fp32 in HBM ([B, F=256, frames, C]); every tensor-core
+operand is an fp16 copy produced by the GroupNorm+SiLU kernel; all convolutions / NINs / attention products run
+on `ops.conv_gemm` (tcgen05).  Only the GroupNorm inputs (+ their statistics) are kept for the backward pass.
+
+This module only orchestrates kernels (pointers, shapes, order); it contains no arithmetic of its own apart from
+the one-time weight repacking.  Host-side tensors are torch CUDA tensors used as device-memory handles.
+"""
+import math
+
+import torch
+
+from . import ops
+from .ops import MODE_DOWN, MODE_NONE, MODE_UP
+
+INV_SQRT2 = 1.0 / math.sqrt(2.0)
+NF = 128
+CH_MULT = (1, 2, 2, 2)
+
+
+def _f16(t):
+    return t.to(torch.float16).contiguous()
+
+
+def _split_k(w, passes):
+    """fp32 [..., N, K] -> fp16 B operand [..., N, passes*K].
+
+    passes 1: [w_hi]; 2: [w_hi | w_hi] (pairs with A = [a_hi | a_lo]); 3: [w_hi | w_hi | w_lo] (A chunks wrap, so the
+    third block meets a_hi again): a_hi*w_hi + a_lo*w_hi + a_hi*w_lo accumulated in fp32 by one launch."""
+    hi = w.to(torch.float16)
+    if passes == 1:
+        return hi.contiguous()
+    if passes == 2:
+        return torch.cat([hi, hi], dim=-1).contiguous()
+    lo = (w - hi.float()).to(torch.float16)
+    return torch.cat([hi, hi, lo], dim=-1).contiguous()
+
+
+def _pack3x3(w, passes):
+    """[Cout, Cin, 3, 3] -> fwd B operand [9, Cout, p*Cin] and dgrad B operand [9, Cin, p*Cout] (taps flipped)."""
+    co, ci = w.shape[:2]
+    fwd = w.permute(2, 3, 0, 1).reshape(9, co, ci)
+    dgr = w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, ci, co)
+    return _split_k(fwd, passes), _split_k(dgr, passes)
+
+
+def _pad_rows(w, rows):
+    if w.shape[-2] >= rows:
+        return w
+    pad = torch.zeros(*w.shape[:-2], rows - w.shape[-2], w.shape[-1], dtype=w.dtype, device=w.device)
+    return torch.cat([w, pad], dim=-2)
+
+
+class _RB:
+    pass
+
+
+class Engine:
+    """Device-resident packed weights + forward / vjp drivers."""
+
+    PRECISIONS = {"fp16": 1, "fp16x2": 2, "fp16x3": 3}
+
+    def __init__(self, state_dict, device, precision="fp16x3"):
+        """precision: operand scheme of the conv GEMMs (all accumulate in fp32 on tcgen05):
+             "fp16"   one pass, 11-bit significands (what cuDNN's default TF32 path gives the reference on a GPU)
+             "fp16x2" activations split hi+lo, weights single
+             "fp16x3" activations and weights split hi+lo (three passes in one launch): fp32-class products"""
+        self.device = torch.device(device)
+        self.precision = precision
+        self.np = self.PRECISIONS[precision]
+        self.split = self.np > 1
+        self.am = 2 if self.split else 1
+        sd = {k: v.detach().to(self.device, torch.float32) for k, v in state_dict.items()}
+        self.sd = sd
+        f32 = lambda t: t.contiguous()
+        # ---- time embedding
+        self.fourier_W = f32(sd["all_modules.0.W"])
+        self.lin1 = (f32(sd["all_modules.1.weight"]), f32(sd["all_modules.1.bias"]))
+        self.lin2 = (f32(sd["all_modules.2.weight"]), f32(sd["all_modules.2.bias"]))
+        # ---- input conv 2 -> NF as an im2col GEMM (K index = tap*2 + ci, padded to 64)
+        w3 = sd["all_modules.3.weight"]  # [NF, 2, 3, 3]
+        w3c = torch.zeros(NF, 64, device=self.device)
+        w3c[:, :18] = w3.permute(0, 2, 3, 1).reshape(NF, 18)
+        self.in_w = _split_k(w3c, self.np)[None]                               # [1, NF, p*64]
+        self.in_wd = _split_k(w3c[:, :32].t().contiguous(), self.np)[None]     # [1, 32, p*NF]
+        self.in_b = f32(sd["all_modules.3.bias"])
+        # ---- walk the module list exactly as the reference builds it
+        self.rb = {}
+        self.comb = {}
+        self.heads = {}
+        i = 4
+        for lvl in range(len(CH_MULT)):
+            self._pack_rb(i)
+            i += 1
+            if lvl != len(CH_MULT) - 1:
+                self._pack_rb(i)
+                i += 1
+                self.comb[i] = (f32(sd[f"all_modules.{i}.Conv_0.weight"].reshape(-1, 2)),
+                                f32(sd[f"all_modules.{i}.Conv_0.bias"]))
+                i += 1
+        self._pack_rb(i)
+        self.attn_idx = i + 1
+        self._pack_attn(i + 1)
+        self._pack_rb(i + 2)
+        i += 3
+        self.up_levels = []
+        for lvl in reversed(range(len(CH_MULT))):
+            blocks = [i, i + 1]
+            self._pack_rb(i)
+            self._pack_rb(i + 1)
+            i += 2
+            self._pack_head(i)
+            head = i
+            i += 2
+            upb = None
+            if lvl != 0:
+                self._pack_rb(i)
+                upb = i
+                i += 1
+            self.up_levels.append((blocks, head, upb))
+        assert i == 36
+        ow = sd["output_layer.weight"].reshape(2, 2)
+        self.out_m = [float(v) for v in ow.reshape(-1).tolist()]
+        self.out_mT = [float(v) for v in ow.t().reshape(-1).tolist()]
+        self.out_b = [float(v) for v in sd["output_layer.bias"].tolist()]
+        self._gsum = None
+
+    # ------------------------------------------------------------------ packing
+    def _pack_rb(self, i):
+        sd, p = self.sd, f"all_modules.{i}."
+        r = _RB()
+        r.g0, r.b0 = sd[p + "GroupNorm_0.weight"].contiguous(), sd[p + "GroupNorm_0.bias"].contiguous()
+        r.g1, r.b1 = sd[p + "GroupNorm_1.weight"].contiguous(), sd[p + "GroupNorm_1.bias"].contiguous()
+        r.w0, r.wd0 = _pack3x3(sd[p + "Conv_0.weight"], self.np)
+        r.w1, r.wd1 = _pack3x3(sd[p + "Conv_1.weight"], self.np)
+        r.bias0 = sd[p + "Conv_0.bias"].contiguous()
+        r.cin, r.cout = sd[p + "Conv_0.weight"].shape[1], sd[p + "Conv_0.weight"].shape[0]
+        r.dense = (sd[p + "Dense_0.weight"].contiguous(), sd[p + "Dense_0.bias"].contiguous())
+        r.has_skip_conv = (p + "Conv_2.weight") in sd
+        if r.has_skip_conv:
+            w2 = sd[p + "Conv_2.weight"].reshape(r.cout, r.cin)
+            r.w2 = _split_k(w2, self.np)                            # [Cout, p*Cin]
+            r.wd2 = _split_k(w2.t().contiguous(), self.np)[None]    # [1, Cin, p*Cout]
+            r.bias1 = (sd[p + "Conv_1.bias"] + sd[p + "Conv_2.bias"]).contiguous()
+        else:
+            r.bias1 = sd[p + "Conv_1.bias"].contiguous()
+        self.rb[i] = r
+
+    def _pack_attn(self, i):
+        sd, p = self.sd, f"all_modules.{i}."
+        a = _RB()
+        a.g, a.b = sd[p + "GroupNorm_0.weight"].contiguous(), sd[p + "GroupNorm_0.bias"].contiguous()
+        ws = [sd[p + f"NIN_{n}.W"] for n in range(4)]  # (in, out)
+        a.c = ws[0].shape[0]
+        a.wqkv = _f16(torch.cat([w.t() for w in ws[:3]], dim=0))[None]       # [1, 3C, C]  rows = outputs
+        a.bqkv = torch.cat([sd[p + f"NIN_{n}.b"] for n in range(3)]).contiguous()
+        a.wqkv_d = _f16(torch.cat(ws[:3], dim=1))[None]                      # [1, C, 3C]  dgrad: rows = inputs
+        a.w3 = _f16(ws[3].t())[None]                                         # [1, C, C]
+        a.w3_d = _f16(ws[3])[None]
+        a.b3 = sd[p + "NIN_3.b"].contiguous()
+        self.attn = a
+
+    def _pack_head(self, i):
+        sd = self.sd
+        h = _RB()
+        h.g, h.b = sd[f"all_modules.{i}.weight"].contiguous(), sd[f"all_modules.{i}.bias"].contiguous()
+        w = sd[f"all_modules.{i + 1}.weight"]  # [2, C, 3, 3]
+        c = w.shape[1]
+        fwd = w.permute(2, 3, 0, 1).reshape(9, 2, c)
+        h.w = _split_k(_pad_rows(fwd, 16), self.np)   # [9, 16, p*C]
+        bias = torch.zeros(16, device=self.device)
+        bias[:2] = sd[f"all_modules.{i + 1}.bias"]
+        h.bias = bias
+        # dgrad as an im2col GEMM: dcol[p][tap'*2+co] = dP[p + tap' offset][co];  wd[c][tap'*2+co] = W[co][c][2-ky'][2-kx']
+        wd = torch.zeros(c, 64, device=self.device)
+        wd[:, :18] = w.flip(2, 3).permute(1, 2, 3, 0).reshape(c, 18)
+        h.wd = _split_k(wd, self.np)[None]            # [1, C, p*64]
+        h.c = c
+        self.heads[i] = h
+
+    # ------------------------------------------------------------------ helpers
+    def _scratch_gsum(self, B):
+        if self._gsum is None or self._gsum.shape[0] < B:
+            self._gsum = torch.empty(B, 64, 2, device=self.device, dtype=torch.float64)
+        return self._gsum
+
+    def _zeros_stats(self, B, C):
+        return torch.zeros(B, C // 4, 2, device=self.device, dtype=torch.float64)
+
+    def time_bias(self, time_cond):
+        """Per-ResBlock additive bias Dense_0(SiLU(temb)) [B, Cout] for every block (ncsnpp.py:299-318)."""
+        B = time_cond.shape[0]
+        dev = self.device
+        emb = torch.empty(B, 2 * NF, device=dev)
+        ops.fourier_features(time_cond.contiguous(), self.fourier_W, emb)
+        t1 = torch.empty(B, 4 * NF, device=dev)
+        ops.dense(emb, self.lin1[0], self.lin1[1], t1)
+        t2 = torch.empty(B, 4 * NF, device=dev)
+        ops.dense(t1, self.lin2[0], self.lin2[1], t2, act_in=True)
+        out = {}
+        for i, r in self.rb.items():
+            o = torch.empty(B, r.cout, device=dev)
+            ops.dense(t2, r.dense[0], r.dense[1], o, act_in=True)
+            out[i] = o
+        return out
+
+    # ------------------------------------------------------------------ ResBlock
+    def _rb_fwd(self, i, xa, sa, xb, sb, tb, mode, save):
+        r = self.rb[i]
+        B, H, W, Ca = xa.shape
+        C = Ca + (xb.shape[3] if xb is not None else 0)
+        assert C == r.cin, (i, C, r.cin)
+        Ho, Wo = (2 * H, 2 * W) if mode == MODE_UP else ((H // 2, W // 2) if mode == MODE_DOWN else (H, W))
+        dev = self.device
+        a0 = torch.empty(B, Ho, Wo, C * self.am, device=dev, dtype=torch.float16)
+        raw = torch.empty_like(a0) if r.has_skip_conv else None
+        ops.gn_apply(xa, sa, r.g0, r.b0, a0, xb=xb, sb=sb, silu=True, mode=mode, out_raw=raw, split=self.split)
+        h1 = torch.empty(B, Ho, Wo, r.cout, device=dev)
+        s1 = self._zeros_stats(B, r.cout)
+        ops.conv_gemm(a0, r.w0, h1, taps=9, n_total=r.cout, bias=r.bias0, bias_b=tb[i], stats=s1)
+        del a0
+        a1 = torch.empty(B, Ho, Wo, r.cout * self.am, device=dev, dtype=torch.float16)
+        ops.gn_apply(h1, s1, r.g1, r.b1, a1, silu=True, split=self.split)
+        out = torch.empty(B, Ho, Wo, r.cout, device=dev)
+        so = self._zeros_stats(B, r.cout)
+        if r.has_skip_conv:
+            ops.conv_gemm(a1, r.w1, out, taps=9, n_total=r.cout, a2=raw, w2=r.w2, bias=r.bias1, scale=INV_SQRT2,
+                          stats=so)
+        else:
+            assert mode == MODE_NONE and xb is None
+            ops.conv_gemm(a1, r.w1, out, taps=9, n_total=r.cout, bias=r.bias1, resid=xa, scale=INV_SQRT2, stats=so)
+        if save is not None:
+            save[i] = (xa, sa, xb, sb, h1, s1, mode)
+        return out, so
+
+    def _rb_bwd(self, i, saved, g16, dout32, extra_a=None, want_a32=True, want_a16=True, a16_scale=INV_SQRT2):
+        """g16 = fp16(dout/sqrt2); returns (dxa32, g16a, dxb32)."""
+        r = self.rb[i]
+        xa, sa, xb, sb, h1, s1, mode = saved[i]
+        B, Ho, Wo, _ = h1.shape
+        dev = self.device
+        gsum = self._scratch_gsum(B)
+        da1 = torch.empty(B, Ho, Wo, r.cout, device=dev)
+        ops.conv_gemm(g16, r.wd1, da1, taps=9, n_total=r.cout)
+        dh1 = torch.empty(B, Ho, Wo, r.cout * self.am, device=dev, dtype=torch.float16)
+        ops.gn_bwd(h1, s1, r.g1, r.b1, da1, gsum, silu=True, g16a=dh1, g16_scale=1.0, split=self.split)
+        del da1
+        da0 = torch.empty(B, Ho, Wo, r.cin, device=dev)
+        ops.conv_gemm(dh1, r.wd0, da0, taps=9, n_total=r.cin)
+        del dh1
+        if r.has_skip_conv:
+            dsk = torch.empty(B, Ho, Wo, r.cin, device=dev)
+            ops.conv_gemm(g16, r.wd2, dsk, taps=1, n_total=r.cin)
+            skip_scale = 1.0
+        else:
+            dsk, skip_scale = dout32, INV_SQRT2
+        Ca = xa.shape[3]
+        dxa = torch.empty_like(xa) if want_a32 else None
+        g16a = (torch.empty(*xa.shape[:3], Ca * self.am, device=dev, dtype=torch.float16) if want_a16 else None)
+        dxb = torch.empty_like(xb) if xb is not None else None
+        ops.gn_bwd(xa, sa, r.g0, r.b0, da0, gsum, xb=xb, sb=sb, silu=True, mode=mode, dskip=dsk, skip_scale=skip_scale,
+                   extra_a=extra_a, dxa=dxa, dxb=dxb, g16a=g16a, g16_scale=a16_scale, split=self.split)
+        return dxa, g16a, dxb
+
+    # ------------------------------------------------------------------ attention
+    def _attn_fwd(self, x, sx, save):
+        a = self.attn
+        B, H, W, C = x.shape
+        N = H * W
+        dev = self.device
+        hn = torch.empty(B, H, W, C, device=dev, dtype=torch.float16)
+        ops.gn_apply(x, sx, a.g, a.b, hn, silu=False)
+        qkv = torch.empty(B, 1, N, 3 * C, device=dev, dtype=torch.float16)
+        ops.conv_gemm(hn.view(B, 1, N, C), a.wqkv, qkv, taps=1, n_total=3 * C, bias=a.bqkv)
+        del hn
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        S = torch.empty(B, 1, N, N, device=dev)
+        ops.conv_gemm(q, k[:, 0], S, taps=1, n_total=N, b_batched=True, scale=float(C) ** -0.5)
+        P = torch.empty(B, N, N, device=dev, dtype=torch.float16)
+        ops.softmax_fwd(S, P)
+        del S
+        vT = torch.empty(B, C, N, device=dev, dtype=torch.float16)
+        ops.transpose_h(v[:, 0], vT)
+        o = torch.empty(B, 1, N, C, device=dev, dtype=torch.float16)
+        ops.conv_gemm(P.view(B, 1, N, N), vT, o, taps=1, n_total=C, b_batched=True)
+        out = torch.empty(B, H, W, C, device=dev)
+        so = self._zeros_stats(B, C)
+        ops.conv_gemm(o.view(B, H, W, C), a.w3, out, taps=1, n_total=C, bias=a.b3, resid=x, scale=INV_SQRT2, stats=so)
+        if save is not None:
+            save["attn"] = (x, sx, qkv, P)
+        return out, so
+
+    def _attn_bwd(self, saved, g16, dout32):
+        a = self.attn
+        x, sx, qkv, P = saved["attn"]
+        B, H, W, C = x.shape
+        N = H * W
+        dev = self.device
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        do = torch.empty(B, 1, N, C, device=dev, dtype=torch.float16)
+        ops.conv_gemm(g16.view(B, 1, N, C * self.am)[..., :C], a.w3_d, do, taps=1, n_total=C)
+        doT = torch.empty(B, C, N, device=dev, dtype=torch.float16)
+        ops.transpose_h(do[:, 0], doT)
+        PT = torch.empty(B, N, N, device=dev, dtype=torch.float16)
+        ops.transpose_h(P, PT)
+        dqkv = torch.empty(B, 1, N, 3 * C, device=dev, dtype=torch.float16)
+        ops.conv_gemm(PT.view(B, 1, N, N), doT, dqkv, taps=1, n_total=C, b_batched=True, col_off=2 * C, ldc=3 * C)
+        del PT, doT
+        dP = torch.empty(B, 1, N, N, device=dev)
+        ops.conv_gemm(do, v[:, 0], dP, taps=1, n_total=N, b_batched=True)
+        dS = torch.empty(B, N, N, device=dev, dtype=torch.float16)
+        ops.softmax_bwd(P, dP, float(C) ** -0.5, dS)
+        del dP
+        kT = torch.empty(B, C, N, device=dev, dtype=torch.float16)
+        ops.transpose_h(k[:, 0], kT)
+        ops.conv_gemm(dS.view(B, 1, N, N), kT, dqkv, taps=1, n_total=C, b_batched=True, col_off=0, ldc=3 * C)
+        dST = torch.empty(B, N, N, device=dev, dtype=torch.float16)
+        ops.transpose_h(dS, dST)
+        qT = kT
+        ops.transpose_h(q[:, 0], qT)
+        ops.conv_gemm(dST.view(B, 1, N, N), qT, dqkv, taps=1, n_total=C, b_batched=True, col_off=C, ldc=3 * C)
+        del dS, dST
+        dhn = torch.empty(B, H, W, C, device=dev)
+        ops.conv_gemm(dqkv.view(B, H, W, 3 * C), a.wqkv_d, dhn, taps=1, n_total=C)
+        dx = torch.empty_like(x)
+        g16x = torch.empty(B, H, W, C * self.am, device=dev, dtype=torch.float16)
+        ops.gn_bwd(x, sx, a.g, a.b, dhn, self._scratch_gsum(B), silu=False, dskip=dout32, skip_scale=INV_SQRT2, dxa=dx,
+                   g16a=g16x, g16_scale=INV_SQRT2, split=self.split)
+        return dx, g16x
+
+    # ------------------------------------------------------------------ pyramid heads
+    def _head_fwd(self, i, h, sh, save):
+        hd = self.heads[i]
+        B, H, W, C = h.shape
+        a = torch.empty(B, H, W, C * self.am, device=self.device, dtype=torch.float16)
+        ops.gn_apply(h, sh, hd.g, hd.b, a, silu=True, split=self.split)
+        out = torch.empty(B, H, W, 2, device=self.device)
+        ops.conv_gemm(a, hd.w, out, taps=9, n_total=2, n_tile=16, bias=hd.bias)
+        return out
+
+    def _head_bwd(self, i, h, sh, dP, extra, want32):
+        """dP fp32 [B,H,W,2] -> gradient w.r.t. h (plus `extra`), fp32 (optional) and fp16/sqrt2."""
+        hd = self.heads[i]
+        B, H, W, C = h.shape
+        dev = self.device
+        col = torch.empty(B, H, W, 64 * self.am, device=dev, dtype=torch.float16)
+        ops.im2col_c2(dP, col, split=self.split)
+        da = torch.empty(B, H, W, C, device=dev)
+        ops.conv_gemm(col, hd.wd, da, taps=1, n_total=C)
+        dx = torch.empty_like(h) if want32 else None
+        g16 = torch.empty(B, H, W, C * self.am, device=dev, dtype=torch.float16)
+        ops.gn_bwd(h, sh, hd.g, hd.b, da, self._scratch_gsum(B), silu=True, extra_a=extra, dxa=dx, g16a=g16,
+                   g16_scale=INV_SQRT2, split=self.split)
+        return dx, g16
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, spec, time_cond, save=True):
+        """spec fp32 [B, 256, Tp, 2] (re, im channels-last), time_cond fp32 [B] -> (out [B,256,Tp,2], ctx)."""
+        assert spec.dtype == torch.float32 and spec.is_contiguous() and spec.shape[1] == 256 and spec.shape[3] == 2
+        B, H, W, _ = spec.shape
+        assert W % 16 == 0, "frame count must be a multiple of 16 (NCSNppTime.stft pads to it)"
+        dev = self.device
+        ctx = {} if save else None
+        tb = self.time_bias(time_cond)
+        # input pyramid (pyramid_downsample = 2x2 mean, ncsnpp.py:355-357)
+        pyr = [spec]
+        for _ in range(3):
+            p = pyr[-1]
+            pyr.append(ops.resample_c2(p, 0, torch.empty(B, p.shape[1] // 2, p.shape[2] // 2, 2, device=dev)))
+        col = torch.empty(B, H, W, 64 * self.am, device=dev, dtype=torch.float16)
+        ops.im2col_c2(spec, col, split=self.split)
+        h = torch.empty(B, H, W, NF, device=dev)
+        sh = self._zeros_stats(B, NF)
+        ops.conv_gemm(col, self.in_w, h, taps=1, n_total=NF, bias=self.in_b, stats=sh)
+        del col
+        hs = [(h, sh)]
+        i = 4
+        for lvl in range(4):
+            h, sh = self._rb_fwd(i, hs[-1][0], hs[-1][1], None, None, tb, MODE_NONE, ctx)
+            i += 1
+            hs.append((h, sh))
+            if lvl != 3:
+                h, sh = self._rb_fwd(i, h, sh, None, None, tb, MODE_DOWN, ctx)
+                i += 1
+                w, b = self.comb[i]
+                hc = ops.combine_fwd(h, pyr[lvl + 1], w, b, torch.empty_like(h))
+                sc = ops.gn_stats(hc)
+                i += 1
+                hs.append((hc, sc))
+        h, sh = self._rb_fwd(i, hs[-1][0], hs[-1][1], None, None, tb, MODE_NONE, ctx)
+        h, sh = self._attn_fwd(h, sh, ctx)
+        h, sh = self._rb_fwd(i + 2, h, sh, None, None, tb, MODE_NONE, ctx)
+        pyramid = None
+        head_in = {}
+        for (blocks, head, upb) in self.up_levels:
+            for bi in blocks:
+                xb, sb = hs.pop()
+                h, sh = self._rb_fwd(bi, h, sh, xb, sb, tb, MODE_NONE, ctx)
+            ph = self._head_fwd(head, h, sh, ctx)
+            head_in[head] = (h, sh)
+            if pyramid is None:
+                pyramid = ph
+            else:
+                pyramid = ops.resample_c2(pyramid, 1, torch.empty_like(ph), add=ph)
+            if upb is not None:
+                h, sh = self._rb_fwd(upb, h, sh, None, None, tb, MODE_UP, ctx)
+        assert not hs
+        out = ops.affine_c2(pyramid, self.out_m, self.out_b, torch.empty_like(pyramid))
+        if save:
+            ctx["head_in"] = head_in
+            ctx["shape"] = (B, H, W)
+        return out, ctx
+
+    # ------------------------------------------------------------------ data-gradient
+    def vjp(self, ctx, dout):
+        """dout fp32 [B,256,Tp,2] (gradient w.r.t. forward's output) -> gradient w.r.t. `spec`."""
+        B, H, W = ctx["shape"]
+        dev = self.device
+        assert dout.shape == (B, H, W, 2) and dout.is_contiguous()
+        zero_b = [0.0, 0.0]
+        dP = [ops.affine_c2(dout, self.out_mT, zero_b, torch.empty_like(dout))]   # level 0 (full res)
+        for _ in range(3):
+            p = dP[-1]
+            dP.append(ops.resample_c2(p, 3, torch.empty(B, p.shape[1] // 2, p.shape[2] // 2, 2, device=dev)))
+        partial_hs = {}     # index into hs (0..7) -> fp32 partial gradient from the up path
+        hs_idx = 0          # the up path pops hs in reverse: 7,6,...,0 ; walking it backwards we see 0,1,...,7
+        carry32 = None      # partial fp32 gradient of the tensor feeding an `up` block (added by the head's gn_bwd)
+        g16 = None
+        for lvl_pos in reversed(range(4)):          # up_levels[3] is the full-resolution level, processed first
+            blocks, head, upb = self.up_levels[lvl_pos]
+            if upb is not None:
+                # `up` block: consumes h (also seen by this level's head) -> partial gradient only
+                carry32, _, _ = self._rb_bwd(upb, ctx, g16, None, want_a32=True, want_a16=False)
+            else:
+                carry32 = None
+            h, sh = ctx["head_in"][head]
+            # the tensor under the head is produced by blocks[1] (has a skip conv): fp16 only is enough
+            _, g16 = self._head_bwd(head, h, sh, dP[3 - lvl_pos], carry32, want32=False)
+            for bi in reversed(blocks):
+                first_of_level = (bi == blocks[0])
+                # producer of the h-part: blocks[0] for blocks[1]; for blocks[0]: the previous level's `up` block
+                # (skip conv) or, at the bottleneck level, ResBlock 16 (identity skip -> needs fp32 as well)
+                need32 = first_of_level and lvl_pos == 0
+                d32, g16, dxb = self._rb_bwd(bi, ctx, g16, None, want_a32=need32, want_a16=True)
+                partial_hs[hs_idx] = dxb
+                hs_idx += 1
+        # bottleneck: RB16 <- attention <- RB14
+        i16 = self.attn_idx + 1
+        d32, g16, _ = self._rb_bwd(i16, ctx, g16, d32, want_a32=True)
+        d32, g16 = self._attn_bwd(ctx, g16, d32)
+        d32, g16, _ = self._rb_bwd(self.attn_idx - 1, ctx, g16, d32, extra_a=partial_hs[7], want_a32=True)
+        # down path, backwards.  hs index k: 7 = RB13 out, 6 = Combine12, 5 = RB10, 4 = Combine9, 3 = RB7,
+        # 2 = Combine6, 1 = RB4, 0 = input conv
+        dpyr = {}
+        i = self.attn_idx - 2       # 13
+        for lvl in (3, 2, 1):
+            # plain block at this level: input is the Combine output hs[2*lvl]
+            d32, g16, _ = self._rb_bwd(i, ctx, g16, d32, extra_a=partial_hs[2 * lvl], want_a32=True)
+            w, _ = self.comb[i - 1]
+            dpyr[lvl] = ops.combine_bwd(d32, w, torch.empty(B, d32.shape[1], d32.shape[2], 2, device=dev))
+            # down block (has skip conv): input hs[2*lvl-1]
+            d32, g16, _ = self._rb_bwd(i - 2, ctx, g16, None, extra_a=partial_hs[2 * lvl - 1], want_a32=True)
+            i -= 3
+        # RB4 (identity skip) : input hs[0]; its producer is the input conv -> fp16 at scale 1
+        _, g16, _ = self._rb_bwd(4, ctx, g16, d32, extra_a=partial_hs[0], want_a32=False, a16_scale=1.0)
+        dcol = torch.empty(B, H, W, 32, device=dev)
+        ops.conv_gemm(g16, self.in_wd, dcol, taps=1, n_total=32)
+        dx = torch.empty(B, H, W, 2, device=dev)
+        ops.col2im_c2(dcol, dx)
+        # input pyramid adjoint: pyr[l+1] = mean4(pyr[l])
+        acc = dpyr[3]
+        for lvl in (2, 1):
+            acc = ops.resample_c2(acc, 2, dpyr[lvl], accumulate=True)
+        ops.resample_c2(acc, 2, dx, accumulate=True)
+        return dx

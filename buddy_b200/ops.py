@@ -47,11 +47,13 @@ def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=N
         d.b2 = ptr(w2)
         d.b2_rows = w2.shape[0]
         d.b2_stride_n = w2.stride(0)
+        d.k2_total = w2.shape[1]
     d.b = ptr(w)
     d.b_rows = w.shape[1]
     d.b_t = w.shape[0]
     d.b_stride_n, d.b_stride_t = w.stride(1), w.stride(0)
-    assert w.shape[2] == C, (w.shape, C)
+    assert w.shape[2] % 64 == 0 and (w.shape[2] == C or w.shape[2] > C), (w.shape, C)
+    d.k_total = w.shape[2]
     d.batch, d.H, d.W = B, H, W
     d.taps = taps
     d.b_batched = 1 if b_batched else 0
@@ -96,7 +98,7 @@ def gn_stats(x, stats=None):
     return stats
 
 
-def _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps):
+def _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps, split=False):
     B, H, W, Ca = xa.shape
     d = GnDesc()
     d.xa, d.Ca, d.stats_a = ptr(xa), Ca, ptr(sa)
@@ -106,14 +108,15 @@ def _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps):
     d.gamma, d.beta = ptr(gamma), ptr(beta)
     d.batch, d.H, d.W = B, H, W
     d.groups, d.eps, d.silu, d.mode = groups, eps, int(silu), mode
+    d.split = int(split)
     return d
 
 
 def gn_apply(xa, sa, gamma, beta, out, *, xb=None, sb=None, groups=32, silu=True, mode=MODE_NONE, out_raw=None,
-             eps=1e-6):
+             eps=1e-6, split=False):
     """out(fp16) = resample(act(GroupNorm([xa|xb]))); out_raw(fp16) = resample([xa|xb])."""
     assert xa.dtype == torch.float32 and xa.is_contiguous() and out.dtype == torch.float16
-    d = _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps)
+    d = _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps, split)
     d.out, d.out_raw = ptr(out), ptr(out_raw)
     check(lib().buddy_gn_apply(ctypes.byref(d), stream_ptr()), "buddy_gn_apply")
     return out
@@ -121,8 +124,8 @@ def gn_apply(xa, sa, gamma, beta, out, *, xb=None, sb=None, groups=32, silu=True
 
 def gn_bwd(xa, sa, gamma, beta, da, gsum, *, xb=None, sb=None, groups=32, silu=True, mode=MODE_NONE, dskip=None,
            skip_scale=1.0, extra_a=None, extra_b=None, dxa=None, dxb=None, g16a=None, g16b=None, g16_scale=1.0,
-           eps=1e-6):
-    d = _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps)
+           eps=1e-6, split=False):
+    d = _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps, split)
     g = GnBwdDesc()
     g.da, g.dskip, g.skip_scale = ptr(da), ptr(dskip), skip_scale
     g.extra_a, g.extra_b, g.gsum = ptr(extra_a), ptr(extra_b), ptr(gsum)
@@ -131,9 +134,10 @@ def gn_bwd(xa, sa, gamma, beta, da, gsum, *, xb=None, sb=None, groups=32, silu=T
     check(lib().buddy_gn_bwd(ctypes.byref(d), ctypes.byref(g), stream_ptr()), "buddy_gn_bwd")
 
 
-def im2col_c2(x, col):
+def im2col_c2(x, col, split=False):
     B, H, W, _ = x.shape
-    check(lib().buddy_im2col_c2(ptr(x), c_int(B), c_int(H), c_int(W), ptr(col), stream_ptr()), "buddy_im2col_c2")
+    check(lib().buddy_im2col_c2(ptr(x), c_int(B), c_int(H), c_int(W), ptr(col), c_int(int(split)), stream_ptr()),
+          "buddy_im2col_c2")
     return col
 
 

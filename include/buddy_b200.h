@@ -84,6 +84,11 @@ typedef struct buddy_gemm_desc {
   float scale;
   double* stats; /* or NULL */
   int32_t max_ctas; /* 0 = one persistent CTA per SM */
+  /* Split-precision operands.  Contraction length per tap of Bw / Bw2 (0 = a_c / a2_c).  When larger than the
+   * A tensor's channel count the A-side chunk index wraps (chunk % (a_c/64)): with A = [a_hi | a_lo] and
+   * Bw = [w_hi | w_hi | w_lo] one launch accumulates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in fp32 (fp32-class
+   * products from fp16 tensor-core operands). */
+  int32_t k_total, k2_total;
 } buddy_gemm_desc;
 
 int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream);
@@ -113,8 +118,9 @@ typedef struct buddy_gn_desc {
   float eps;
   int32_t silu; /* 1: SiLU after the affine */
   int32_t mode; /* 0 none, 1 nearest x2 upsample after the activation, 2 2x2 mean after the activation */
-  void* out;     /* fp16 [batch][H'][W'][Ca+Cb] */
+  void* out;     /* fp16 [batch][H'][W'][Ca+Cb]   (split: [..][2*(Ca+Cb)] = [hi | lo]) */
   void* out_raw; /* optional fp16 copy of the (resampled) input x, operand of the 1x1 skip conv */
+  int32_t split; /* 1: every fp16 output carries a second half lo = fp16(v - float(hi)) */
 } buddy_gn_desc;
 
 typedef struct buddy_gn_bwd_desc {
@@ -143,7 +149,7 @@ int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, void* strea
  *            (pyramid_upsample, layerspp.py:117), 2 = adjoint of 0, 3 = adjoint of 1.
  * combine_*: Combine.forward, method 'sum' (layerspp.py:52-59): out = h + Conv1x1(pyr) and d/dpyr.
  * affine_c2: 2x2 affine map per pixel = output_layer (ncsnpp.py:113,445) and its adjoint. */
-int buddy_im2col_c2(const float* x, int B, int H, int W, void* col, void* stream);
+int buddy_im2col_c2(const float* x, int B, int H, int W, void* col, int split /* [64 hi | 64 lo] */, void* stream);
 int buddy_col2im_c2(const float* dcol, int ld, int B, int H, int W, float* dx, int accumulate, void* stream);
 int buddy_resample_c2(const float* in, int B, int Hin, int Win, int mode, const float* add, float* out,
                       int accumulate, void* stream);

@@ -51,7 +51,20 @@ def _down2(x):  # naive_downsample_2d, :66-69 (== 2x2 mean)
     return F.avg_pool2d(x, 2)
 
 
+RECORD = None  # debugging aid: set to a dict to capture every block output ({module index: tensor})
+
+
+def _rec(i, t):
+    if RECORD is not None:
+        RECORD[i] = t.detach()
+    return t
+
+
 def _resblock(sd, i, x, temb_act, up=False, down=False):
+    return _rec(i, _resblock_impl(sd, i, x, temb_act, up, down))
+
+
+def _resblock_impl(sd, i, x, temb_act, up=False, down=False):
     """ResnetBlockBigGANpp.forward, layerspp.py:242-274 (dropout p=0 is the identity)."""
     p = f"all_modules.{i}"
     h = F.silu(_gn(x, sd, p + ".GroupNorm_0"))
@@ -96,7 +109,7 @@ def ncsnpp_forward(sd, spec, time_cond):
     x = torch.cat([spec.real, spec.imag], dim=1)  # (B,2,F,T)   :291-297
     ta = time_embedding(sd, time_cond)
     pyr_in = x
-    hs = [F.conv2d(x, sd["all_modules.3.weight"], sd["all_modules.3.bias"], padding=1)]
+    hs = [_rec(3, F.conv2d(x, sd["all_modules.3.weight"], sd["all_modules.3.bias"], padding=1))]
     i = 4
     for lvl in range(4):
         h = _resblock(sd, i, hs[-1], ta)
@@ -107,10 +120,11 @@ def ncsnpp_forward(sd, spec, time_cond):
             i += 1
             pyr_in = F.avg_pool2d(pyr_in, 2)  # pyramid_downsample (with_conv=False), layerspp.py:156
             h = F.conv2d(pyr_in, sd[f"all_modules.{i}.Conv_0.weight"], sd[f"all_modules.{i}.Conv_0.bias"]) + h
+            _rec(i, h)
             i += 1
             hs.append(h)
     h = _resblock(sd, i, hs[-1], ta)
-    h = _attn(sd, i + 1, h)
+    h = _rec(i + 1, _attn(sd, i + 1, h))
     h = _resblock(sd, i + 2, h, ta)
     i += 3
     pyramid = None
@@ -120,6 +134,7 @@ def ncsnpp_forward(sd, spec, time_cond):
             i += 1
         ph = F.silu(F.group_norm(h, 32, sd[f"all_modules.{i}.weight"], sd[f"all_modules.{i}.bias"], eps=1e-6))
         ph = F.conv2d(ph, sd[f"all_modules.{i + 1}.weight"], sd[f"all_modules.{i + 1}.bias"], padding=1)
+        _rec(i + 1, ph)
         i += 2
         pyramid = ph if pyramid is None else F.interpolate(pyramid, scale_factor=2, mode="nearest") + ph
         if lvl != 0:
