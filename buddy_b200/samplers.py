@@ -1,0 +1,295 @@
+"""Drop-in samplers: `Sampler`, `EulerHeunSampler`, `EulerHeunSamplerDPS`
+(reference testing/Sampler.py:6-72, testing/EulerHeunSampler.py:6-107, testing/EulerHeunSamplerDPS.py:14-204).
+
+Same constructor `(model, diff_params, args)`, same methods and return values, so Hydra can swap them in by
+`tester.sampler._target_=buddy_b200.samplers.EulerHeunSamplerDPS` with `test.py` unchanged.  Differences by design
+(SURVEY.md App. C2/C7):
+  * a batch is B independent utterances: every `.std()`, `torch.norm`, loss mean is per utterance
+    (the reference only ever runs B = 1, where the two coincide);
+  * the whole loop stays on the device: the schedule, gamma, t_hat and every coefficient are host floats computed
+    up-front, so there is no device->host sync inside the loop; noise comes from a per-utterance Philox stream
+    (or from `self.noise_source`, an iterator of pre-drawn tensors, for parity tests);
+  * the likelihood gradient is not taken by autograd but by the hand-written VJP kernels.
+"""
+import math
+
+import torch
+
+from . import ops
+from .ncsnpp import NCSNppTime
+from .spectral import LossSTFT, RirConv
+
+
+def _get(cfg, name, default=None):
+    if cfg is None:
+        return default
+    if isinstance(cfg, dict):
+        return cfg.get(name, default)
+    return getattr(cfg, name, default) if default is not None or hasattr(cfg, name) else default
+
+
+class Sampler:
+    def __init__(self, model, diff_params, args):
+        self.model = model.eval()
+        self.diff_params = diff_params
+        self.args = args
+        sp = args.tester.sampling_params
+        self.sde_hp = diff_params.sde_hp if sp.same_as_training else sp.sde_hp
+        self.T = sp.T
+        self.step_counter = 0
+        # extensions (all optional)
+        self.noise_source = None          # iterator of pre-drawn N(0,1) tensors (parity tests)
+        self.seed_base = 3000             # Philox stream of utterance b = seed_base + utterance_offset + b
+        self.utterance_offset = 0         # global index of this rank's first utterance (multi-GPU shards)
+        self.micro_batch = 16             # utterances per network evaluation
+        self._draw = 0
+
+    # ---- schedule (Sampler.py:39-56) -----------------------------------------------------------------
+    def create_schedule(self, sigma_min=None, sigma_max=None, rho=None, T=None):
+        sigma_min = self.sde_hp.sigma_min if sigma_min is None else sigma_min
+        sigma_max = self.sde_hp.sigma_max if sigma_max is None else sigma_max
+        rho = self.sde_hp.rho if rho is None else rho
+        T = self.T if T is None else T
+        if self.args.tester.sampling_params.schedule == "edm":
+            a = torch.arange(0, T + 1)
+            t = (sigma_max ** (1 / rho) + a / (T - 1) * (sigma_min ** (1 / rho) - sigma_max ** (1 / rho))) ** rho
+            t[-1] = 0
+            return t
+        raise NotImplementedError(f"schedule {self.args.tester.sampling_params.schedule} not implemented")
+
+    def Tweedie2score(self, tweedie, xt, t):
+        return self.diff_params.Tweedie2score(tweedie, xt, t)
+
+    def get_Tweedie_estimate(self, x, t_i):
+        return self.diff_params.denoiser(x.unsqueeze(1), self.model, t_i).squeeze(1)
+
+    # ---- noise ---------------------------------------------------------------------------------------
+    def _randn(self, shape, device):
+        if self.noise_source is not None:
+            z = next(self.noise_source).to(device=device, dtype=torch.float32)
+            assert tuple(z.shape) == tuple(shape), (z.shape, shape)
+            return z.contiguous()
+        B, n = shape
+        seeds = torch.arange(B, dtype=torch.int64, device=device) + (self.seed_base + self.utterance_offset)
+        out = torch.empty(B, n, device=device)
+        ops.philox_normal(seeds, self._draw, out)
+        self._draw += 1
+        return out
+
+
+def _vec(v, B, device):
+    return torch.full((B,), float(v), device=device, dtype=torch.float32)
+
+
+class EulerHeunSampler(Sampler):
+    def __init__(self, model, diff_params, args):
+        super().__init__(model, diff_params, args)
+        sp = self.args.tester.sampling_params
+        self.Schurn, self.Snoise, self.Stmin, self.Stmax, self.order = sp.Schurn, sp.Snoise, sp.Stmin, sp.Stmax, sp.order
+
+    def initialize_x(self, shape, device, schedule):
+        return float(schedule[0]) * self._randn(shape, device)
+
+    def get_gamma(self, t):
+        N = t.shape[0]
+        gamma = torch.zeros(t.shape)
+        idx = torch.logical_and(t > self.Stmin, t < self.Stmax)
+        gamma[idx] = gamma[idx] + torch.min(torch.Tensor([self.Schurn / N, 2 ** (1 / 2) - 1]))
+        return gamma
+
+    def stochastic_timestep(self, x, t, gamma, Snoise=1):
+        t, gamma = float(t), float(gamma)
+        t_hat = t + gamma * t
+        eps = self._randn(x.shape, x.device)
+        B = x.shape[0]
+        x_hat = ops.lincomb3(torch.empty_like(x), x, _vec(1.0, B, x.device), eps,
+                             _vec(math.sqrt(max(t_hat ** 2 - t ** 2, 0.0)) * Snoise, B, x.device))
+        return x_hat, t_hat
+
+    # ---- denoiser on raw kernels (no autograd graph) --------------------------------------------------
+    def _edm_scalars(self, sigma):
+        sd = float(self.diff_params.sigma_data)
+        s2 = sigma * sigma + sd * sd
+        return sd * sd / s2, sigma * sd / math.sqrt(s2), 1.0 / math.sqrt(s2), 0.25 * math.log(sigma)
+
+    def _denoise(self, x_hat, sigma, save):
+        """x_den = cskip*x + cout*F(cin*x, cnoise) for a micro-batch; returns (x_den, ctx)."""
+        net = self.model
+        if not isinstance(net, NCSNppTime):
+            raise TypeError("buddy_b200 samplers drive buddy_b200.NCSNppTime (load the reference checkpoint into it)")
+        B, n = x_hat.shape
+        dev = x_hat.device
+        cskip, cout, cin, cnoise = self._edm_scalars(sigma)
+        eng, st = net.engine(), net.stft_engine()
+        spec = st.forward(x_hat, scale_b=_vec(cin, B, dev))
+        fspec, ctx = eng.forward(spec, _vec(cnoise, B, dev), save=save)
+        F = st.inverse(fspec, n)
+        x_den = ops.lincomb3(torch.empty_like(x_hat), x_hat, _vec(cskip, B, dev), F, _vec(cout, B, dev))
+        return x_den, ctx
+
+    def step(self, x_i, t_i, t_iplus1, gamma_i, blind=False):
+        x_hat, t_hat = self.stochastic_timestep(x_i, t_i, gamma_i)
+        t_next = float(t_iplus1)
+        B, dev = x_hat.shape[0], x_hat.device
+        d, x_den = self._ode_term(x_hat, t_hat)
+        dt = t_next - t_hat
+        if t_next != 0 and self.order == 2:
+            x_prime = ops.lincomb3(torch.empty_like(x_hat), x_hat, _vec(1.0, B, dev), d, _vec(dt, B, dev))
+            d2, x_den = self._ode_term(x_prime, t_next)
+            x_next = ops.lincomb3(torch.empty_like(x_hat), x_hat, _vec(1.0, B, dev), d, _vec(0.5 * dt, B, dev), d2,
+                                  _vec(0.5 * dt, B, dev))
+        else:
+            x_next = ops.lincomb3(torch.empty_like(x_hat), x_hat, _vec(1.0, B, dev), d, _vec(dt, B, dev))
+        return x_next, x_den
+
+    def _ode_term(self, x, sigma):
+        """d = (x - D(x, sigma)) / sigma   (Tweedie2score + _ode_integrand, edm.py:83-96), micro-batched."""
+        B, dev = x.shape[0], x.device
+        d = torch.empty_like(x)
+        x_den = torch.empty_like(x)
+        for s in range(0, B, self.micro_batch):
+            sl = slice(s, min(B, s + self.micro_batch))
+            xd, _ = self._denoise(x[sl].contiguous(), sigma, save=False)
+            x_den[sl] = xd
+            nb = xd.shape[0]
+            d[sl] = ops.lincomb3(torch.empty_like(xd), x[sl].contiguous(), _vec(1.0 / sigma, nb, dev), xd,
+                                 _vec(-1.0 / sigma, nb, dev))
+        return d, x_den
+
+    def predict(self, shape, device, blind=False):
+        t = self.create_schedule()
+        self._draw = 0
+        x = self.initialize_x(tuple(shape), device, t)
+        gamma = self.get_gamma(t)
+        x_den = None
+        for i in range(self.T):
+            self.step_counter = i
+            x, x_den = self.step(x, t[i], t[i + 1], gamma[i], blind)
+        self._last_x_den = x_den
+        return x.detach()
+
+    def predict_unconditional(self, shape, device):
+        self.y = None
+        self.degradation = None
+        return self.predict(shape, device)
+
+    def predict_conditional(self, *args, **kwargs):
+        raise NotImplementedError
+
+
+class EulerHeunSamplerDPS(EulerHeunSampler):
+    """Diffusion posterior sampling with the compressed-STFT likelihood (EulerHeunSamplerDPS.py:14-204)."""
+
+    def __init__(self, model, diff_params, args):
+        super().__init__(model, diff_params, args)
+        self.zeta = self.args.tester.posterior_sampling.zeta
+
+    def initialize_x(self, shape, device, schedule):
+        ps = self.args.tester.posterior_sampling
+        mode = ps.warm_initialization.mode
+        z = self._randn(shape, device)
+        B = shape[0]
+        if mode == "none":
+            return float(schedule[0]) * z
+        if mode == "reverb_scaled":
+            st = ops.row_stats(self.y)
+            n = self.y.shape[1]
+            std = torch.sqrt((st[:, 1] - st[:, 0] ** 2 / n) / (n - 1)).float()     # unbiased, per utterance
+            coef = (float(ps.warm_initialization.scaling_factor) / std).contiguous()
+            return ops.lincomb3(torch.empty_like(z), self.y, coef, z, _vec(float(schedule[0]), B, device))
+        if mode == "wpe_scaled":
+            raise NotImplementedError("wpe_scaled warm initialisation depends on nara_wpe (third-party, CPU): "
+                                      "out of scope, use reverb_scaled / none (SURVEY.md §8f-2)")
+        raise NotImplementedError(mode)
+
+    # ---- operator binding -----------------------------------------------------------------------------
+    def _bind_operator(self, operator, y, blind):
+        dev = y.device
+        n = y.shape[1]
+        self._loss_stft = LossSTFT(dev)
+        ps = self.args.tester.posterior_sampling
+        self._loss_w = float(ps.rec_loss.weight)
+        self._loss_c = float(ps.rec_loss.compression_factor)
+        if ps.rec_loss.name != "l2_comp_stft_summean":
+            raise NotImplementedError(f"rec_loss {ps.rec_loss.name}: only l2_comp_stft_summean is on the hot path")
+        self._Y = self._loss_stft.forward(y)
+        if blind:
+            raise NotImplementedError("blind (BlindSubbandFiltering) posterior sampling: see buddy_b200.blind")
+        rir = getattr(operator, "params", None)
+        if rir is None:
+            raise ValueError("operator has no RIR (`.params`): call operator.update_params(rir) first")
+        self._rir = RirConv(rir.detach().to(dev), n, dev)
+
+    def get_likelihood_score(self, x_den, ctx, x_hat, sigma):
+        """zeta/(||g||/sqrt(audio_len)+1e-8) * g with g = d rec_loss / d x_hat through the denoiser; per utterance."""
+        B, n = x_den.shape
+        dev = x_den.device
+        cskip, cout, cin, _ = self._edm_scalars(sigma)
+        net = self.model
+        eng, st = net.engine(), net.stft_engine()
+        y_hat = self._rir.forward(x_den)
+        Yh = self._loss_stft.forward(y_hat)
+        loss = torch.empty(B, device=dev, dtype=torch.float64)
+        G = torch.empty_like(Yh)
+        ops.comp_loss(self._Y_mb, Yh, Yh.shape[2], self._loss_c, self._loss_w, loss, G)
+        gd = self._rir.adjoint(self._loss_stft.adjoint(G, n))               # d loss / d x_den
+        rs = ops.row_stats(gd)
+        rms = torch.sqrt(rs[:, 1] / n).float().clamp_min(1e-30)
+        dspec = eng.vjp(ctx, st.inverse_adjoint(gd, scale_b=(1.0 / rms).contiguous()))
+        v = st.forward_adjoint(dspec, n, scale_b=(rms * (cin * cout)).contiguous())
+        g = ops.lincomb3(torch.empty_like(gd), gd, _vec(cskip, B, dev), v, _vec(1.0, B, dev))
+        gs = ops.row_stats(g)
+        normguide = torch.sqrt(gs[:, 1]).float() / (self.args.exp.audio_len ** 0.5)
+        coef = (self.zeta / (normguide + 1e-8)).contiguous()
+        return g, coef, loss
+
+    def _ode_term(self, x, sigma):
+        """d = (x - x_den)/sigma + lh_score   (EulerHeunSamplerDPS.py:118-134), micro-batched."""
+        B, dev = x.shape[0], x.device
+        d = torch.empty_like(x)
+        x_den = torch.empty_like(x)
+        ps = self.args.tester.posterior_sampling
+        rescale = bool(ps.constraint_speech_magnitude.use)
+        for s in range(0, B, self.micro_batch):
+            sl = slice(s, min(B, s + self.micro_batch))
+            xs = x[sl].contiguous()
+            nb = xs.shape[0]
+            self._Y_mb = self._Y[sl]
+            xd, ctx = self._denoise(xs, sigma, save=True)
+            g, coef, loss = self.get_likelihood_score(xd, ctx, xs, sigma)
+            del ctx
+            if rescale:
+                st = ops.row_stats(xd)
+                n = xd.shape[1]
+                std = torch.sqrt((st[:, 1] - st[:, 0] ** 2 / n) / (n - 1)).float()
+                sc = (float(ps.constraint_speech_magnitude.speech_scaling) / std).contiguous()
+                xd = ops.lincomb3(torch.empty_like(xd), xd, sc)
+            x_den[sl] = xd
+            d[sl] = ops.lincomb3(torch.empty_like(xd), xs, _vec(1.0 / sigma, nb, dev), xd, _vec(-1.0 / sigma, nb, dev),
+                                 g, coef)
+            self.rec_loss_value = loss
+        return d, x_den
+
+    def predict(self, shape, device, blind=False):
+        t = self.create_schedule()
+        self._draw = 0
+        x = self.initialize_x(tuple(shape), device, t)
+        gamma = self.get_gamma(t)
+        x_den = None
+        for i in range(self.T):
+            self.step_counter = i
+            x, x_den = self.step(x, t[i], t[i + 1], gamma[i], blind)
+        return x_den.detach()
+
+    def predict_unconditional(self, *args, **kwargs):
+        raise ValueError("DPS not made for unconditional sampling")
+
+    def predict_conditional(self, y, operator, shape=None, blind=False, **kwargs):
+        if not y.is_cuda:
+            raise RuntimeError("buddy_b200 samplers run on CUDA tensors only (no CPU fallback)")
+        self.operator = operator
+        self.y = y.detach().float().contiguous()
+        self._bind_operator(operator, self.y, blind)
+        if shape is None:
+            shape = y.shape
+        return self.predict(shape, y.device, blind)
