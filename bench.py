@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — sampler steps/s of the BUDDy reverse-diffusion dereverberation hot path on N x B200.
+
+Workload (BASELINE.json configs[1]): batch = 32 synthetic utterances of 4.096 s @ 16 kHz per GPU, informed DPS
+(EulerHeunSamplerDPS + RIROperator, conf/tester/informed_dereverberation_DPS.yaml), T = 35, order 2, NCSN++ with
+random (non-degenerate) weights.  One bench "step" = one Euler-Heun sampler step over the whole batch = 2 DPS
+network evaluations (forward + data-gradient) per utterance.  value = utterance-steps per second, whole job.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, weak scaling: 32 utt per GPU)
+
+`--impl reference` times the reference's own algorithm on the host CPU cores (the oracle port — the Python
+reference cannot travel to the GPU box), B = 1, same config.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_SAMPLES = 65536
+T_STEPS = 35
+BATCH_PER_GPU = 32
+EVALS_PER_UTT = 2 * (T_STEPS - 1) + 1          # 69 (order 2, last step is Euler)
+GFLOP_PER_EVAL = 2578.7                        # fwd 1289.3 + VJP 1289.3
+
+
+class AD(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
+def informed_args(T):
+    sde = AD(sigma_data=0.05, sigma_min=1e-4, sigma_max=0.5, rho=10)
+    loss = AD(name="l2_comp_stft_summean", weight=512, frequency_weighting="none", compression_factor=0.667,
+              multiple_compression_factors=False)
+    return AD(exp=AD(audio_len=N_SAMPLES, sample_rate=16000),
+              tester=AD(sampling_params=AD(same_as_training=False, sde_hp=sde, Schurn=10, Snoise=1, Stmin=0, Stmax=10,
+                                           order=2, T=T, schedule="edm"),
+                        posterior_sampling=AD(zeta=2.75, rec_loss=loss, normalization_type="grad_norm",
+                                              warm_initialization=AD(mode="reverb_scaled", scaling_factor=0.05),
+                                              constraint_speech_magnitude=AD(use=False))))
+
+
+def synth_batch(first, count):
+    """Speech surrogate + RIR per utterance: seeds 1000+b / 2000+b, host side, fp32."""
+    import numpy as np
+    from scipy.signal import lfilter
+    s = torch.empty(count, N_SAMPLES)
+    h = torch.empty(count, 16000)
+    for i in range(count):
+        b = first + i
+        n = torch.randn(N_SAMPLES, generator=torch.Generator().manual_seed(1000 + b)).numpy()
+        lp = torch.from_numpy(lfilter([1.0], [1.0, -0.95], n).astype(np.float32))
+        s[i] = 0.05 * lp / lp.std()
+        g = torch.Generator().manual_seed(2000 + b)
+        t60 = 0.3 + 0.7 * torch.rand(1, generator=g).item()
+        r = torch.randn(16000, generator=g) * torch.exp(-6.908 * torch.arange(16000) / (t60 * 16000))
+        r[0] = 1.0
+        h[i] = r / r.abs().max()
+    return s, h
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                     0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.1)
+        except Exception as e:  # NVML missing: report nothing rather than fail the bench
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["bf16_tflops_sustained"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step_time(steps, warmup, threads=None):
+    """Oracle port of the reference sampler on the host cores: B = 1, one Euler-Heun DPS step per 'step'."""
+    from oracle import operators as oop
+    from oracle import sampler as osm
+    from oracle.weights import make_state_dict
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = make_state_dict(0)
+    s, h = synth_batch(0, 1)
+    y = oop.fast_apply_rir(s, h[0])
+    t = osm.create_schedule(T_STEPS)
+    gamma = osm.get_gamma(t, 10)
+    g = torch.Generator().manual_seed(3000)
+    x = 0.05 * y / y.std() + t[0] * torch.randn(1, N_SAMPLES, generator=g)
+    degrade = lambda v: oop.fast_apply_rir(v, h[0])
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        x_hat, t_hat = osm._perturb(x, t[i], gamma[i], torch.randn(1, N_SAMPLES, generator=g))
+        d, x_den, x_hat = osm._likelihood(sd, x_hat, t_hat, y, degrade, 2.75, N_SAMPLES, False)
+        dt = t[i + 1] - t_hat
+        x_p = x_hat + dt * d
+        d2, x_den, _ = osm._likelihood(sd, x_p, t[i + 1], y, degrade, 2.75, N_SAMPLES, False)
+        x = x_hat + dt * 0.5 * (d + d2)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sec, threads = cpu_reference_step_time(args.steps, args.warmup)
+    val = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": "sampler_steps_per_sec", "value": val, "unit": "utterance-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(1, "cpu"),
+        "utterances_per_sec": val * 2 / EVALS_PER_UTT,
+        "cpu_baseline": {"value": val, "unit": "utterance-steps/s", "cores": threads, "kind": "port",
+                         "sample": "B=1, one Euler-Heun DPS step (2 network fwd+VJP evaluations) per step, fp32, "
+                                   "oracle port of the reference run on all host cores"},
+        "e2e": {"value": val, "unit": "utterance-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(batch, precision):
+    return {"workload": "informed EulerHeunSamplerDPS T=35 order 2, synthetic 4.096 s @ 16 kHz (65536 samples), "
+                        "NCSN++ 27.7M random-init (non-degenerate) weights",
+            "batch_per_gpu": batch, "samples": N_SAMPLES, "T": T_STEPS, "order": 2,
+            "evals_per_utterance": EVALS_PER_UTT, "gflop_per_eval": GFLOP_PER_EVAL, "precision": precision,
+            "step_definition": "one Euler-Heun sampler step over the batch = 2 network fwd+VJP evaluations per "
+                               "utterance", "l2_policy": "inputs_larger_than_L2 (>= 1.3 GB of activations per "
+                                                         "utterance per evaluation vs 126 MB L2)"}
+
+
+# --------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from buddy_b200 import _capi, ops
+    from buddy_b200.edm import EDM
+    from buddy_b200.ncsnpp import NCSNppTime
+    from buddy_b200.operators import RIROperator
+    from buddy_b200.samplers import EulerHeunSamplerDPS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+
+    torch.manual_seed(0)
+    net = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2], init_scale=1.0,
+                     precision=args.precision)
+    with torch.no_grad():   # GroupNorm affine away from the identity so every path carries signal
+        for k, p in net.named_parameters():
+            if "GroupNorm" in k or k.split(".")[1] in ("19", "24", "29", "34") and p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    net = net.to(dev).eval()
+    if world > 1:   # replicate rank 0's weights (the only collective besides the timing barriers)
+        for p in net.parameters():
+            dist.broadcast(p.data, src=0)
+
+    s_host, h_host = synth_batch(rank * B, B)
+    op = RIROperator()
+    op.update_params(h_host.to(dev))
+    y = op.degradation(s_host.to(dev))
+    y_host = y.cpu().pin_memory()
+
+    smp = EulerHeunSamplerDPS(net, EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10)),
+                              informed_args(T_STEPS))
+    smp.utterance_offset = rank * B
+    smp.micro_batch = args.micro_batch
+    smp.operator, smp.y = op, y
+    smp._bind_operator(op, y, False)
+    t = smp.create_schedule()
+    gamma = smp.get_gamma(t)
+    x = smp.initialize_x((B, N_SAMPLES), dev, t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step_i = 0
+
+    def one_step(xc):
+        nonlocal step_i
+        i = step_i % (T_STEPS - 1)      # Heun steps only (the final Euler step is half a step)
+        step_i += 1
+        xn, _ = smp.step(xc, t[i], t[i + 1], gamma[i])
+        return xn
+
+    for _ in range(args.warmup):
+        x = one_step(x)
+    clk = ClockSampler(local)
+    barrier()
+    clk.start()
+    _capi.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ops.KernelTimer() as kt:
+        e0.record()
+        for _ in range(args.steps):
+            x = one_step(x)
+        e1.record()
+        barrier()
+    launches = _capi.launch_count()
+    clk.stop_flag = True
+    clk.join()
+    ms = e0.elapsed_time(e1)
+    summ = kt.summary()
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = tms.item()
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: the public step() call with host buffers, H2D + D2H inside the timed region
+    x_host = x.cpu().pin_memory()
+    out_host = torch.empty(2, B, N_SAMPLES).pin_memory()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        smp.y = y_host.to(dev, non_blocking=True)
+        smp._Y = smp._loss_stft.forward(smp.y)      # observation spectrum recomputed from the fresh copy
+        i = step_i % (T_STEPS - 1)
+        step_i += 1
+        xn, xden = smp.step(xd, t[i], t[i + 1], gamma[i])
+        out_host[0].copy_(xn, non_blocking=True)
+        out_host[1].copy_(xden, non_blocking=True)
+        torch.cuda.synchronize()
+        x_host.copy_(out_host[0])
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms_e2e = tms.item()
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak_tf, peak_gbs, peak_src = peaks()
+    calls, conv_ms, conv_flops = summ.get("conv_gemm", (0, 0.0, 0.0))
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None
+    np_ = net.engine().np
+    total_ms_ops = sum(v[1] for v in summ.values())
+    line = {
+        "metric": "sampler_steps_per_sec", "value": value, "unit": "utterance-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": f"f16 operands x{np_} passes / f32 accumulate+activations",
+        "data": "synthetic", "config": config_dict(B, args.precision),
+        "utterances_per_sec": value * 2 / EVALS_PER_UTT,
+        "evals_per_sec": value * 2, "algorithmic_tflops": value * 2 * GFLOP_PER_EVAL / 1e3,
+        "e2e": {"value": e2e_value, "unit": "utterance-steps/s", "h2d_bytes_per_step": 2 * B * N_SAMPLES * 4,
+                "d2h_bytes_per_step": 2 * B * N_SAMPLES * 4},
+        "gpu_launches": int(launches),
+        "clocks": clk.result(),
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv, all conv/NIN/attention "
+                     "launches of the timed region)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": (achieved / peak_tf) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "achieved_definition": "algorithmic FLOPs (2*M*N*K of the convolution, split-precision passes "
+                                            "NOT counted) / summed CUDA-event duration of the launches",
+                     "issued_mma_tflops": (achieved * np_) if achieved else None, "launches": calls,
+                     "share_of_step": conv_ms / total_ms_ops if total_ms_ops else None},
+        "kernel_time_share": {k: round(v[1] / total_ms_ops, 4) for k, v in
+                              sorted(summ.items(), key=lambda kv: -kv[1][1])[:6]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sec, threads = cpu_reference_step_time(1, 0)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "utterance-steps/s", "cores": threads, "kind": "port",
+                                "sample": "B=1, ONE Euler-Heun DPS step (2 fwd+VJP evaluations) of the same config, "
+                                          "oracle port of the reference on all host cores, no warm-up"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--micro-batch", type=int, default=16)
+    ap.add_argument("--precision", default=os.environ.get("BUDDY_PRECISION", "fp16x3"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (buddy_b200 has no CPU fallback; use --impl reference for the "
+                             "CPU arm)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

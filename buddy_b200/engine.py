@@ -220,18 +220,18 @@ class Engine:
         ops.gn_apply(xa, sa, r.g0, r.b0, a0, xb=xb, sb=sb, silu=True, mode=mode, out_raw=raw, split=self.split)
         h1 = torch.empty(B, Ho, Wo, r.cout, device=dev)
         s1 = self._zeros_stats(B, r.cout)
-        ops.conv_gemm(a0, r.w0, h1, taps=9, n_total=r.cout, bias=r.bias0, bias_b=tb[i], stats=s1)
+        ops.conv_gemm(a0, r.w0, h1, passes=self.np, taps=9, n_total=r.cout, bias=r.bias0, bias_b=tb[i], stats=s1)
         del a0
         a1 = torch.empty(B, Ho, Wo, r.cout * self.am, device=dev, dtype=torch.float16)
         ops.gn_apply(h1, s1, r.g1, r.b1, a1, silu=True, split=self.split)
         out = torch.empty(B, Ho, Wo, r.cout, device=dev)
         so = self._zeros_stats(B, r.cout)
         if r.has_skip_conv:
-            ops.conv_gemm(a1, r.w1, out, taps=9, n_total=r.cout, a2=raw, w2=r.w2, bias=r.bias1, scale=INV_SQRT2,
+            ops.conv_gemm(a1, r.w1, out, passes=self.np, taps=9, n_total=r.cout, a2=raw, w2=r.w2, bias=r.bias1, scale=INV_SQRT2,
                           stats=so)
         else:
             assert mode == MODE_NONE and xb is None
-            ops.conv_gemm(a1, r.w1, out, taps=9, n_total=r.cout, bias=r.bias1, resid=xa, scale=INV_SQRT2, stats=so)
+            ops.conv_gemm(a1, r.w1, out, passes=self.np, taps=9, n_total=r.cout, bias=r.bias1, resid=xa, scale=INV_SQRT2, stats=so)
         if save is not None:
             save[i] = (xa, sa, xb, sb, h1, s1, mode)
         return out, so
@@ -244,16 +244,16 @@ class Engine:
         dev = self.device
         gsum = self._scratch_gsum(B)
         da1 = torch.empty(B, Ho, Wo, r.cout, device=dev)
-        ops.conv_gemm(g16, r.wd1, da1, taps=9, n_total=r.cout)
+        ops.conv_gemm(g16, r.wd1, da1, passes=self.np, taps=9, n_total=r.cout)
         dh1 = torch.empty(B, Ho, Wo, r.cout * self.am, device=dev, dtype=torch.float16)
         ops.gn_bwd(h1, s1, r.g1, r.b1, da1, gsum, silu=True, g16a=dh1, g16_scale=1.0, split=self.split)
         del da1
         da0 = torch.empty(B, Ho, Wo, r.cin, device=dev)
-        ops.conv_gemm(dh1, r.wd0, da0, taps=9, n_total=r.cin)
+        ops.conv_gemm(dh1, r.wd0, da0, passes=self.np, taps=9, n_total=r.cin)
         del dh1
         if r.has_skip_conv:
             dsk = torch.empty(B, Ho, Wo, r.cin, device=dev)
-            ops.conv_gemm(g16, r.wd2, dsk, taps=1, n_total=r.cin)
+            ops.conv_gemm(g16, r.wd2, dsk, passes=self.np, taps=1, n_total=r.cin)
             skip_scale = 1.0
         else:
             dsk, skip_scale = dout32, INV_SQRT2
@@ -338,7 +338,7 @@ class Engine:
         a = torch.empty(B, H, W, C * self.am, device=self.device, dtype=torch.float16)
         ops.gn_apply(h, sh, hd.g, hd.b, a, silu=True, split=self.split)
         out = torch.empty(B, H, W, 2, device=self.device)
-        ops.conv_gemm(a, hd.w, out, taps=9, n_total=2, n_tile=16, bias=hd.bias)
+        ops.conv_gemm(a, hd.w, out, passes=self.np, taps=9, n_total=2, n_tile=16, bias=hd.bias)
         return out
 
     def _head_bwd(self, i, h, sh, dP, extra, want32):
@@ -349,7 +349,7 @@ class Engine:
         col = torch.empty(B, H, W, 64 * self.am, device=dev, dtype=torch.float16)
         ops.im2col_c2(dP, col, split=self.split)
         da = torch.empty(B, H, W, C, device=dev)
-        ops.conv_gemm(col, hd.wd, da, taps=1, n_total=C)
+        ops.conv_gemm(col, hd.wd, da, passes=self.np, taps=1, n_total=C)
         dx = torch.empty_like(h) if want32 else None
         g16 = torch.empty(B, H, W, C * self.am, device=dev, dtype=torch.float16)
         ops.gn_bwd(h, sh, hd.g, hd.b, da, self._scratch_gsum(B), silu=True, extra_a=extra, dxa=dx, g16a=g16,
@@ -374,7 +374,7 @@ class Engine:
         ops.im2col_c2(spec, col, split=self.split)
         h = torch.empty(B, H, W, NF, device=dev)
         sh = self._zeros_stats(B, NF)
-        ops.conv_gemm(col, self.in_w, h, taps=1, n_total=NF, bias=self.in_b, stats=sh)
+        ops.conv_gemm(col, self.in_w, h, passes=self.np, taps=1, n_total=NF, bias=self.in_b, stats=sh)
         del col
         hs = [(h, sh)]
         i = 4
@@ -467,7 +467,7 @@ class Engine:
         # RB4 (identity skip) : input hs[0]; its producer is the input conv -> fp16 at scale 1
         _, g16, _ = self._rb_bwd(4, ctx, g16, d32, extra_a=partial_hs[0], want_a32=False, a16_scale=1.0)
         dcol = torch.empty(B, H, W, 32, device=dev)
-        ops.conv_gemm(g16, self.in_wd, dcol, taps=1, n_total=32)
+        ops.conv_gemm(g16, self.in_wd, dcol, passes=self.np, taps=1, n_total=32)
         dx = torch.empty(B, H, W, 2, device=dev)
         ops.col2im_c2(dcol, dx)
         # input pyramid adjoint: pyr[l+1] = mean4(pyr[l])

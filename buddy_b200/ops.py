@@ -23,7 +23,7 @@ def _pick_n_tile(n_total):
 
 
 def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=None, bias_b=None, resid=None,
-              scale=1.0, stats=None, b_batched=False, col_off=0, ldc=None, max_ctas=0):
+              scale=1.0, stats=None, b_batched=False, col_off=0, ldc=None, max_ctas=0, passes=1):
     """out[b,h,w,n] = scale*(sum_{tap,k} a[b,h+dy,w+dx,k] w[tap,n,k] + sum_k a2[b,h,w,k] w2[n,k] + bias + bias_b + resid).
 
     a, a2 : fp16 [B,H,W,C] (channel stride 1, other strides arbitrary multiples of 8 elements)
@@ -309,3 +309,67 @@ def lincomb3(out, x, ca, y=None, cb=None, z=None, cc=None):
     check(lib().buddy_lincomb3(ptr(x), ptr(y), ptr(z), ptr(ca), ptr(cb), ptr(cc), c_int(B), c_int(n), ptr(out),
                                stream_ptr()), "buddy_lincomb3")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# optional per-kernel device timing (CUDA events on the launching stream) — used by bench.py for the roofline
+# ------------------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """with KernelTimer() as kt: ...; kt.summary() -> {op: (calls, total_ms, work)}; work = FLOPs or bytes."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _timer
+        _timer = self
+        return self
+
+    def __exit__(self, *a):
+        global _timer
+        _timer = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, work in self.records:
+            c, ms, w = out.get(name, (0, 0.0, 0.0))
+            out[name] = (c + 1, ms + e0.elapsed_time(e1), w + work)
+        return out
+
+
+_timer = None
+
+
+def _conv_flops(args, kwargs):
+    a, w = args[0], args[1]
+    B, H, W, _ = a.shape
+    flops = 2.0 * B * H * W * kwargs["n_total"] * w.shape[2] * (1 if kwargs.get("b_batched") else w.shape[0])
+    if kwargs.get("b_batched"):
+        flops = 2.0 * B * H * W * kwargs["n_total"] * w.shape[2]
+    if kwargs.get("w2") is not None:
+        flops += 2.0 * B * H * W * kwargs["n_total"] * kwargs["w2"].shape[1]
+    return flops / kwargs.get("passes", 1)   # algorithmic FLOPs: split-precision passes are not useful work
+
+
+def _timed(fn, work_fn=None):
+    def wrapper(*args, **kwargs):
+        if _timer is None:
+            return fn(*args, **kwargs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*args, **kwargs)
+        e1.record()
+        _timer.records.append((fn.__name__, e0, e1, work_fn(args, kwargs) if work_fn else 0.0))
+        return r
+    wrapper.__name__ = fn.__name__
+    wrapper.__doc__ = fn.__doc__
+    return wrapper
+
+
+conv_gemm = _timed(conv_gemm, _conv_flops)
+for _n in ("gn_stats", "gn_apply", "gn_bwd", "im2col_c2", "col2im_c2", "resample_c2", "combine_fwd", "combine_bwd",
+           "affine_c2", "softmax_fwd", "softmax_bwd", "transpose_h", "cast_scale_h", "dft_analysis", "dft_synthesis",
+           "ola_gather", "pad_signal", "reflect_fold", "comp_loss", "row_stats", "fftconv", "fourier_features",
+           "dense", "philox_normal", "lincomb3"):
+    globals()[_n] = _timed(globals()[_n])
