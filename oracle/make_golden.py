@@ -176,6 +176,56 @@ def main():
         xu = smu.predict_unconditional((1, NS), "cpu")
     save("sampler_uncond_T3.pt", {"T": T, "n": NS, "noise_seed0": 100, "x": xu})
 
+    # ---- blind DPS (order 1, 10 operator-Adam iterations per step) with injected noise
+    T = 2
+    s = synth_utterance(61, NS)
+    h = synth_rir(62, 2000, 0.5)
+    op = RIROperator(hp, time_kernel_size=h.shape[-1], sample_rate=16000)
+    op.update_params(h)
+    y = op.degradation(s[None])
+    torch.manual_seed(7)
+    bop = BlindSubbandFiltering(hp, sample_rate=16000)
+    with torch.no_grad():
+        bop.update_H(use_noise=True)
+    init = {"decays": bop.params[0].detach().clone(), "weights": bop.params[1].detach().clone(),
+            "phases": bop.params_phases[0].detach().clone(), "H": bop.H.detach().clone()}
+    # single operator-iteration gradients (strong pin: the multi-iteration Adam trajectory amplifies rounding)
+    for k in range(2):
+        bop.params[k].requires_grad = True
+    bop.params_phases[0].requires_grad = True
+    bop.update_H()
+    x_probe = s[None] + 0.01 * randn(63, 1, NS)
+    n_probe = randn(64, 13824)
+    bargs = rh.make_args("blind", T)
+    lrec = get_loss(bargs.tester.posterior_sampling.rec_loss_params, operator=bop)
+    lreg = get_loss(bargs.tester.posterior_sampling.RIR_noise_regularization.loss, operator=bop)
+    rec_v = lrec(y, bop.degradation(x_probe, mode="waveform"))
+    rir_v = bop.get_time_RIR()
+    reg_v = lreg(rir_v, (rir_v + 0.01 * n_probe).detach())
+    gr = torch.autograd.grad(rec_v + reg_v, [bop.params[0], bop.params[1], bop.params_phases[0]])
+    iter_gold = {"x_probe_seed": 63, "noise_seed": 64, "t_op": 0.01, "rec": rec_v.detach(), "reg": reg_v.detach(),
+                 "g_decays": gr[0], "g_weights": gr[1], "g_phases": gr[2], "rir": rir_v.detach()}
+    for k in range(2):
+        bop.params[k].requires_grad = False
+    bop.params_phases[0] = bop.params_phases[0].detach()
+    with torch.no_grad():
+        bop.update_H()
+    step_noise = [randn(300 + i, 1, NS) for i in range(T + 1)]
+    rir_noise = [randn(400 + i, 13824) for i in range(10 * T)]
+    # reference call order: initialize_x, then per step: stochastic_timestep, 10 x randn_like(rir)
+    order = [step_noise[0]]
+    for i in range(T):
+        order.append(step_noise[1 + i])
+        order += rir_noise[10 * i:10 * (i + 1)]
+    smp = EulerHeunSamplerDPS(net, edm, rh.make_args("blind", T, audio_len=65536))
+    with rh.injected_noise(order):
+        pred = smp.predict_conditional(y, bop, shape=(1, NS), blind=True)
+    save("sampler_blind_T2.pt", {"T": T, "n": NS, "y": y, "init": init, "step_noise_seed0": 300, "rir_noise_seed0": 400,
+                                 "pred": pred, "s": s, "iter": iter_gold, "final_decays": bop.params[0].detach().clone(),
+                                 "final_weights": bop.params[1].detach().clone(),
+                                 "final_phases": bop.params_phases[0].detach().clone(),
+                                 "final_H": bop.H.detach().clone()})
+
 
 if __name__ == "__main__":
     main()

@@ -102,3 +102,58 @@ def dps_informed(sd, y, rir, T, noise, zeta=2.75, Schurn=10, order=2, audio_len=
         else:
             x = x_hat + dt * d
     return x_den
+
+
+class BlindState:
+    """Per-utterance blind-operator state: parameters + Adam moments (EulerHeunSamplerDPS.py:198; torch.optim.Adam)."""
+
+    def __init__(self, decays, weights, phases, H):
+        self.decays = decays.clone().requires_grad_(True)      # (1,25)
+        self.weights = weights.clone().requires_grad_(True)    # (1,25)
+        self.phases = phases.clone().requires_grad_(True)      # (513,100)
+        self.H = H.clone()
+        self.opt = torch.optim.Adam([self.decays, self.weights, self.phases], lr=0.1, betas=(0.9, 0.99),
+                                    weight_decay=0)
+
+
+def optimize_op(state, x_den, y, t, rir_noise_iter, n_iter=10, crop_max=0.01, crop_min=5e-4):
+    """EulerHeunSamplerDPS.optimize_op (:71-113) for one utterance."""
+    for _ in range(n_iter):
+        state.H = oop.design_H(state.decays, state.weights, state.phases)
+        rec = oop.comp_loss(y, oop.blind_degradation(x_den, state.H), 512.0).sum()
+        rir = oop.time_rir(state.H)
+        t_op = max(min(float(t), crop_max), crop_min)
+        reg = oop.comp_loss(rir[None], (rir + t_op * next(rir_noise_iter)).detach()[None], 2560.0).sum()
+        state.opt.zero_grad()
+        (rec + reg).backward()
+        state.opt.step()
+        with torch.no_grad():
+            d, w = oop.project_params(state.decays, state.weights)
+            state.decays.copy_(d)
+            state.weights.copy_(w)
+
+
+def dps_blind(sd, y, state, T, noise, rir_noise, zeta=0.5, Schurn=50, audio_len=65536, warm="reverb_scaled",
+              n_iter=10):
+    """Blind DPS (conf/tester/blind_dereverberation_BUDDy.yaml; order 1) for ONE utterance y (1,N).
+    noise: [init, step0, step1, ...]; rir_noise: iterable of (13824,) draws, one per operator-Adam iteration."""
+    t = create_schedule(T)
+    gamma = get_gamma(t, Schurn)
+    it, rit = iter(noise), iter(rir_noise)
+    x = t[0] * next(it)
+    if warm == "reverb_scaled":
+        x = SIGMA_DATA * y.clone() / y.std() + x
+    x_den = None
+    for i in range(T):
+        x_hat, t_hat = _perturb(x, t[i], gamma[i], next(it))
+        x_hat = x_hat.detach().requires_grad_(True)
+        x_den = denoise(sd, x_hat, t_hat)
+        optimize_op(state, x_den.clone().detach(), y, t_hat, rit, n_iter)
+        rec = oop.comp_loss(y, oop.blind_degradation(x_den, state.H.detach()), 512.0).sum()
+        g = torch.autograd.grad(rec, x_hat)[0]
+        lh = zeta / (torch.norm(g) / (audio_len ** 0.5) + 1e-8) * g
+        x_den = x_den.detach()
+        x_den = SIGMA_DATA / x_den.std() * x_den
+        d = (x_hat.detach() - x_den) / t_hat + lh
+        x = x_hat.detach() + (t[i + 1] - t_hat) * d
+    return x_den
