@@ -373,3 +373,55 @@ for _n in ("gn_stats", "gn_apply", "gn_bwd", "im2col_c2", "col2im_c2", "resample
            "ola_gather", "pad_signal", "reflect_fold", "comp_loss", "row_stats", "fftconv", "fourier_features",
            "dense", "philox_normal", "lincomb3"):
     globals()[_n] = _timed(globals()[_n])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# blind operator kernels
+# ------------------------------------------------------------------------------------------------------------
+def subband_fir(a, h_or_dy, out, *, Nf, pre, mode, shared_h=False, accumulate=False):
+    """a, out: fp32 [B, F, T, 2]; mode 0/1: h_or_dy = H [B or 1, F, Nf, 2]; mode 2: h_or_dy = dY, out = dH."""
+    B, F, Tx, _ = a.shape
+    stride = 0 if shared_h else F * Nf * 2
+    check(lib().buddy_subband_fir(ptr(a), ptr(h_or_dy), c_i64(stride), ptr(out), c_int(B), c_int(F), c_int(Tx),
+                                  c_int(Nf), c_int(pre), c_int(mode), c_int(int(accumulate)), stream_ptr()),
+          "buddy_subband_fir")
+    return out
+
+
+def blind_design_fwd(decays, weights, phases, tabs, A, H0):
+    B, F, Nf = phases.shape
+    check(lib().buddy_blind_design_fwd(ptr(decays), ptr(weights), ptr(phases), ptr(tabs["kidx"]), ptr(tabs["frac"]),
+                                       ptr(tabs["corr"]), ptr(tabs["dpmag"]), c_int(B), c_int(F), c_int(Nf), ptr(A),
+                                       ptr(H0), stream_ptr()), "buddy_blind_design_fwd")
+
+
+def blind_design_bwd(decays, weights, phases, A, tabs, G, dphases, ddecays, dweights):
+    B, F, Nf = phases.shape
+    check(lib().buddy_blind_design_bwd(ptr(decays), ptr(weights), ptr(phases), ptr(A), ptr(tabs["kidx"]),
+                                       ptr(tabs["frac"]), ptr(tabs["corr"]), ptr(tabs["dpmag"]), ptr(G), c_int(B),
+                                       c_int(F), c_int(Nf), ptr(dphases), ptr(ddecays), ptr(dweights), stream_ptr()),
+          "buddy_blind_design_bwd")
+
+
+def fft_mixed(x, in_real, work, out, N1, sign, tw512):
+    B = x.shape[0]
+    check(lib().buddy_fft_mixed(ptr(x), c_int(int(in_real)), ptr(work), ptr(out), c_int(B), c_int(N1), c_int(sign),
+                                ptr(tw512), stream_ptr()), "buddy_fft_mixed")
+    return out
+
+
+def minphase_pw(mode, B, N, T, c0=None, c1=None, r0=None, r1=None, oc=None, or0=None, or1=None, scale_inv_n=False):
+    check(lib().buddy_minphase_pw(c_int(mode), ptr(c0), ptr(c1), ptr(r0), ptr(r1), ptr(oc), ptr(or0), ptr(or1),
+                                  c_int(B), c_int(N), c_int(T), c_int(int(scale_inv_n)), stream_ptr()),
+          "buddy_minphase_pw")
+
+
+def adam_project(p, g, m, v, step, lr, beta1, beta2, eps, dmin, dmax, wmin, wmax):
+    B, n_per = p.shape
+    check(lib().buddy_adam_project(ptr(p), ptr(g), ptr(m), ptr(v), c_int(B), c_int(n_per), c_int(step), c_float(lr),
+                                   c_float(beta1), c_float(beta2), c_float(eps), c_float(dmin), c_float(dmax),
+                                   c_float(wmin), c_float(wmax), stream_ptr()), "buddy_adam_project")
+
+
+for _n in ("subband_fir", "blind_design_fwd", "blind_design_bwd", "fft_mixed", "minphase_pw", "adam_project"):
+    globals()[_n] = _timed(globals()[_n])

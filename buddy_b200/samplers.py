@@ -64,16 +64,22 @@ class Sampler:
         return self.diff_params.denoiser(x.unsqueeze(1), self.model, t_i).squeeze(1)
 
     # ---- noise ---------------------------------------------------------------------------------------
-    def _randn(self, shape, device):
+    def _randn(self, shape, device, draw=None, first=0):
+        """N(0,1) [B, n].  Philox stream of utterance b = seed_base + utterance_offset + first + b; `draw` is the draw
+        index inside the stream (explicit, so results do not depend on micro-batching or on the GPU count)."""
         if self.noise_source is not None:
             z = next(self.noise_source).to(device=device, dtype=torch.float32)
+            if z.dim() == 1:
+                z = z[None]
             assert tuple(z.shape) == tuple(shape), (z.shape, shape)
             return z.contiguous()
         B, n = shape
-        seeds = torch.arange(B, dtype=torch.int64, device=device) + (self.seed_base + self.utterance_offset)
+        seeds = torch.arange(B, dtype=torch.int64, device=device) + (self.seed_base + self.utterance_offset + first)
         out = torch.empty(B, n, device=device)
-        ops.philox_normal(seeds, self._draw, out)
-        self._draw += 1
+        if draw is None:
+            draw = self._draw
+            self._draw += 1
+        ops.philox_normal(seeds, draw, out)
         return out
 
 
@@ -213,8 +219,23 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
         if ps.rec_loss.name != "l2_comp_stft_summean":
             raise NotImplementedError(f"rec_loss {ps.rec_loss.name}: only l2_comp_stft_summean is on the hot path")
         self._Y = self._loss_stft.forward(y)
+        self._is_blind = bool(blind)
+        self._eval_index = 0
         if blind:
-            raise NotImplementedError("blind (BlindSubbandFiltering) posterior sampling: see buddy_b200.blind")
+            from .blind import BlindEngine
+            hp = ps.blind_hp
+            rp, reg = ps.rec_loss_params, ps.RIR_noise_regularization
+            if rp.name != "l2_comp_stft_summean" or reg.loss.name != "l2_comp_stft_summean":
+                raise NotImplementedError("blind path: only l2_comp_stft_summean losses are on the hot path")
+            self._blind = BlindEngine(n, dev, op_hp=getattr(operator, "op_hp", None),
+                                      sample_rate=self.args.exp.sample_rate)
+            self._blind.init_state(y.shape[0], operator.params[0], operator.params[1], operator.params_phases[0],
+                                   operator.H)
+            self._blind_hp = dict(iters=int(hp.op_updates_per_step), lr=float(hp.lr_op), beta1=float(hp.beta1),
+                                  beta2=float(hp.beta2), comp=float(rp.compression_factor), w_rec=float(rp.weight),
+                                  w_reg=float(reg.loss.weight), crop_max=float(reg.crop_sigma_max),
+                                  crop_min=float(reg.crop_sigma_min))
+            return
         rir = getattr(operator, "params", None)
         if rir is None:
             raise ValueError("operator has no RIR (`.params`): call operator.update_params(rir) first")
@@ -227,12 +248,15 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
         cskip, cout, cin, _ = self._edm_scalars(sigma)
         net = self.model
         eng, st = net.engine(), net.stft_engine()
-        y_hat = self._rir.forward(x_den)
-        Yh = self._loss_stft.forward(y_hat)
-        loss = torch.empty(B, device=dev, dtype=torch.float64)
-        G = torch.empty_like(Yh)
-        ops.comp_loss(self._Y_mb, Yh, Yh.shape[2], self._loss_c, self._loss_w, loss, G)
-        gd = self._rir.adjoint(self._loss_stft.adjoint(G, n))               # d loss / d x_den
+        if self._is_blind:
+            gd, loss = self._blind.likelihood_grad(x_den, self._Y_mb, self._loss_w, self._loss_c)
+        else:
+            y_hat = self._rir.forward(x_den)
+            Yh = self._loss_stft.forward(y_hat)
+            loss = torch.empty(B, device=dev, dtype=torch.float64)
+            G = torch.empty_like(Yh)
+            ops.comp_loss(self._Y_mb, Yh, Yh.shape[2], self._loss_c, self._loss_w, loss, G)
+            gd = self._rir.adjoint(self._loss_stft.adjoint(G, n))           # d loss / d x_den
         rs = ops.row_stats(gd)
         rms = torch.sqrt(rs[:, 1] / n).float().clamp_min(1e-30)
         dspec = eng.vjp(ctx, st.inverse_adjoint(gd, scale_b=(1.0 / rms).contiguous()))
@@ -256,6 +280,8 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
             nb = xs.shape[0]
             self._Y_mb = self._Y[sl]
             xd, ctx = self._denoise(xs, sigma, save=True)
+            if self._is_blind:
+                self.optimize_op(xd, sigma, sl)
             g, coef, loss = self.get_likelihood_score(xd, ctx, xs, sigma)
             del ctx
             if rescale:
@@ -268,18 +294,51 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
             d[sl] = ops.lincomb3(torch.empty_like(xd), xs, _vec(1.0 / sigma, nb, dev), xd, _vec(-1.0 / sigma, nb, dev),
                                  g, coef)
             self.rec_loss_value = loss
+        self._eval_index += 1
         return d, x_den
+
+    def optimize_op(self, x_den, t, sl=None):
+        """Operator-parameter updates for the utterances in `sl` (EulerHeunSamplerDPS.optimize_op, :71-113)."""
+        sl = slice(0, x_den.shape[0]) if sl is None else sl
+        first = sl.start or 0
+        k = [0]
+        base = 1_000_000 + self._eval_index * 256
+
+        def noise_fn(shape):
+            z = self._randn(shape, x_den.device, draw=base + k[0], first=first)
+            k[0] += 1
+            return z
+
+        self._blind.select(sl)
+        self._blind.optimize(x_den, self._Y[sl], t, noise_fn, self._blind_hp)
 
     def predict(self, shape, device, blind=False):
         t = self.create_schedule()
         self._draw = 0
+        self._eval_index = 0
         x = self.initialize_x(tuple(shape), device, t)
         gamma = self.get_gamma(t)
         x_den = None
         for i in range(self.T):
             self.step_counter = i
             x, x_den = self.step(x, t[i], t[i + 1], gamma[i], blind)
+        if blind:
+            self._write_back_operator()
         return x_den.detach()
+
+    def _write_back_operator(self):
+        """After a blind run the estimated filter lives in the operator object again (tester.py:161 reads it)."""
+        st, op = self._blind.full, self.operator
+        H = torch.view_as_complex(st["H"].contiguous())
+        try:
+            if st["B"] == 1:
+                op.params[0] = st["decays"].clone()
+                op.params[1] = st["weights"].clone()
+                op.params_phases[0] = st["phases"][0].clone()
+                op.H = H[0].clone()
+            op.H_batch, op.params_batch = H, (st["decays"], st["weights"], st["phases"])
+        except Exception:
+            pass
 
     def predict_unconditional(self, *args, **kwargs):
         raise ValueError("DPS not made for unconditional sampling")

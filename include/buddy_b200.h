@@ -214,6 +214,38 @@ int buddy_philox_normal(const int64_t* seeds, uint64_t draw, int batch, int n, f
 int buddy_lincomb3(const float* x, const float* y, const float* z, const float* ca, const float* cb, const float* cc,
                    int batch, int n, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Blind reverb operator (BlindSubbandFiltering, testing/operators/subband_filtering.py:67-74,193-351;
+ * utils/reverb_utils.py:3-23; optimiser of testing/EulerHeunSamplerDPS.py:71-113,198).  All batched over
+ * utterances: every utterance owns H, its 25+25+513*100 parameters and its Adam state.
+ *
+ * subband_fir (complex, [batch][F][T] rows):
+ *   mode 0: Y[t]  = sum_n H[n] X[t+pre-n]            (a = X, h_or_dy = H [batch][F][Nf], stride 0 = shared)
+ *   mode 1: dX[s] = sum_n conj(H[n]) dY[s-pre+n]     (a = dY, h_or_dy = H)
+ *   mode 2: dH[n] (+)= sum_t conj(X[t+pre-n]) dY[t]  (a = X, h_or_dy = dY)
+ * blind_design_fwd/bwd: (decays, weights, phases) -> A [batch][F][Nf], H0 = A e^{j phase} as [batch][F][Nf+2]
+ *   complex with a zero frame on each side; kidx/frac = piecewise-linear interpolation tables over the 27 EQ knots.
+ * fft_mixed: complex (or real-input) FFT of length N1*256 (25 856 = 101*256), sign -1 forward / +1 inverse, unnormalised.
+ * minphase_pw: pointwise stages of minimum_phase_version and of its backward (mode 0..7, see buddy_b200/blind.py).
+ * adam_project: torch.optim.Adam update (lr, betas, eps; bias-corrected) + project_params clamps; per utterance layout
+ *   [25 decays | 25 weights | phases].
+ */
+int buddy_subband_fir(const float* a, const float* h_or_dy, int64_t h_batch_stride, float* out, int batch, int F,
+                      int Tx, int Nf, int pre, int mode, int accumulate, void* stream);
+int buddy_blind_design_fwd(const float* decays, const float* weights, const float* phases, const int* kidx,
+                           const float* frac, const float* corr, const float* dpmag, int batch, int F, int Nf,
+                           float* A, float* H0, void* stream);
+int buddy_blind_design_bwd(const float* decays, const float* weights, const float* phases, const float* A,
+                           const int* kidx, const float* frac, const float* corr, const float* dpmag, const float* G,
+                           int batch, int F, int Nf, float* dphases, float* ddecays, float* dweights, void* stream);
+int buddy_fft_mixed(const float* in, int in_real, float* work, float* out, int batch, int N1, int sign,
+                    const float* tw512, void* stream);
+int buddy_minphase_pw(int mode, const float* c0, const float* c1, const float* r0, const float* r1, float* oc,
+                      float* or0, float* or1, int batch, int N, int T, int scale_inv_n, void* stream);
+int buddy_adam_project(float* p, const float* g, float* m, float* v, int batch, int n_per, int step, float lr,
+                       float beta1, float beta2, float eps, float dmin, float dmax, float wmin, float wmax,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

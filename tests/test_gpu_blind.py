@@ -1,0 +1,218 @@
+"""Blind operator parity: CUDA kernels vs the oracle restatement (autograd) and the reference fixtures."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def randn(seed, *shape):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def test_fft_mixed_25856():
+    from buddy_b200 import ops
+    from buddy_b200.blind import BlindEngine
+    eng = BlindEngine(8192, "cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B, N = 2, 25856
+    x = torch.randn(B, N, 2, device="cuda", generator=g)
+    work, out = torch.empty_like(x), torch.empty_like(x)
+    ops.fft_mixed(x, False, work, out, 101, -1, eng.tw512)
+    ref = torch.fft.fft(torch.view_as_complex(x))
+    assert rel(out, torch.view_as_real(ref)) < 2e-6
+    ops.fft_mixed(x, False, work, out, 101, +1, eng.tw512)
+    ref = torch.fft.ifft(torch.view_as_complex(x)) * N
+    assert rel(out, torch.view_as_real(ref)) < 2e-6
+    xr = torch.randn(B, N, device="cuda", generator=g)
+    ops.fft_mixed(xr, True, work, out, 101, -1, eng.tw512)
+    assert rel(out, torch.view_as_real(torch.fft.fft(xr))) < 2e-6
+
+
+def test_subband_fir_fwd_bwd():
+    from buddy_b200 import ops
+    from oracle import operators as oop
+    g = torch.Generator(device="cuda").manual_seed(2)
+    B, F, T, Nf = 2, 513, 517, 100
+    X = torch.randn(B, F, T, 2, device="cuda", generator=g)
+    H = torch.randn(B, F, Nf, 2, device="cuda", generator=g)
+    Y = ops.subband_fir(X, H, torch.empty_like(X), Nf=Nf, pre=1, mode=0)
+    Xc = torch.view_as_complex(X).clone().requires_grad_(True)
+    Hc = torch.view_as_complex(H).clone().requires_grad_(True)
+    ref = torch.stack([oop.subband_fir(Xc[b:b + 1], Hc[b])[0] for b in range(B)])
+    assert rel(Y, torch.view_as_real(ref.detach())) < 1e-5
+    dY = torch.randn(B, F, T, 2, device="cuda", generator=g)
+    gX, gH = torch.autograd.grad(ref, [Xc, Hc], torch.view_as_complex(dY))
+    dX = ops.subband_fir(dY, H, torch.empty_like(X), Nf=Nf, pre=1, mode=1)
+    dH = ops.subband_fir(X, dY, torch.empty_like(H), Nf=Nf, pre=1, mode=2)
+    assert rel(dX, torch.view_as_real(gX)) < 1e-5
+    assert rel(dH, torch.view_as_real(gH)) < 1e-5
+
+
+def _engine_from_gold(g, B=1):
+    from buddy_b200.blind import BlindEngine
+    eng = BlindEngine(g["n"], "cuda")
+    i = g["init"]
+    eng.init_state(B, i["decays"], i["weights"], i["phases"], i["H"])
+    eng.select(slice(0, B))
+    return eng
+
+
+def test_update_H_and_time_rir_vs_reference_fixture():
+    g = torch.load(os.path.join(GOLD, "sampler_blind_T2.pt"), weights_only=False)
+    from oracle import operators as oop
+    eng = _engine_from_gold(g)
+    H = eng.update_H()
+    i = g["init"]
+    ref = oop.design_H(i["decays"], i["weights"], i["phases"])
+    assert rel(H[0].cpu(), torch.view_as_real(ref)) < 1e-4
+    rir = eng.get_time_RIR()
+    assert rel(rir[0].cpu(), g["iter"]["rir"]) < 1e-4
+
+
+def test_operator_iteration_gradients_vs_reference_fixture():
+    """rec + reg losses and their gradients w.r.t. (decays, weights, phases) for one operator iteration."""
+    g = torch.load(os.path.join(GOLD, "sampler_blind_T2.pt"), weights_only=False)
+    from buddy_b200 import ops
+    it, n = g["iter"], g["n"]
+    eng = _engine_from_gold(g)
+    x_probe = (g["s"][None] + 0.01 * randn(it["x_probe_seed"], 1, n)).cuda()
+    y = g["y"].cuda()
+    Y = eng.loss_stft.forward(y)
+    noise = randn(it["noise_seed"], 13824).cuda()[None]
+    st = eng.state
+    p0 = {k: st[k].clone() for k in ("decays", "weights", "phases")}
+    grads = []
+    orig = ops.adam_project
+
+    def capture(p, gr, m, v, *a):     # intercept the optimiser step: record the gradient, leave parameters alone
+        grads.append(gr.clone())
+    import buddy_b200.blind as bl
+    bl.ops.adam_project = capture
+    try:
+        hp = dict(iters=1, lr=0.1, beta1=0.9, beta2=0.99, comp=0.667, w_rec=512.0, w_reg=2560.0, crop_max=0.01,
+                  crop_min=5e-4)
+        eng.optimize(x_probe, Y, 0.5, lambda shape: noise, hp)
+    finally:
+        bl.ops.adam_project = orig
+    rec, reg = eng.last_losses
+    assert abs(rec.item() - it["rec"].item()) / it["rec"].item() < 1e-4
+    assert abs(reg.item() - it["reg"].item()) / it["reg"].item() < 1e-4
+    gd, gw, gp = grads[0], grads[1], grads[2].view(513, 100)
+    e = (rel(gd.cpu(), it["g_decays"]), rel(gw.cpu(), it["g_weights"]), rel(gp.cpu(), it["g_phases"]))
+    print(f"\n[blind iteration grads] decays {e[0]:.2e} weights {e[1]:.2e} phases {e[2]:.2e}")
+    assert max(e) < 1e-3
+
+
+def test_adam_project_matches_torch():
+    from buddy_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, n = 2, 51300
+    p = torch.randn(B, n, device="cuda", generator=g)
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=0.1, betas=(0.9, 0.99))
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    inf = float("inf")
+    for step in range(1, 4):
+        gr = torch.randn(B, n, device="cuda", generator=g)
+        pr.grad = gr.clone()
+        opt.step()
+        ops.adam_project(p, gr, m, v, step, 0.1, 0.9, 0.99, 1e-8, -inf, inf, -inf, inf)
+    assert rel(p, pr.detach()) < 1e-6
+    d = torch.full((1, 25), 0.5, device="cuda")
+    ops.adam_project(d, torch.full_like(d, -1.0), torch.zeros_like(d), torch.zeros_like(d), 1, 0.1, 0.9, 0.99, 1e-8,
+                     0.027632, 0.55264, -inf, inf)
+    assert abs(d.max().item() - 0.55264) < 1e-6
+
+
+def test_blind_dps_trajectory_vs_reference_fixture():
+    from buddy_b200.edm import EDM
+    from buddy_b200.ncsnpp import NCSNppTime
+    from buddy_b200.samplers import EulerHeunSamplerDPS
+    from oracle import ref_harness as rh
+    from oracle.weights import make_state_dict
+    g = torch.load(os.path.join(GOLD, "sampler_blind_T2.pt"), weights_only=False)
+    T, n = g["T"], g["n"]
+    net = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    net.load_state_dict(make_state_dict(0))
+    net = net.cuda().eval()
+    smp = EulerHeunSamplerDPS(net, EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10)),
+                              rh.make_args("blind", T))
+    step_noise = [randn(g["step_noise_seed0"] + i, 1, n) for i in range(T + 1)]
+    rir_noise = [randn(g["rir_noise_seed0"] + i, 13824) for i in range(10 * T)]
+    order = [step_noise[0]]
+    for i in range(T):
+        order.append(step_noise[1 + i])
+        order += rir_noise[10 * i:10 * (i + 1)]
+    smp.noise_source = iter(order)
+
+    class Op:      # duck-typed stand-in for the reference BlindSubbandFiltering object (only its state is read)
+        pass
+    op = Op()
+    i = g["init"]
+    op.params = [i["decays"].clone(), i["weights"].clone()]
+    op.params_phases = [i["phases"].clone()]
+    op.H = i["H"].clone()
+    pred = smp.predict_conditional(g["y"].cuda(), op, shape=(1, n), blind=True)
+    e_pred = rel(pred.cpu(), g["pred"])
+    e_H = rel(torch.view_as_real(op.H.cpu()), torch.view_as_real(g["final_H"]))
+    e_d = rel(op.params[0].cpu(), g["final_decays"])
+    e_w = rel(op.params[1].cpu(), g["final_weights"])
+    print(f"\n[blind DPS T2] pred {e_pred:.2e}  H {e_H:.2e}  decays {e_d:.2e}  weights {e_w:.2e}")
+    # 20 Adam iterations: the optimiser divides each element by its own gradient scale, so elements with noise-level
+    # gradients take +-lr steps in an implementation-dependent direction (the reference and its fp32 restatement already
+    # differ by 5e-4 / 4e-3 (pred / H) here, tests/test_oracle_golden.py::test_blind_dps_sampler).  Every deterministic
+    # stage is pinned tightly elsewhere in this file (one-iteration losses/gradients 1e-4..1e-3, update_H 1e-4) and
+    # test_blind_single_iteration_trajectory below holds 1e-3 on the trajectory itself.
+    assert e_pred < 5e-3 and e_H < 2e-2 and e_d < 5e-3 and e_w < 5e-3
+
+
+def test_blind_single_iteration_trajectory_vs_oracle():
+    """T=2 blind DPS with ONE operator update per step (no chaotic amplification): 1e-3 on the sampler output."""
+    from buddy_b200.edm import EDM
+    from buddy_b200.ncsnpp import NCSNppTime
+    from buddy_b200.samplers import EulerHeunSamplerDPS
+    from oracle import ref_harness as rh
+    from oracle import sampler as osm
+    from oracle.weights import make_state_dict
+    g = torch.load(os.path.join(GOLD, "sampler_blind_T2.pt"), weights_only=False)
+    T, n, i = 2, g["n"], g["init"]
+    sd = make_state_dict(0)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    step_noise = [randn(300 + k, 1, n) for k in range(T + 1)]
+    rir_noise = [randn(400 + k, 13824) for k in range(T)]
+    st = osm.BlindState(i["decays"].cuda(), i["weights"].cuda(), i["phases"].cuda(), i["H"].cuda())
+    pref = osm.dps_blind(sdc, g["y"].cuda(), st, T, [z.cuda() for z in step_noise], [z.cuda() for z in rir_noise],
+                         n_iter=1)
+    net = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    args = rh.make_args("blind", T)
+    args.tester.posterior_sampling.blind_hp["op_updates_per_step"] = 1
+    smp = EulerHeunSamplerDPS(net, EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10)), args)
+    order = [step_noise[0]]
+    for k in range(T):
+        order += [step_noise[1 + k], rir_noise[k]]
+    smp.noise_source = iter(order)
+
+    class Op:
+        pass
+    op = Op()
+    op.params, op.params_phases, op.H = [i["decays"].clone(), i["weights"].clone()], [i["phases"].clone()], i["H"].clone()
+    pred = smp.predict_conditional(g["y"].cuda(), op, shape=(1, n), blind=True)
+    e = rel(pred, pref)
+    eH = rel(torch.view_as_real(op.H), torch.view_as_real(st.H.detach()))
+    print(f"\n[blind DPS T2, 1 op-iteration/step] pred {e:.2e} H {eH:.2e}")
+    assert e < 1e-3 and eH < 1e-3
