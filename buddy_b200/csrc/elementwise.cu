@@ -132,6 +132,8 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, long long P, int C,
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm apply (+SiLU) (+resample) -> fp16 operand; optional raw fp16 copy of x for the 1x1 skip conv
+// Thread = one fixed 4-channel bundle, looping over pixels (two per iteration, loads issued first): all per-channel
+// constants (rstd*gamma, beta - mean*rstd*gamma) are hoisted into registers, the inner loop is FMA + SiLU + stores.
 // ------------------------------------------------------------------------------------------------
 struct GnApplyArgs {
   GnSrc s;
@@ -147,73 +149,119 @@ struct GnApplyArgs {
   int split;
 };
 
-__device__ __forceinline__ void gn_act8(const float (&x)[8], int c, const float* s_mean, const float* s_rstd,
-                                        const float* gamma, const float* beta, int cpg, int silu, float (&y)[8]) {
-  float g[8], be[8];
-  load8(gamma + c, g);
-  load8(beta + c, be);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int grp = (c + j) / cpg;
-    const float z = (x[j] - s_mean[grp]) * s_rstd[grp] * g[j] + be[j];
-    y[j] = silu ? silu_f(z) : z;
+__device__ __forceinline__ float4 ld4(const GnSrc& s, long long pix, int c) {
+  const float* p = (c < s.Ca) ? s.xa + pix * s.Ca + c : s.xb + pix * s.Cb + (c - s.Ca);
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ uint2 pack4h(float a, float b, float c, float d) {
+  __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(c, d);
+  uint2 q;
+  q.x = *reinterpret_cast<uint32_t*>(&h0);
+  q.y = *reinterpret_cast<uint32_t*>(&h1);
+  return q;
+}
+// fp16 operand store of 4 channels; split: row = [hi (C) | lo (C)]
+__device__ __forceinline__ void store_op4(__half* base, long long pix, int C, int c, int split, float4 v) {
+  if (!split) {
+    *reinterpret_cast<uint2*>(base + pix * C + c) = pack4h(v.x, v.y, v.z, v.w);
+    return;
   }
+  const float hx = __half2float(__float2half_rn(v.x)), hy = __half2float(__float2half_rn(v.y));
+  const float hz = __half2float(__float2half_rn(v.z)), hw = __half2float(__float2half_rn(v.w));
+  *reinterpret_cast<uint2*>(base + pix * (2 * C) + c) = pack4h(hx, hy, hz, hw);
+  *reinterpret_cast<uint2*>(base + pix * (2 * C) + C + c) = pack4h(v.x - hx, v.y - hy, v.z - hz, v.w - hw);
+}
+__device__ __forceinline__ float4 act4(float4 x, const float (&sc)[4], const float (&sh)[4], int silu) {
+  float4 y = make_float4(fmaf(x.x, sc[0], sh[0]), fmaf(x.y, sc[1], sh[1]), fmaf(x.z, sc[2], sh[2]),
+                         fmaf(x.w, sc[3], sh[3]));
+  if (silu) {
+    y.x = silu_f(y.x);
+    y.y = silu_f(y.y);
+    y.z = silu_f(y.z);
+    y.w = silu_f(y.w);
+  }
+  return y;
 }
 
-__global__ void gn_apply_kernel(const GnApplyArgs a) {
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyArgs a) {
   __shared__ float s_mean[64], s_rstd[64];
   const int b = blockIdx.y;
   const int C = a.s.Ca + a.s.Cb;
   group_stats_to_smem(s_mean, s_rstd, a.s, b, a.G, a.cpg, static_cast<double>(a.cpg) * a.H * a.W, a.eps);
   __syncthreads();
-  const int c8n = C >> 3;
+  const int c4n = C >> 2;  // blockDim.x is a multiple of c4n
+  const int c = (threadIdx.x % c4n) * 4;
+  const int lane_p = threadIdx.x / c4n;
+  const int ppb = blockDim.x / c4n;
+  float sc[4], sh[4];
+  {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+    const float gv[4] = {g.x, g.y, g.z, g.w}, bv[4] = {be.x, be.y, be.z, be.w};
+    const int grp = c / a.cpg;  // a 4-channel bundle never straddles a group (cpg % 4 == 0)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sc[j] = s_rstd[grp] * gv[j];
+      sh[j] = bv[j] - s_mean[grp] * sc[j];
+    }
+  }
   const int Ho = (a.mode == 1) ? a.H * 2 : (a.mode == 2 ? a.H / 2 : a.H);
   const int Wo = (a.mode == 1) ? a.W * 2 : (a.mode == 2 ? a.W / 2 : a.W);
   const long long Pwork = (a.mode == 2) ? static_cast<long long>(Ho) * Wo : static_cast<long long>(a.H) * a.W;
-  const long long items = Pwork * c8n;
   const long long in_img = static_cast<long long>(b) * a.H * a.W;
   const long long out_img = static_cast<long long>(b) * Ho * Wo;
-  for (long long it = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; it < items;
-       it += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long p = it / c8n;
-    const int c = static_cast<int>(it - p * c8n) * 8;
-    float x[8], y[8];
+  const long long stride = static_cast<long long>(gridDim.x) * ppb;
+  for (long long p0 = static_cast<long long>(blockIdx.x) * ppb + lane_p; p0 < Pwork; p0 += 2 * stride) {
+    const long long p1 = p0 + stride;
+    const bool has1 = p1 < Pwork;
     if (a.mode == 0) {
-      load8(a.s, in_img + p, c, x);
-      gn_act8(x, c, s_mean, s_rstd, a.gamma, a.beta, a.cpg, a.silu, y);
-      store_op8(a.out, out_img + p, C, c, a.split, y);
-      if (a.out_raw) store_op8(a.out_raw, out_img + p, C, c, a.split, x);
-    } else if (a.mode == 1) {
-      const int h = static_cast<int>(p / a.W), w = static_cast<int>(p - static_cast<long long>(h) * a.W);
-      load8(a.s, in_img + p, c, x);
-      gn_act8(x, c, s_mean, s_rstd, a.gamma, a.beta, a.cpg, a.silu, y);
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const long long po = out_img + static_cast<long long>(2 * h + (d >> 1)) * Wo + (2 * w + (d & 1));
-        store_op8(a.out, po, C, c, a.split, y);
-        if (a.out_raw) store_op8(a.out_raw, po, C, c, a.split, x);
+      const float4 x0 = ld4(a.s, in_img + p0, c);
+      const float4 x1 = has1 ? ld4(a.s, in_img + p1, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      store_op4(a.out, out_img + p0, C, c, a.split, act4(x0, sc, sh, a.silu));
+      if (a.out_raw) store_op4(a.out_raw, out_img + p0, C, c, a.split, x0);
+      if (has1) {
+        store_op4(a.out, out_img + p1, C, c, a.split, act4(x1, sc, sh, a.silu));
+        if (a.out_raw) store_op4(a.out_raw, out_img + p1, C, c, a.split, x1);
       }
-    } else {
-      const int ho = static_cast<int>(p / Wo), wo = static_cast<int>(p - static_cast<long long>(ho) * Wo);
-      float ya[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    } else if (a.mode == 1) {
+      const float4 x0 = ld4(a.s, in_img + p0, c);
+      const float4 x1 = has1 ? ld4(a.s, in_img + p1, c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const long long pi = in_img + static_cast<long long>(2 * ho + (d >> 1)) * a.W + (2 * wo + (d & 1));
-        load8(a.s, pi, c, x);
-        gn_act8(x, c, s_mean, s_rstd, a.gamma, a.beta, a.cpg, a.silu, y);
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !has1) break;
+        const long long p = u ? p1 : p0;
+        const float4 x = u ? x1 : x0;
+        const float4 y = act4(x, sc, sh, a.silu);
+        const int h = static_cast<int>(p / a.W), w = static_cast<int>(p - static_cast<long long>(h) * a.W);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          ya[j] += y[j];
-          xa[j] += x[j];
+        for (int d = 0; d < 4; ++d) {
+          const long long po = out_img + static_cast<long long>(2 * h + (d >> 1)) * Wo + (2 * w + (d & 1));
+          store_op4(a.out, po, C, c, a.split, y);
+          if (a.out_raw) store_op4(a.out_raw, po, C, c, a.split, x);
         }
       }
+    } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        ya[j] *= 0.25f;
-        xa[j] *= 0.25f;
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !has1) break;
+        const long long p = u ? p1 : p0;
+        const int ho = static_cast<int>(p / Wo), wo = static_cast<int>(p - static_cast<long long>(ho) * Wo);
+        float4 xs[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+          xs[d] = ld4(a.s, in_img + static_cast<long long>(2 * ho + (d >> 1)) * a.W + (2 * wo + (d & 1)), c);
+        float4 ya = make_float4(0.f, 0.f, 0.f, 0.f), xa = ya;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const float4 y = act4(xs[d], sc, sh, a.silu);
+          ya.x += y.x; ya.y += y.y; ya.z += y.z; ya.w += y.w;
+          xa.x += xs[d].x; xa.y += xs[d].y; xa.z += xs[d].z; xa.w += xs[d].w;
+        }
+        ya = make_float4(ya.x * 0.25f, ya.y * 0.25f, ya.z * 0.25f, ya.w * 0.25f);
+        xa = make_float4(xa.x * 0.25f, xa.y * 0.25f, xa.z * 0.25f, xa.w * 0.25f);
+        store_op4(a.out, out_img + p, C, c, a.split, ya);
+        if (a.out_raw) store_op4(a.out_raw, out_img + p, C, c, a.split, xa);
       }
-      store_op8(a.out, out_img + p, C, c, a.split, ya);
-      if (a.out_raw) store_op8(a.out_raw, out_img + p, C, c, a.split, xa);
     }
   }
 }
@@ -223,6 +271,7 @@ __global__ void gn_apply_kernel(const GnApplyArgs a) {
 //   da : fp32 gradient w.r.t. the activation output, at the conv's resolution, C = Ca + Cb channels
 //   pass 1 (gn_bwd_stats): per (image, group) S1 = sum dxh, S2 = sum dxh*xh   (dxh = dz*gamma)
 //   pass 2 (gn_bwd)      : dx = rstd*(dxh - S1/n - xh*S2/n) + R^T(dskip)*skip_scale + extra
+// Thread = one fixed 4-channel bundle (constants hoisted), looping over pixels.
 // ------------------------------------------------------------------------------------------------
 struct GnBwdArgs {
   GnSrc s;
@@ -247,117 +296,102 @@ struct GnBwdArgs {
   int split;
 };
 
-// gradient w.r.t. the activation output pulled back through the resample, for x-pixel (h,w), channels c..c+8
-__device__ __forceinline__ void pull_back8(const float* t, int mode, int b, int h, int w, int H, int W, int C, int c,
-                                           float (&g)[8]) {
+// gradient w.r.t. the activation output pulled back through the resample, for x-pixel (h,w), channels c..c+4
+__device__ __forceinline__ float4 pull_back4(const float* __restrict__ t, int mode, int b, int h, int w, int H, int W,
+                                             int C, int c) {
   if (mode == 0) {
-    load8(t + ((static_cast<long long>(b) * H + h) * W + w) * C + c, g);
+    return __ldg(reinterpret_cast<const float4*>(t + ((static_cast<long long>(b) * H + h) * W + w) * C + c));
   } else if (mode == 1) {  // forward was nearest x2: sum the 4 children
     const int Wc = 2 * W;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
-      load8(t + ((static_cast<long long>(b) * 2 * H + 2 * h + (d >> 1)) * Wc + 2 * w + (d & 1)) * C + c, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] += v[j];
+      const float4 v = __ldg(reinterpret_cast<const float4*>(
+          t + ((static_cast<long long>(b) * 2 * H + 2 * h + (d >> 1)) * Wc + 2 * w + (d & 1)) * C + c));
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
     }
+    return g;
   } else {  // forward was 2x2 mean: a quarter of the parent
     const int Hc = H / 2, Wc = W / 2;
-    load8(t + ((static_cast<long long>(b) * Hc + (h >> 1)) * Wc + (w >> 1)) * C + c, g);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
+    const float4 v =
+        __ldg(reinterpret_cast<const float4*>(t + ((static_cast<long long>(b) * Hc + (h >> 1)) * Wc + (w >> 1)) * C + c));
+    return make_float4(v.x * 0.25f, v.y * 0.25f, v.z * 0.25f, v.w * 0.25f);
   }
 }
 
 template <bool kPass2>
-__global__ void gn_bwd_kernel(const GnBwdArgs a) {
-  __shared__ float s_mean[64], s_rstd[64], s_m1[64], s_m2[64];
+__global__ void __launch_bounds__(256, 4) gn_bwd_kernel(const GnBwdArgs a) {
+  __shared__ float s_mean[64], s_rstd[64];
   __shared__ float s_acc[64][2];
   const int b = blockIdx.y;
   const int C = a.s.Ca + a.s.Cb;
   const double n = static_cast<double>(a.cpg) * a.H * a.W;
   group_stats_to_smem(s_mean, s_rstd, a.s, b, a.G, a.cpg, n, a.eps);
-  if (kPass2) {
-    for (int g = threadIdx.x; g < a.G; g += blockDim.x) {
-      s_m1[g] = static_cast<float>(a.gsum[(static_cast<long long>(b) * a.G + g) * 2] / n);
-      s_m2[g] = static_cast<float>(a.gsum[(static_cast<long long>(b) * a.G + g) * 2 + 1] / n);
-    }
-  } else {
+  if (!kPass2)
     for (int g = threadIdx.x; g < a.G; g += blockDim.x) s_acc[g][0] = s_acc[g][1] = 0.f;
-  }
   __syncthreads();
-  const int c8n = C >> 3;  // blockDim.x is a multiple of c8n -> each thread keeps one channel chunk
-  const int c = (threadIdx.x % c8n) * 8;
+  const int c4n = C >> 2;  // blockDim.x is a multiple of c4n -> each thread keeps one channel bundle
+  const int c = (threadIdx.x % c4n) * 4;
+  const int grp = c / a.cpg;
   const long long P = static_cast<long long>(a.H) * a.W;
-  const long long ppb = blockDim.x / c8n;
-  float gam[8], bet[8];
-  load8(a.gamma + c, gam);
-  load8(a.beta + c, bet);
-  float p1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, p2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / c8n; p < P;
+  const int ppb = blockDim.x / c4n;
+  const float rstd = s_rstd[grp], nmr = -s_mean[grp] * rstd;  // xh = x*rstd + nmr
+  float gam[4], bet[4];
+  {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+    gam[0] = g.x; gam[1] = g.y; gam[2] = g.z; gam[3] = g.w;
+    bet[0] = be.x; bet[1] = be.y; bet[2] = be.z; bet[3] = be.w;
+  }
+  float m1 = 0.f, m2 = 0.f;
+  if (kPass2) {
+    m1 = static_cast<float>(a.gsum[(static_cast<long long>(b) * a.G + grp) * 2] / n);
+    m2 = static_cast<float>(a.gsum[(static_cast<long long>(b) * a.G + grp) * 2 + 1] / n);
+  }
+  const bool in_a = c < a.s.Ca;
+  const int cl = in_a ? c : c - a.s.Ca;
+  const int Cl = in_a ? a.s.Ca : a.s.Cb;
+  const float* ex = in_a ? a.extra_a : a.extra_b;
+  float* o32 = in_a ? a.dxa : a.dxb;
+  __half* o16 = in_a ? a.g16a : a.g16b;
+  float p1 = 0.f, p2 = 0.f;
+  for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / c4n; p < P;
        p += static_cast<long long>(gridDim.x) * ppb) {
     const int h = static_cast<int>(p / a.W), w = static_cast<int>(p - static_cast<long long>(h) * a.W);
-    float x[8], g[8];
-    load8(a.s, static_cast<long long>(b) * P + p, c, x);
-    pull_back8(a.da, a.mode, b, h, w, a.H, a.W, C, c, g);
-    float dxh[8], xh[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int grp = (c + j) / a.cpg;
-      xh[j] = (x[j] - s_mean[grp]) * s_rstd[grp];
-      float dz = g[j];
-      if (a.silu) dz *= dsilu_f(xh[j] * gam[j] + bet[j]);
-      dxh[j] = dz * gam[j];
+    const long long pix = static_cast<long long>(b) * P + p;
+    const float4 x4 = ld4(a.s, pix, c);
+    const float4 g4 = pull_back4(a.da, a.mode, b, h, w, a.H, a.W, C, c);
+    float4 sk4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = sk4;
+    if (kPass2) {
+      if (a.dskip) sk4 = pull_back4(a.dskip, a.mode, b, h, w, a.H, a.W, C, c);
+      if (ex) e4 = __ldg(reinterpret_cast<const float4*>(ex + pix * Cl + cl));
     }
-    if (!kPass2) {
+    const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
+    const float sv[4] = {sk4.x, sk4.y, sk4.z, sk4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
+    float dx[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        p1[j] += dxh[j];
-        p2[j] += dxh[j] * xh[j];
+    for (int j = 0; j < 4; ++j) {
+      const float xh = fmaf(xv[j], rstd, nmr);
+      float dz = gv[j];
+      if (a.silu) dz *= dsilu_f(fmaf(xh, gam[j], bet[j]));
+      const float dxh = dz * gam[j];
+      if (!kPass2) {
+        p1 += dxh;
+        p2 = fmaf(dxh, xh, p2);
+      } else {
+        dx[j] = rstd * (dxh - m1 - xh * m2) + sv[j] * a.skip_scale + ev[j];
       }
-    } else {
-      float dx[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int grp = (c + j) / a.cpg;
-        dx[j] = s_rstd[grp] * (dxh[j] - s_m1[grp] - xh[j] * s_m2[grp]);
-      }
-      if (a.dskip) {
-        float sk[8];
-        pull_back8(a.dskip, a.mode, b, h, w, a.H, a.W, C, c, sk);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dx[j] += sk[j] * a.skip_scale;
-      }
-      const bool in_a = c < a.s.Ca;
-      const int cl = in_a ? c : c - a.s.Ca;
-      const int Cl = in_a ? a.s.Ca : a.s.Cb;
-      const long long off = (static_cast<long long>(b) * P + p) * Cl + cl;
-      const float* ex = in_a ? a.extra_a : a.extra_b;
-      if (ex) {
-        float e[8];
-        load8(ex + off, e);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dx[j] += e[j];
-      }
-      float* o32 = in_a ? a.dxa : a.dxb;
-      if (o32) store8(o32 + off, dx);
-      __half* o16 = in_a ? a.g16a : a.g16b;
-      if (o16) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dx[j] *= a.g16_scale;
-        store_op8(o16, static_cast<long long>(b) * P + p, Cl, cl, a.split, dx);
-      }
+    }
+    if (kPass2) {
+      if (o32) *reinterpret_cast<float4*>(o32 + pix * Cl + cl) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+      if (o16)
+        store_op4(o16, pix, Cl, cl, a.split,
+                  make_float4(dx[0] * a.g16_scale, dx[1] * a.g16_scale, dx[2] * a.g16_scale, dx[3] * a.g16_scale));
     }
   }
   if (!kPass2) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int grp = (c + j) / a.cpg;
-      atomicAdd(&s_acc[grp][0], p1[j]);
-      atomicAdd(&s_acc[grp][1], p2[j]);
-    }
+    atomicAdd(&s_acc[grp][0], p1);
+    atomicAdd(&s_acc[grp][1], p2);
     __syncthreads();
     for (int g = threadIdx.x; g < a.G; g += blockDim.x) {
       atomicAdd(a.gsum + (static_cast<long long>(b) * a.G + g) * 2, static_cast<double>(s_acc[g][0]));
@@ -647,7 +681,7 @@ extern "C" int buddy_gn_stats(const float* x, int B, int64_t P, int C, double* s
 
 static int check_gn(int Ca, int Cb, int G, const char* who) {
   const int C = Ca + Cb;
-  if (Ca % 8 || Cb % 8 || C <= 0 || G <= 0 || G > 64 || C % G || (C / G) % 4) {
+  if (Ca % 8 || Cb % 8 || C <= 0 || C > 1024 || G <= 0 || G > 64 || C % G || (C / G) % 4) {
     set_last_error("%s: unsupported channel/group configuration Ca=%d Cb=%d G=%d", who, Ca, Cb, G);
     return BUDDY_ERR_UNSUPPORTED;
   }
@@ -675,9 +709,14 @@ extern "C" int buddy_gn_apply(const buddy_gn_desc* d, void* stream) {
   a.out = static_cast<__half*>(d->out);
   a.out_raw = static_cast<__half*>(d->out_raw);
   a.split = d->split;
-  const long long items = static_cast<long long>(d->mode == 2 ? (d->H / 2) * (d->W / 2) : d->H * d->W) *
-                          ((d->Ca + d->Cb) / 8);
-  gn_apply_kernel<<<dim3(grid_for(items, 256, 148 * 8), d->batch), 256, 0, STREAM>>>(a);
+  const int c4n = (d->Ca + d->Cb) / 4;
+  const int threads = c4n * (256 / c4n > 0 ? 256 / c4n : 1);
+  const long long ppb = threads / c4n;
+  const long long Pw = static_cast<long long>(d->mode == 2 ? (d->H / 2) * (d->W / 2) : d->H * d->W);
+  long long gx = (Pw + ppb * 8 - 1) / (ppb * 8);   // ~8 pixels per thread
+  if (gx > 148 * 16) gx = 148 * 16;
+  if (gx < 1) gx = 1;
+  gn_apply_kernel<<<dim3((unsigned)gx, d->batch), threads, 0, STREAM>>>(a);
   LAUNCH_END("gn_apply_kernel");
 }
 
@@ -708,12 +747,12 @@ extern "C" int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, 
   a.g16b = static_cast<__half*>(g->g16b);
   a.g16_scale = g->g16_scale;
   a.split = d->split;
-  const int c8n = C / 8;
-  const int threads = c8n * (256 / c8n > 0 ? 256 / c8n : 1);
-  const long long ppb = threads / c8n;
+  const int c4n = C / 4;
+  const int threads = c4n * (256 / c4n > 0 ? 256 / c4n : 1);
+  const long long ppb = threads / c4n;
   const long long P = static_cast<long long>(d->H) * d->W;
-  long long gx = (P + ppb * 4 - 1) / (ppb * 4);
-  if (gx > 148 * 8) gx = 148 * 8;
+  long long gx = (P + ppb * 8 - 1) / (ppb * 8);
+  if (gx > 148 * 16) gx = 148 * 16;
   if (gx < 1) gx = 1;
   e = check_cuda(cudaMemsetAsync(g->gsum, 0, sizeof(double) * 2 * d->groups * d->batch, STREAM), "memset gsum");
   if (e) return e;
