@@ -159,6 +159,21 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def blind_args(T):
+    a = informed_args(T)
+    sp = a.tester.sampling_params
+    sp["Schurn"], sp["order"] = 50, 1
+    loss = a.tester.posterior_sampling.rec_loss
+    a.tester["posterior_sampling"] = AD(
+        zeta=0.5, rec_loss=loss, rec_loss_params=loss,
+        RIR_noise_regularization=AD(use=True, crop_sigma_max=0.01, crop_sigma_min=5e-4,
+                                    loss=AD(name="l2_comp_stft_summean", weight=2560, compression_factor=0.667)),
+        blind_hp=AD(optimizer="adam", lr_op=0.1, beta1=0.9, beta2=0.99, weight_decay=0, op_updates_per_step=10),
+        warm_initialization=AD(mode="reverb_scaled", scaling_factor=0.05),
+        constraint_speech_magnitude=AD(use=True, speech_scaling=0.05))
+    return a
+
+
 def config_dict(batch, precision):
     return {"workload": "informed EulerHeunSamplerDPS T=35 order 2, synthetic 4.096 s @ 16 kHz (65536 samples), "
                         "NCSN++ 27.7M random-init (non-degenerate) weights",
@@ -205,12 +220,36 @@ def run_ours(args):
     y = op.degradation(s_host.to(dev))
     y_host = y.cpu().pin_memory()
 
+    blind = args.mode == "blind"
+    T_run = 60 if blind else T_STEPS
     smp = EulerHeunSamplerDPS(net, EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10)),
-                              informed_args(T_STEPS))
+                              blind_args(T_run) if blind else informed_args(T_STEPS))
     smp.utterance_offset = rank * B
     smp.micro_batch = args.micro_batch
-    smp.operator, smp.y = op, y
-    smp._bind_operator(op, y, False)
+    if blind:
+        # reference initialisation (tester.py:149-151): T60 = 0.1 s, weight 2, phases of coherent noise, per utterance
+        from buddy_b200.blind import BlindEngine
+        be = BlindEngine(N_SAMPLES, dev)
+        g = torch.Generator().manual_seed(4000 + rank)
+        ph0 = torch.angle(torch.view_as_complex(be.loss_stft.forward(
+            torch.randn(B, be.LEN_RIR, generator=g).to(dev))[:, :, 1:101].contiguous()))
+        be.init_state(B, torch.full((1, 25), 6.908 / (0.1 * 125)), torch.full((1, 25), 2.0), ph0,
+                      torch.zeros(B, 513, 100, dtype=torch.complex64))
+        be.select(slice(0, B))
+        H0 = torch.view_as_complex(be.update_H())
+
+        class _Op:
+            pass
+        bop = _Op()
+        bop.params = [be.full["decays"].clone(), be.full["weights"].clone()]
+        bop.params_phases = [torch.angle(H0)]
+        bop.H = H0
+        del be
+        smp.operator, smp.y = bop, y
+        smp._bind_operator(bop, y, True)
+    else:
+        smp.operator, smp.y = op, y
+        smp._bind_operator(op, y, False)
     t = smp.create_schedule()
     gamma = smp.get_gamma(t)
     x = smp.initialize_x((B, N_SAMPLES), dev, t)
@@ -224,9 +263,9 @@ def run_ours(args):
 
     def one_step(xc):
         nonlocal step_i
-        i = step_i % (T_STEPS - 1)      # Heun steps only (the final Euler step is half a step)
+        i = step_i % (T_run - 1)        # regular steps only (the final step of a trajectory is an Euler step)
         step_i += 1
-        xn, _ = smp.step(xc, t[i], t[i + 1], gamma[i])
+        xn, _ = smp.step(xc, t[i], t[i + 1], gamma[i], blind)
         return xn
 
     for _ in range(args.warmup):
@@ -262,9 +301,9 @@ def run_ours(args):
         xd = x_host.to(dev, non_blocking=True)
         smp.y = y_host.to(dev, non_blocking=True)
         smp._Y = smp._loss_stft.forward(smp.y)      # observation spectrum recomputed from the fresh copy
-        i = step_i % (T_STEPS - 1)
+        i = step_i % (T_run - 1)
         step_i += 1
-        xn, xden = smp.step(xd, t[i], t[i + 1], gamma[i])
+        xn, xden = smp.step(xd, t[i], t[i + 1], gamma[i], blind)
         out_host[0].copy_(xn, non_blocking=True)
         out_host[1].copy_(xden, non_blocking=True)
         torch.cuda.synchronize()
@@ -292,8 +331,9 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": f"f16 operands x{np_} passes / f32 accumulate+activations",
         "data": "synthetic", "config": config_dict(B, args.precision),
-        "utterances_per_sec": value * 2 / EVALS_PER_UTT,
-        "evals_per_sec": value * 2, "algorithmic_tflops": value * 2 * GFLOP_PER_EVAL / 1e3,
+        "utterances_per_sec": (value / 60) if blind else (value * 2 / EVALS_PER_UTT),
+        "evals_per_sec": value * (1 if blind else 2),
+        "algorithmic_tflops": value * (1 if blind else 2) * GFLOP_PER_EVAL / 1e3,
         "e2e": {"value": e2e_value, "unit": "utterance-steps/s", "h2d_bytes_per_step": 2 * B * N_SAMPLES * 4,
                 "d2h_bytes_per_step": 2 * B * N_SAMPLES * 4},
         "gpu_launches": int(launches),
@@ -308,7 +348,12 @@ def run_ours(args):
         "kernel_time_share": {k: round(v[1] / total_ms_ops, 4) for k, v in
                               sorted(summ.items(), key=lambda kv: -kv[1][1])[:6]},
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if blind:
+        line["config"]["workload"] = ("blind EulerHeunSamplerDPS T=60 order 1 + 10 operator-Adam iterations per step "
+                                      "(BASELINE configs[2]), synthetic 4.096 s @ 16 kHz")
+        line["config"]["step_definition"] = "one Euler sampler step over the batch = 1 network fwd+VJP + 10 operator updates"
+        line["config"]["T"], line["config"]["order"], line["config"]["evals_per_utterance"] = 60, 1, 60
+    if world == 1 and not args.no_cpu_baseline and not blind:
         sec, threads = cpu_reference_step_time(1, 0)
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "utterance-steps/s", "cores": threads, "kind": "port",
                                 "sample": "B=1, ONE Euler-Heun DPS step (2 fwd+VJP evaluations) of the same config, "
@@ -328,6 +373,9 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=16)
     ap.add_argument("--precision", default=os.environ.get("BUDDY_PRECISION", "fp16x3"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="informed", choices=["informed", "blind"],
+                    help="informed = BASELINE configs[1] (default, the bench line); blind = configs[2] (order 1, T=60, "
+                         "10 operator-Adam iterations per step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
