@@ -33,6 +33,10 @@ class GemmDesc(ctypes.Structure):
         ("out", c_void_p), ("out_fp16", c_int), ("ldc", c_i64), ("col_off", c_int),
         ("bias", c_void_p), ("bias_b", c_void_p), ("resid", c_void_p), ("ld_res", c_i64),
         ("scale", c_float), ("stats", c_void_p), ("max_ctas", c_int), ("k_total", c_int), ("k2_total", c_int),
+        ("a8", c_void_p), ("a8_c", c_int), ("a8_stride_w", c_i64), ("a8_stride_h", c_i64), ("a8_stride_b", c_i64),
+        ("b8", c_void_p),
+        ("a8_2", c_void_p), ("a8_2_c", c_int), ("a8_2_stride_w", c_i64), ("a8_2_stride_h", c_i64),
+        ("a8_2_stride_b", c_i64), ("b8_2", c_void_p),
     ]
 
 
@@ -86,6 +90,7 @@ class GnDesc(ctypes.Structure):
         ("stats_a", c_void_p), ("stats_b", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
         ("batch", c_int), ("H", c_int), ("W", c_int), ("groups", c_int), ("eps", c_float),
         ("silu", c_int), ("mode", c_int), ("out", c_void_p), ("out_raw", c_void_p), ("split", c_int),
+        ("out8", c_void_p), ("out_raw8", c_void_p),
     ]
 
 
@@ -95,4 +100,5 @@ class GnBwdDesc(ctypes.Structure):
         ("da", c_void_p), ("dskip", c_void_p), ("skip_scale", c_float),
         ("extra_a", c_void_p), ("extra_b", c_void_p), ("gsum", c_void_p),
         ("dxa", c_void_p), ("dxb", c_void_p), ("g16a", c_void_p), ("g16b", c_void_p), ("g16_scale", c_float),
+        ("g8a", c_void_p), ("g8b", c_void_p),
     ]

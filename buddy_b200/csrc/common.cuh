@@ -134,6 +134,26 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, but the accumulator input is first scaled by 2^-14:  D = A*B + D * 2^-14  (scale-input-d immediate).
+// Used right after the fp8 correction passes, which accumulate 2^14 * (a_lo*w_hi + a_hi*w_lo).
+__device__ __forceinline__ void umma_f16_scale_d14(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 14;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc)
+      : "memory");
+}
+// kind::f8f6f4 (here: e4m3 x e4m3, fp32 accumulate), K = 32 per instruction
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -173,6 +193,17 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
   d |= 0u << 10;                                // b_format = F16
   d |= static_cast<uint32_t>(N >> 3) << 17;     // n_dim
   d |= static_cast<uint32_t>(M >> 4) << 24;     // m_dim
+  return d;
+}
+
+// kind::f8f6f4 instruction descriptor: e4m3 A/B (format code 0), K-major both, fp32 accumulate
+__host__ __device__ __forceinline__ uint32_t make_idesc_e4m3(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                                 // c_format = F32
+  d |= 0u << 7;                                 // a_format = E4M3
+  d |= 0u << 10;                                // b_format = E4M3
+  d |= static_cast<uint32_t>(N >> 3) << 17;
+  d |= static_cast<uint32_t>(M >> 4) << 24;
   return d;
 }
 

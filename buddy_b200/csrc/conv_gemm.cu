@@ -37,6 +37,7 @@ struct GemmParams {
   int n_tiles, n_tile, n_total;
   int taps, kchunks1, kchunks2, b_batched;
   int a_wrap1, a_wrap2;  // A-side channel chunk = k-chunk % a_wrap (split-precision operands re-read the hi half)
+  int kchunks8_1, kchunks8_2;  // fp8 correction phases (128-byte chunks per tap / for the skip conv); 0 = none
   int stages;
   float* out32;
   __half* out16;
@@ -53,6 +54,8 @@ struct GemmParams {
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                 const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8,
+                 const __grid_constant__ CUtensorMap tmA82, const __grid_constant__ CUtensorMap tmB82,
                  const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16B aligned by the runtime: round up to 1024 (swizzle-128B atoms)
@@ -96,8 +99,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const int total_tiles = p.batch * tiles_per_img * p.n_tiles;
+  // k-block order: [fp8 correction: conv taps | skip conv] then [fp16: conv taps | skip conv]
+  const int kb8_1 = p.taps * p.kchunks8_1;
+  const int kb8 = kb8_1 + p.kchunks8_2;
   const int kb_phase1 = p.taps * p.kchunks1;
-  const int num_kb = kb_phase1 + p.kchunks2;
+  const int num_kb = kb8 + kb_phase1 + p.kchunks2;
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -116,9 +122,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kStageA;
           mbar_expect_tx(&full_bar[stage], stage_bytes);
-          if (kb < kb_phase1) {
-            const int tap = kb / p.kchunks1;
-            const int kc = kb - tap * p.kchunks1;
+          if (kb < kb8) {
+            if (kb < kb8_1) {
+              const int tap = kb / p.kchunks8_1;
+              const int kc = kb - tap * p.kchunks8_1;
+              int dy = 0, dx = 0;
+              if (p.taps == 9) {
+                dy = tap / 3 - 1;
+                dx = tap % 3 - 1;
+              }
+              tma_load_4d(&tmA8, sa, &full_bar[stage], kc * 128, w0 + dx, h0 + dy, b);
+              tma_load_3d(&tmB8, sb, &full_bar[stage], kc * 128, nt * p.n_tile, tap);
+            } else {
+              const int kc = kb - kb8_1;
+              tma_load_4d(&tmA82, sa, &full_bar[stage], kc * 128, w0, h0, b);
+              tma_load_3d(&tmB82, sb, &full_bar[stage], kc * 128, nt * p.n_tile, 0);
+            }
+          } else if (kb - kb8 < kb_phase1) {
+            const int kk = kb - kb8;
+            const int tap = kk / p.kchunks1;
+            const int kc = kk - tap * p.kchunks1;
             int dy = 0, dx = 0;
             if (p.taps == 9) {
               dy = tap / 3 - 1;
@@ -127,7 +150,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_4d(&tmA, sa, &full_bar[stage], (kc % p.a_wrap1) * kBlockK, w0 + dx, h0 + dy, b);
             tma_load_3d(&tmB, sb, &full_bar[stage], kc * kBlockK, nt * p.n_tile, p.b_batched ? b : tap);
           } else {
-            const int kc = kb - kb_phase1;
+            const int kc = kb - kb8 - kb_phase1;
             tma_load_4d(&tmA2, sa, &full_bar[stage], (kc % p.a_wrap2) * kBlockK, w0, h0, b);
             tma_load_3d(&tmB2, sb, &full_bar[stage], kc * kBlockK, nt * p.n_tile, 0);
           }
@@ -142,6 +165,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================================================ MMA issuer (single thread)
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(kTileM, p.n_tile);
+      const uint32_t idesc8 = make_idesc_e4m3(kTileM, p.n_tile);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -156,10 +180,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint64_t da = make_sw128_kmajor_desc(sa);
           const uint64_t db = make_sw128_kmajor_desc(sa + kStageA);
+          // each MMA consumes 32 bytes of K per row (16 fp16 or 32 e4m3): +2 in (addr >> 4) units
+          if (kb < kb8) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 fp16 = 32 bytes along K inside the 128B swizzle row: +2 in (addr >> 4) units
-            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc8, (kb > 0 || k > 0) ? 1u : 0u);
+          } else if (kb == kb8 && kb8 > 0) {
+            // first fp16 block after the corrections: fold their 2^14 scale away (D = A*B + D * 2^-14)
+            umma_f16_scale_d14(d_tmem, da, db, idesc);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
           if (++stage == p.stages) {
@@ -332,9 +364,9 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// fp16 tensor map with `rank` dims (dim 0 contiguous), 128B swizzle, zero OOB fill.
+// fp16 (esize 2) or byte (esize 1) tensor map with `rank` dims (dim 0 contiguous), 128B swizzle, zero OOB fill.
 static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
-                      const uint32_t* box) {
+                      const uint32_t* box, int esize = 2) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -348,7 +380,7 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
     gdim[i] = dims[i];
     bx[i] = box[i];
     es[i] = 1;
-    if (i > 0) gstr[i - 1] = strides_el[i] * 2;  // bytes
+    if (i > 0) gstr[i - 1] = strides_el[i] * esize;  // bytes
   }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
     set_last_error("tensor map base not 16B aligned");
@@ -359,7 +391,7 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
       set_last_error("tensor map stride %d (%llu bytes) not a multiple of 16", i + 1, (unsigned long long)gstr[i]);
       return BUDDY_ERR_INVALID;
     }
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = fn(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, rank, const_cast<void*>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -473,7 +505,41 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   p.scale = d->scale;
   p.stats = d->stats;
 
-  CUtensorMap tmA, tmB, tmA2, tmB2;
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmA8, tmB8, tmA82, tmB82;
+  p.kchunks8_1 = 0;
+  p.kchunks8_2 = 0;
+  if (d->a8) {
+    if (!d->b8 || d->a8_c <= 0 || d->a8_c % 128 || d->b_batched) {
+      set_last_error("buddy_conv_gemm: fp8 correction operands need b8, a8_c %% 128 == 0 and no batched B");
+      return BUDDY_ERR_UNSUPPORTED;
+    }
+    p.kchunks8_1 = d->a8_c / 128;
+    uint64_t dims[4] = {(uint64_t)d->a8_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
+    uint64_t str[4] = {1, (uint64_t)d->a8_stride_w, (uint64_t)d->a8_stride_h, (uint64_t)d->a8_stride_b};
+    uint32_t box[4] = {128, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    int e = encode_map(&tmA8, d->a8, 4, dims, str, box, 1);
+    if (e) return e;
+    uint64_t dimsb[3] = {(uint64_t)d->a8_c, (uint64_t)d->b_rows, (uint64_t)d->b_t};
+    uint64_t strb[3] = {1, (uint64_t)d->a8_c, (uint64_t)d->a8_c * (uint64_t)d->b_rows};
+    uint32_t boxb[3] = {128, (uint32_t)d->n_tile, 1};
+    e = encode_map(&tmB8, d->b8, 3, dimsb, strb, boxb, 1);
+    if (e) return e;
+    if (d->a2) {
+      if (!d->a8_2 || !d->b8_2 || d->a8_2_c % 128) {
+        set_last_error("buddy_conv_gemm: fp8 correction of the skip conv needs a8_2 / b8_2");
+        return BUDDY_ERR_INVALID;
+      }
+      p.kchunks8_2 = d->a8_2_c / 128;
+      uint64_t dims2[4] = {(uint64_t)d->a8_2_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
+      uint64_t str2[4] = {1, (uint64_t)d->a8_2_stride_w, (uint64_t)d->a8_2_stride_h, (uint64_t)d->a8_2_stride_b};
+      e = encode_map(&tmA82, d->a8_2, 4, dims2, str2, box, 1);
+      if (e) return e;
+      uint64_t dimsb2[3] = {(uint64_t)d->a8_2_c, (uint64_t)d->b2_rows, 1};
+      uint64_t strb2[3] = {1, (uint64_t)d->a8_2_c, (uint64_t)d->a8_2_c * (uint64_t)d->b2_rows};
+      e = encode_map(&tmB82, d->b8_2, 3, dimsb2, strb2, boxb, 1);
+      if (e) return e;
+    }
+  }
   {
     uint64_t dims[4] = {(uint64_t)d->a_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
     uint64_t str[4] = {1, (uint64_t)d->a_stride_w, (uint64_t)d->a_stride_h, (uint64_t)d->a_stride_b};
@@ -503,6 +569,14 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     tmA2 = tmA;
     tmB2 = tmB;
   }
+  if (!d->a8) {
+    tmA8 = tmA;
+    tmB8 = tmB;
+  }
+  if (p.kchunks8_2 == 0) {
+    tmA82 = tmA;
+    tmB82 = tmB;
+  }
 
   const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static bool attr_set = false;
@@ -517,7 +591,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   int grid = num_sms();
   if (d->max_ctas > 0 && d->max_ctas < grid) grid = d->max_ctas;
   if (total_tiles < grid) grid = (int)total_tiles;
-  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmA2, tmB2, tmA8, tmB8, tmA82, tmB82, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   BUDDY_CHECK_LAUNCH("conv_gemm_kernel");
   return 0;

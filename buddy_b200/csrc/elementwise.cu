@@ -6,6 +6,8 @@
 // naive_up/downsample_2d (up_or_down_sampling.py:59-69), Combine (layerspp.py:52-59),
 // AttnBlockpp softmax (layerspp.py:81-85), pyramid up/down (layerspp.py:117,156).
 // All 128-bit loads/stores; one CTA never crosses an image (grid.y = batch index).
+#include <cuda_fp8.h>
+
 #include <atomic>
 
 #include "../../include/buddy_b200.h"
@@ -82,8 +84,25 @@ __device__ __forceinline__ void store8h(__half* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = q;
 }
 
-// fp16 operand store; split: row = [hi (C) | lo (C)], lo = fp16(v - float(hi))
-__device__ __forceinline__ void store_op8(__half* base, long long pix, int C, int c, int split, const float (&v)[8]) {
+__device__ __forceinline__ uint32_t pack4_e4m3(float a, float b, float c, float d);
+// fp16 operand store; split: row = [hi (C) | lo (C)], lo = fp16(v - float(hi)); split 2: fp16 hi + e4m3 pair (base8)
+__device__ __forceinline__ void store_op8(__half* base, long long pix, int C, int c, int split, const float (&v)[8],
+                                          uint8_t* base8 = nullptr) {
+  if (split == 2) {
+    float hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hi[j] = __half2float(__float2half_rn(v[j]));
+      lo[j] = (v[j] - hi[j]) * 512.f;
+    }
+    store8h(base + pix * C + c, hi);
+    uint8_t* r8 = base8 + pix * (2 * C);
+    *reinterpret_cast<uint2*>(r8 + c) =
+        make_uint2(pack4_e4m3(lo[0], lo[1], lo[2], lo[3]), pack4_e4m3(lo[4], lo[5], lo[6], lo[7]));
+    *reinterpret_cast<uint2*>(r8 + C + c) =
+        make_uint2(pack4_e4m3(hi[0], hi[1], hi[2], hi[3]), pack4_e4m3(hi[4], hi[5], hi[6], hi[7]));
+    return;
+  }
   if (!split) {
     store8h(base + pix * C + c, v);
     return;
@@ -147,6 +166,8 @@ struct GnApplyArgs {
   __half* out;
   __half* out_raw;
   int split;
+  uint8_t* out8;
+  uint8_t* out_raw8;
 };
 
 __device__ __forceinline__ float4 ld4(const GnSrc& s, long long pix, int c) {
@@ -160,8 +181,25 @@ __device__ __forceinline__ uint2 pack4h(float a, float b, float c, float d) {
   q.y = *reinterpret_cast<uint32_t*>(&h1);
   return q;
 }
-// fp16 operand store of 4 channels; split: row = [hi (C) | lo (C)]
-__device__ __forceinline__ void store_op4(__half* base, long long pix, int C, int c, int split, float4 v) {
+__device__ __forceinline__ uint32_t pack4_e4m3(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+// fp16 operand store of 4 channels.  split 1: row = [hi (C) | lo (C)] fp16.
+// split 2: fp16 hi in `base` (row C) + e4m3 pair in `base8` (row 2C bytes) = [e4m3(lo * 2^9) | e4m3(hi)].
+__device__ __forceinline__ void store_op4(__half* base, uint8_t* base8, long long pix, int C, int c, int split,
+                                          float4 v) {
+  if (split == 2) {
+    const float hx = __half2float(__float2half_rn(v.x)), hy = __half2float(__float2half_rn(v.y));
+    const float hz = __half2float(__float2half_rn(v.z)), hw = __half2float(__float2half_rn(v.w));
+    *reinterpret_cast<uint2*>(base + pix * C + c) = pack4h(hx, hy, hz, hw);
+    uint8_t* r8 = base8 + pix * (2 * C);
+    *reinterpret_cast<uint32_t*>(r8 + c) =
+        pack4_e4m3((v.x - hx) * 512.f, (v.y - hy) * 512.f, (v.z - hz) * 512.f, (v.w - hw) * 512.f);
+    *reinterpret_cast<uint32_t*>(r8 + C + c) = pack4_e4m3(hx, hy, hz, hw);
+    return;
+  }
   if (!split) {
     *reinterpret_cast<uint2*>(base + pix * C + c) = pack4h(v.x, v.y, v.z, v.w);
     return;
@@ -217,11 +255,11 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyArgs a) {
     if (a.mode == 0) {
       const float4 x0 = ld4(a.s, in_img + p0, c);
       const float4 x1 = has1 ? ld4(a.s, in_img + p1, c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      store_op4(a.out, out_img + p0, C, c, a.split, act4(x0, sc, sh, a.silu));
-      if (a.out_raw) store_op4(a.out_raw, out_img + p0, C, c, a.split, x0);
+      store_op4(a.out, a.out8, out_img + p0, C, c, a.split, act4(x0, sc, sh, a.silu));
+      if (a.out_raw) store_op4(a.out_raw, a.out_raw8, out_img + p0, C, c, a.split, x0);
       if (has1) {
-        store_op4(a.out, out_img + p1, C, c, a.split, act4(x1, sc, sh, a.silu));
-        if (a.out_raw) store_op4(a.out_raw, out_img + p1, C, c, a.split, x1);
+        store_op4(a.out, a.out8, out_img + p1, C, c, a.split, act4(x1, sc, sh, a.silu));
+        if (a.out_raw) store_op4(a.out_raw, a.out_raw8, out_img + p1, C, c, a.split, x1);
       }
     } else if (a.mode == 1) {
       const float4 x0 = ld4(a.s, in_img + p0, c);
@@ -236,8 +274,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyArgs a) {
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
           const long long po = out_img + static_cast<long long>(2 * h + (d >> 1)) * Wo + (2 * w + (d & 1));
-          store_op4(a.out, po, C, c, a.split, y);
-          if (a.out_raw) store_op4(a.out_raw, po, C, c, a.split, x);
+          store_op4(a.out, a.out8, po, C, c, a.split, y);
+          if (a.out_raw) store_op4(a.out_raw, a.out_raw8, po, C, c, a.split, x);
         }
       }
     } else {
@@ -259,8 +297,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyArgs a) {
         }
         ya = make_float4(ya.x * 0.25f, ya.y * 0.25f, ya.z * 0.25f, ya.w * 0.25f);
         xa = make_float4(xa.x * 0.25f, xa.y * 0.25f, xa.z * 0.25f, xa.w * 0.25f);
-        store_op4(a.out, out_img + p, C, c, a.split, ya);
-        if (a.out_raw) store_op4(a.out_raw, out_img + p, C, c, a.split, xa);
+        store_op4(a.out, a.out8, out_img + p, C, c, a.split, ya);
+        if (a.out_raw) store_op4(a.out_raw, a.out_raw8, out_img + p, C, c, a.split, xa);
       }
     }
   }
@@ -294,6 +332,8 @@ struct GnBwdArgs {
   __half* g16b;
   float g16_scale;
   int split;
+  uint8_t* g8a;
+  uint8_t* g8b;
 };
 
 // gradient w.r.t. the activation output pulled back through the resample, for x-pixel (h,w), channels c..c+4
@@ -354,6 +394,7 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_kernel(const GnBwdArgs a) {
   const float* ex = in_a ? a.extra_a : a.extra_b;
   float* o32 = in_a ? a.dxa : a.dxb;
   __half* o16 = in_a ? a.g16a : a.g16b;
+  uint8_t* o8 = in_a ? a.g8a : a.g8b;
   float p1 = 0.f, p2 = 0.f;
   for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / c4n; p < P;
        p += static_cast<long long>(gridDim.x) * ppb) {
@@ -385,7 +426,7 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_kernel(const GnBwdArgs a) {
     if (kPass2) {
       if (o32) *reinterpret_cast<float4*>(o32 + pix * Cl + cl) = make_float4(dx[0], dx[1], dx[2], dx[3]);
       if (o16)
-        store_op4(o16, pix, Cl, cl, a.split,
+        store_op4(o16, o8, pix, Cl, cl, a.split,
                   make_float4(dx[0] * a.g16_scale, dx[1] * a.g16_scale, dx[2] * a.g16_scale, dx[3] * a.g16_scale));
     }
   }
@@ -404,7 +445,7 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_kernel(const GnBwdArgs a) {
 // 2-channel 3x3 im2col -> fp16 [B][H][W][64] (K index = tap*2 + ci, 18 used, rest zero); and its adjoint
 // ------------------------------------------------------------------------------------------------
 __global__ void im2col_c2_kernel(const float* __restrict__ x, int B, int H, int W, __half* __restrict__ col,
-                                 int split) {
+                                 int split, uint8_t* __restrict__ col8, float in_scale) {
   const long long P = static_cast<long long>(B) * H * W;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < P * 8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -426,10 +467,10 @@ __global__ void im2col_c2_kernel(const float* __restrict__ x, int B, int H, int 
           v1 = q.y;
         }
       }
-      v[2 * j] = v0;
-      v[2 * j + 1] = v1;
+      v[2 * j] = v0 * in_scale;
+      v[2 * j + 1] = v1 * in_scale;
     }
-    store_op8(col, p, 64, chunk * 8, split, v);
+    store_op8(col, p, 64, chunk * 8, split, v, col8);
   }
 }
 
@@ -709,6 +750,12 @@ extern "C" int buddy_gn_apply(const buddy_gn_desc* d, void* stream) {
   a.out = static_cast<__half*>(d->out);
   a.out_raw = static_cast<__half*>(d->out_raw);
   a.split = d->split;
+  a.out8 = static_cast<uint8_t*>(d->out8);
+  a.out_raw8 = static_cast<uint8_t*>(d->out_raw8);
+  if (d->split == 2 && (!d->out8 || (d->out_raw && !d->out_raw8))) {
+    set_last_error("buddy_gn_apply: split 2 needs the fp8 output buffers");
+    return BUDDY_ERR_INVALID;
+  }
   const int c4n = (d->Ca + d->Cb) / 4;
   const int threads = c4n * (256 / c4n > 0 ? 256 / c4n : 1);
   const long long ppb = threads / c4n;
@@ -747,6 +794,12 @@ extern "C" int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, 
   a.g16b = static_cast<__half*>(g->g16b);
   a.g16_scale = g->g16_scale;
   a.split = d->split;
+  a.g8a = static_cast<uint8_t*>(g->g8a);
+  a.g8b = static_cast<uint8_t*>(g->g8b);
+  if (d->split == 2 && ((g->g16a && !g->g8a) || (g->g16b && !g->g8b))) {
+    set_last_error("buddy_gn_bwd: split 2 needs the fp8 output buffers");
+    return BUDDY_ERR_INVALID;
+  }
   const int c4n = C / 4;
   const int threads = c4n * (256 / c4n > 0 ? 256 / c4n : 1);
   const long long ppb = threads / c4n;
@@ -763,9 +816,11 @@ extern "C" int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, 
   LAUNCH_END("gn_bwd_kernel<apply>");
 }
 
-extern "C" int buddy_im2col_c2(const float* x, int B, int H, int W, void* col, int split, void* stream) {
+extern "C" int buddy_im2col_c2(const float* x, int B, int H, int W, void* col, int split, void* col8, float in_scale,
+                               void* stream) {
   const long long items = static_cast<long long>(B) * H * W * 8;
-  im2col_c2_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(x, B, H, W, static_cast<__half*>(col), split);
+  im2col_c2_kernel<<<grid_for(items, 256), 256, 0, STREAM>>>(x, B, H, W, static_cast<__half*>(col), split,
+                                                              static_cast<uint8_t*>(col8), in_scale);
   LAUNCH_END("im2col_c2_kernel");
 }
 extern "C" int buddy_col2im_c2(const float* dcol, int ld, int B, int H, int W, float* dx, int accumulate,

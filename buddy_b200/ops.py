@@ -23,7 +23,8 @@ def _pick_n_tile(n_total):
 
 
 def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=None, bias_b=None, resid=None,
-              scale=1.0, stats=None, b_batched=False, col_off=0, ldc=None, max_ctas=0, passes=1):
+              scale=1.0, stats=None, b_batched=False, col_off=0, ldc=None, max_ctas=0, passes=1, a8=None, w8=None,
+              a8_2=None, w8_2=None):
     """out[b,h,w,n] = scale*(sum_{tap,k} a[b,h+dy,w+dx,k] w[tap,n,k] + sum_k a2[b,h,w,k] w2[n,k] + bias + bias_b + resid).
 
     a, a2 : fp16 [B,H,W,C] (channel stride 1, other strides arbitrary multiples of 8 elements)
@@ -71,6 +72,16 @@ def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=N
     d.scale = float(scale)
     d.stats = ptr(stats)
     d.max_ctas = max_ctas
+    if a8 is not None:
+        assert a8.dtype == torch.uint8 and w8.dtype == torch.uint8 and a8.shape[:3] == a.shape[:3]
+        assert w8.is_contiguous() and w8.shape[:2] == w.shape[:2] and w8.shape[2] == a8.shape[3]
+        d.a8, d.a8_c, d.b8 = ptr(a8), a8.shape[3], ptr(w8)
+        d.a8_stride_w, d.a8_stride_h, d.a8_stride_b = a8.stride(2), a8.stride(1), a8.stride(0)
+        if a2 is not None:
+            assert a8_2.dtype == torch.uint8 and w8_2.dtype == torch.uint8 and w8_2.is_contiguous()
+            assert w8_2.shape == (w2.shape[0], a8_2.shape[3])
+            d.a8_2, d.a8_2_c, d.b8_2 = ptr(a8_2), a8_2.shape[3], ptr(w8_2)
+            d.a8_2_stride_w, d.a8_2_stride_h, d.a8_2_stride_b = a8_2.stride(2), a8_2.stride(1), a8_2.stride(0)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= n_total
     if bias_b is not None:
@@ -113,31 +124,33 @@ def _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps, split=False):
 
 
 def gn_apply(xa, sa, gamma, beta, out, *, xb=None, sb=None, groups=32, silu=True, mode=MODE_NONE, out_raw=None,
-             eps=1e-6, split=False):
+             eps=1e-6, split=False, out8=None, out_raw8=None):
     """out(fp16) = resample(act(GroupNorm([xa|xb]))); out_raw(fp16) = resample([xa|xb])."""
     assert xa.dtype == torch.float32 and xa.is_contiguous() and out.dtype == torch.float16
     d = _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps, split)
     d.out, d.out_raw = ptr(out), ptr(out_raw)
+    d.out8, d.out_raw8 = ptr(out8), ptr(out_raw8)
     check(lib().buddy_gn_apply(ctypes.byref(d), stream_ptr()), "buddy_gn_apply")
     return out
 
 
 def gn_bwd(xa, sa, gamma, beta, da, gsum, *, xb=None, sb=None, groups=32, silu=True, mode=MODE_NONE, dskip=None,
            skip_scale=1.0, extra_a=None, extra_b=None, dxa=None, dxb=None, g16a=None, g16b=None, g16_scale=1.0,
-           eps=1e-6, split=False):
+           eps=1e-6, split=False, g8a=None, g8b=None):
     d = _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps, split)
     g = GnBwdDesc()
     g.da, g.dskip, g.skip_scale = ptr(da), ptr(dskip), skip_scale
     g.extra_a, g.extra_b, g.gsum = ptr(extra_a), ptr(extra_b), ptr(gsum)
     g.dxa, g.dxb, g.g16a, g.g16b, g.g16_scale = ptr(dxa), ptr(dxb), ptr(g16a), ptr(g16b), g16_scale
+    g.g8a, g.g8b = ptr(g8a), ptr(g8b)
     assert da.dtype == torch.float32 and gsum.dtype == torch.float64
     check(lib().buddy_gn_bwd(ctypes.byref(d), ctypes.byref(g), stream_ptr()), "buddy_gn_bwd")
 
 
-def im2col_c2(x, col, split=False):
+def im2col_c2(x, col, split=False, col8=None, in_scale=1.0):
     B, H, W, _ = x.shape
-    check(lib().buddy_im2col_c2(ptr(x), c_int(B), c_int(H), c_int(W), ptr(col), c_int(int(split)), stream_ptr()),
-          "buddy_im2col_c2")
+    check(lib().buddy_im2col_c2(ptr(x), c_int(B), c_int(H), c_int(W), ptr(col), c_int(int(split)), ptr(col8),
+                                c_float(in_scale), stream_ptr()), "buddy_im2col_c2")
     return col
 
 

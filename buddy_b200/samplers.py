@@ -257,10 +257,8 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
             G = torch.empty_like(Yh)
             ops.comp_loss(self._Y_mb, Yh, Yh.shape[2], self._loss_c, self._loss_w, loss, G)
             gd = self._rir.adjoint(self._loss_stft.adjoint(G, n))           # d loss / d x_den
-        rs = ops.row_stats(gd)
-        rms = torch.sqrt(rs[:, 1] / n).float().clamp_min(1e-30)
-        dspec = eng.vjp(ctx, st.inverse_adjoint(gd, scale_b=(1.0 / rms).contiguous()))
-        v = st.forward_adjoint(dspec, n, scale_b=(rms * (cin * cout)).contiguous())
+        dspec = eng.vjp(ctx, st.inverse_adjoint(gd))
+        v = st.forward_adjoint(dspec, n, scale_b=_vec(cin * cout, B, dev))
         g = ops.lincomb3(torch.empty_like(gd), gd, _vec(cskip, B, dev), v, _vec(1.0, B, dev))
         gs = ops.row_stats(g)
         normguide = torch.sqrt(gs[:, 1]).float() / (self.args.exp.audio_len ** 0.5)

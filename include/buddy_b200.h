@@ -89,6 +89,19 @@ typedef struct buddy_gemm_desc {
    * Bw = [w_hi | w_hi | w_lo] one launch accumulates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in fp32 (fp32-class
    * products from fp16 tensor-core operands). */
   int32_t k_total, k2_total;
+  /* Optional fp8 (e4m3) correction operands, accumulated BEFORE the fp16 products and folded with 2^-14
+   * (tcgen05 scale-input-d): a8 = uint8 [batch][H][W][a8_c] = [e4m3(a_lo * 2^9) | e4m3(a_hi)],
+   * b8 = uint8 [taps][b_rows][a8_c] = [e4m3(w_hi * 2^5) | e4m3(w_lo * 2^14)], so that
+   * out = a_hi*w_hi + 2^-14 * (2^14 (a_lo*w_hi + a_hi*w_lo)) at the cost of ONE extra fp16-pass equivalent
+   * (fp8 MMAs consume twice the K per instruction).  a8_2 / b8_2: same for the fused skip conv. */
+  const void* a8;
+  int32_t a8_c;
+  int64_t a8_stride_w, a8_stride_h, a8_stride_b;
+  const void* b8;
+  const void* a8_2;
+  int32_t a8_2_c;
+  int64_t a8_2_stride_w, a8_2_stride_h, a8_2_stride_b;
+  const void* b8_2;
 } buddy_gemm_desc;
 
 int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream);
@@ -120,7 +133,10 @@ typedef struct buddy_gn_desc {
   int32_t mode; /* 0 none, 1 nearest x2 upsample after the activation, 2 2x2 mean after the activation */
   void* out;     /* fp16 [batch][H'][W'][Ca+Cb]   (split: [..][2*(Ca+Cb)] = [hi | lo]) */
   void* out_raw; /* optional fp16 copy of the (resampled) input x, operand of the 1x1 skip conv */
-  int32_t split; /* 1: every fp16 output carries a second half lo = fp16(v - float(hi)) */
+  int32_t split; /* 1: every fp16 output carries a second half lo = fp16(v - float(hi));
+                    2: fp16 hi only + e4m3 pair [e4m3(lo * 2^9) | e4m3(hi)] in out8 / out_raw8 (see buddy_gemm_desc.a8) */
+  void* out8;     /* uint8 [batch][H'][W'][2*(Ca+Cb)] when split == 2 */
+  void* out_raw8;
 } buddy_gn_desc;
 
 typedef struct buddy_gn_bwd_desc {
@@ -135,6 +151,8 @@ typedef struct buddy_gn_bwd_desc {
   void* g16a;           /* optional fp16 out = dxa * g16_scale (dgrad operand of the producer) */
   void* g16b;
   float g16_scale;
+  void* g8a; /* e4m3 pairs of g16a / g16b when the gn desc has split == 2 */
+  void* g8b;
 } buddy_gn_bwd_desc;
 
 int buddy_gn_stats(const float* x, int batch, int64_t pixels, int C, double* stats /* += */, void* stream);
@@ -149,7 +167,8 @@ int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, void* strea
  *            (pyramid_upsample, layerspp.py:117), 2 = adjoint of 0, 3 = adjoint of 1.
  * combine_*: Combine.forward, method 'sum' (layerspp.py:52-59): out = h + Conv1x1(pyr) and d/dpyr.
  * affine_c2: 2x2 affine map per pixel = output_layer (ncsnpp.py:113,445) and its adjoint. */
-int buddy_im2col_c2(const float* x, int B, int H, int W, void* col, int split /* [64 hi | 64 lo] */, void* stream);
+int buddy_im2col_c2(const float* x, int B, int H, int W, void* col, int split /* 1: [64 hi | 64 lo]; 2: + col8 */,
+                    void* col8, float in_scale, void* stream);
 int buddy_col2im_c2(const float* dcol, int ld, int B, int H, int W, float* dx, int accumulate, void* stream);
 int buddy_resample_c2(const float* in, int B, int Hin, int Win, int mode, const float* add, float* out,
                       int accumulate, void* stream);

@@ -129,3 +129,28 @@ def test_big_conv_speed():
     ref = ref_conv(a[:1, :64], w, 9)
     # interior rows only (the reference slab was cut at row 64, so its last row sees a different halo)
     assert rel(out[:1, :63], ref[:, :63]) < 1e-5
+
+
+def test_fp8_corrected_products():
+    """fp16 main pass + e4m3 correction passes (scale-input-d fold) reproduce fp32 products to ~1e-5."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    B, H, W, C, N = 2, 16, 24, 128, 256
+    a = torch.randn(B, H, W, C, device="cuda", generator=g) * 1.3
+    w = torch.randn(9, N, C, device="cuda", generator=g) * 0.04
+    a_hi = a.half()
+    a_lo = a - a_hi.float()
+    w_hi = w.half()
+    w_lo = w - w_hi.float()
+    e4 = lambda t: t.clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)
+    a8 = torch.cat([e4(a_lo * 512.0), e4(a_hi.float())], dim=-1).contiguous()
+    w8 = torch.cat([e4(w_hi.float() * 32.0), e4(w_lo * 16384.0)], dim=-1).contiguous()
+    out = torch.empty(B, H, W, N, device="cuda")
+    ops.conv_gemm(a_hi, w_hi, out, taps=9, n_total=N, a8=a8, w8=w8)
+    x = a.permute(0, 3, 1, 2).double()
+    ref = F.conv2d(x, w.double().view(3, 3, N, C).permute(2, 3, 0, 1), padding=1).permute(0, 2, 3, 1).float()
+    single = torch.empty_like(out)
+    ops.conv_gemm(a_hi, w_hi, single, taps=9, n_total=N)
+    e_c8, e_1 = rel(out, ref), rel(single, ref)
+    print(f"\n[conv precision] fp16 single pass {e_1:.2e}   fp16 + e4m3 corrections {e_c8:.2e}")
+    assert e_1 > 1e-4 and e_c8 < 3e-5
