@@ -345,9 +345,18 @@ class KernelTimer:
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1, work in self.records:
+        for name, e0, e1, work, _ in self.records:
             c, ms, w = out.get(name, (0, 0.0, 0.0))
             out[name] = (c + 1, ms + e0.elapsed_time(e1), w + work)
+        return out
+
+    def by_tag(self):
+        """{(op, tag): (calls, total_ms, work)} — tag = shape key of the launch (conv: B,H,W,K,N,taps,skipK)."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, work, tag in self.records:
+            c, ms, w = out.get((name, tag), (0, 0.0, 0.0))
+            out[(name, tag)] = (c + 1, ms + e0.elapsed_time(e1), w + work)
         return out
 
 
@@ -365,7 +374,22 @@ def _conv_flops(args, kwargs):
     return flops / kwargs.get("passes", 1)   # algorithmic FLOPs: split-precision passes are not useful work
 
 
-def _timed(fn, work_fn=None):
+def _conv_tag(args, kwargs):
+    a, w = args[0], args[1]
+    B, H, W, C = a.shape
+    w2 = kwargs.get("w2")
+    return (B, H, W, C, kwargs["n_total"], kwargs["taps"], w2.shape[1] if w2 is not None else 0,
+            "c8" if kwargs.get("a8") is not None else f"x{kwargs.get('passes', 1)}", str(args[2].dtype)[6:])
+
+
+def _shape_tag(args, kwargs):
+    for t in args:
+        if isinstance(t, torch.Tensor):
+            return tuple(t.shape)
+    return ()
+
+
+def _timed(fn, work_fn=None, tag_fn=_shape_tag):
     def wrapper(*args, **kwargs):
         if _timer is None:
             return fn(*args, **kwargs)
@@ -373,14 +397,14 @@ def _timed(fn, work_fn=None):
         e0.record()
         r = fn(*args, **kwargs)
         e1.record()
-        _timer.records.append((fn.__name__, e0, e1, work_fn(args, kwargs) if work_fn else 0.0))
+        _timer.records.append((fn.__name__, e0, e1, work_fn(args, kwargs) if work_fn else 0.0, tag_fn(args, kwargs)))
         return r
     wrapper.__name__ = fn.__name__
     wrapper.__doc__ = fn.__doc__
     return wrapper
 
 
-conv_gemm = _timed(conv_gemm, _conv_flops)
+conv_gemm = _timed(conv_gemm, _conv_flops, _conv_tag)
 for _n in ("gn_stats", "gn_apply", "gn_bwd", "im2col_c2", "col2im_c2", "resample_c2", "combine_fwd", "combine_bwd",
            "affine_c2", "softmax_fwd", "softmax_bwd", "transpose_h", "cast_scale_h", "dft_analysis", "dft_synthesis",
            "ola_gather", "pad_signal", "reflect_fold", "comp_loss", "row_stats", "fftconv", "fourier_features",
