@@ -49,24 +49,34 @@ struct GemmParams {
   long long ld_res;
   float scale;
   double* stats;
+  int staged;      // 1: epilogue stages 128x32 fp32 chunks in shared memory and writes them with TMA stores
+  int res_staged;  // 1: the residual is TMA-loaded into the staging buffer (needs staged)
 };
+
+constexpr int kChunkBytes = kTileM * 128;   // one staged epilogue chunk: 128 rows x 32 fp32
+constexpr int kEpiThreads = 128;
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8,
                  const __grid_constant__ CUtensorMap tmA82, const __grid_constant__ CUtensorMap tmB82,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16B aligned by the runtime: round up to 1024 (swizzle-128B atoms)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = kStageA + p.n_tile * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  // [pipeline stages][2 staged epilogue chunks (if staged)][bias row 1 KB (if staged)][barriers]
+  uint8_t* stage_out = smem + p.stages * stage_bytes;
+  float* bias_s = reinterpret_cast<float*>(stage_out + 2 * kChunkBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + (p.staged ? 2 * kChunkBytes + 1024 : 0));
   uint64_t* full_bar = bars;                     // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
   uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,6 +95,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+      mbar_init(&res_bar[s], 1);
+    }
+    if (p.staged) {
+      tma_prefetch_desc(&tmOut);
+      if (p.res_staged) tma_prefetch_desc(&tmRes);
     }
     fence_barrier_init();
   }
@@ -206,8 +221,137 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
+  } else if (p.staged) {
+    // ================================================================ epilogue, staged (4 warps, 128 threads)
+    // Per 32-column chunk: TMEM -> registers -> (+bias row, +residual, *scale) -> swizzled smem chunk
+    // [128 rows][128 B] -> one TMA store (hardware clips the image border); GroupNorm bundle statistics are taken
+    // column-wise from the staged chunk (no warp shuffles over rows).  Two chunk buffers: the store of chunk i and
+    // the residual load of chunk i+1 overlap the arithmetic.
+    const int wq = warp & 3;
+    const int et = wq * 32 + lane;  // 0..127 = accumulator row handled by this thread
+    const int m = et;
+    const int hl = m / p.bw;
+    const int wl = m - hl * p.bw;
+    const bool elected = (et == 0);
+    const int nchunks = p.n_tile >> 5;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t cc = 0;                 // running chunk counter -> staging buffer parity
+    uint32_t res_phase = 0;          // bit s = parity to wait for on res_bar[s]
+    const int sw = (m & 7);          // swizzle phase of this thread's staging row
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % p.n_tiles;
+      const int pt = t / p.n_tiles;
+      const int b = pt / tiles_per_img;
+      const int r = pt - b * tiles_per_img;
+      const int h0 = (r / p.tiles_w) * p.bh;
+      const int w0 = (r % p.tiles_w) * p.bw;
+      const bool valid = (h0 + hl < p.H) && (w0 + wl < p.W);
+      const int ncol_base = nt * p.n_tile;
+      // bias row of this tile (bias + per-image bias): every reader of the previous tile's row is past its last
+      // chunk barrier, so it can be overwritten; the chunk-0 barrier below publishes it
+      for (int i = et; i < p.n_tile; i += kEpiThreads) {
+        float bv = 0.f;
+        if (p.bias) bv += __ldg(p.bias + ncol_base + i);
+        if (p.bias_b) bv += __ldg(p.bias_b + static_cast<long long>(b) * p.n_total + ncol_base + i);
+        bias_s[i] = bv;
+      }
+      if (p.res_staged && elected) {
+        // staging buffer cc&1 is free: the store that last read it was waited for before the previous chunk barrier
+        mbar_expect_tx(&res_bar[cc & 1], kChunkBytes);
+        tma_load_4d(&tmRes, stage_out + (cc & 1) * kChunkBytes, &res_bar[cc & 1], ncol_base, w0, h0, b);
+      }
+      named_bar_sync(1, kEpiThreads);
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * kAccStride;
+      uint32_t rr[32];
+      tmem_ld_32x32(taddr, rr);
+      tmem_ld_wait_dep(rr);
+      for (int c = 0; c < nchunks; ++c, ++cc) {
+        const int sbuf = cc & 1;
+        uint8_t* srow = stage_out + sbuf * kChunkBytes + m * 128;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+        if (c + 1 < nchunks) {
+          tmem_ld_32x32(taddr + (c + 1) * 32, rr);   // in flight while this chunk is finished
+        } else {
+          // every TMEM read of this accumulator has landed in registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        const float4* bp = reinterpret_cast<const float4*>(bias_s + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 q = bp[j];
+          v[4 * j] += q.x;
+          v[4 * j + 1] += q.y;
+          v[4 * j + 2] += q.z;
+          v[4 * j + 3] += q.w;
+        }
+        if (p.res_staged) {
+          mbar_wait(&res_bar[sbuf], (res_phase >> sbuf) & 1u);
+          res_phase ^= 1u << sbuf;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 q = *reinterpret_cast<const float4*>(srow + ((j ^ sw) << 4));
+            v[4 * j] += q.x;
+            v[4 * j + 1] += q.y;
+            v[4 * j + 2] += q.z;
+            v[4 * j + 3] += q.w;
+          }
+        }
+        const float sc = valid ? p.scale : 0.f;   // rows outside the image: zero (clipped by the store, inert in the statistics)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(srow + ((j ^ sw) << 4)) =
+              make_float4(v[4 * j] * sc, v[4 * j + 1] * sc, v[4 * j + 2] * sc, v[4 * j + 3] * sc);
+        fence_proxy_async();
+        if (elected) tma_store_wait_read0();   // the previous chunk's store no longer reads the other buffer
+        named_bar_sync(1, kEpiThreads);
+        if (elected) {
+          tma_store_4d(&tmOut, stage_out + sbuf * kChunkBytes, ncol_base + c * 32, w0, h0, b);
+          tma_store_commit();
+          if (p.res_staged && c + 1 < nchunks) {
+            mbar_expect_tx(&res_bar[sbuf ^ 1], kChunkBytes);
+            tma_load_4d(&tmRes, stage_out + (sbuf ^ 1) * kChunkBytes, &res_bar[sbuf ^ 1], ncol_base + (c + 1) * 32, w0,
+                        h0, b);
+          }
+        }
+        if (p.stats) {
+          // thread -> (bundle = et & 7, rows 8*(et>>3) .. +8): column sums of the staged chunk
+          const int bun = et & 7;
+          const uint8_t* sbase = stage_out + sbuf * kChunkBytes + (et >> 3) * 1024;
+          float s = 0.f, q = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 x = *reinterpret_cast<const float4*>(sbase + i * 128 + ((bun ^ i) << 4));
+            s += (x.x + x.y) + (x.z + x.w);
+            q = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, q))));
+          }
+          s += __shfl_xor_sync(0xffffffffu, s, 8);
+          q += __shfl_xor_sync(0xffffffffu, q, 8);
+          s += __shfl_xor_sync(0xffffffffu, s, 16);
+          q += __shfl_xor_sync(0xffffffffu, q, 16);
+          if (lane < 8) {
+            double* sp = p.stats + (static_cast<long long>(b) * (p.n_total >> 2) + ((ncol_base + c * 32) >> 2) + bun) * 2;
+            atomicAdd(sp, static_cast<double>(s));
+            atomicAdd(sp + 1, static_cast<double>(q));
+          }
+        }
+        if (c + 1 < nchunks) tmem_ld_wait_dep(rr);
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (elected) tma_store_wait_all();
   } else {
-    // ================================================================ epilogue (4 warps, 128 threads)
+    // ================================================================ epilogue, direct (4 warps, 128 threads)
     const int wq = warp & 3;  // TMEM lane quarter this warp may access
     const int m = wq * 32 + lane;
     const int hl = m / p.bw;
@@ -364,7 +508,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// fp16 (esize 2) or byte (esize 1) tensor map with `rank` dims (dim 0 contiguous), 128B swizzle, zero OOB fill.
+// fp16 (esize 2), fp32 (esize 4) or byte (esize 1) tensor map with `rank` dims (dim 0 contiguous), 128B swizzle, zero OOB fill.
 static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_el,
                       const uint32_t* box, int esize = 2) {
   EncodeTiledFn fn = get_encode_fn();
@@ -391,7 +535,9 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
       set_last_error("tensor map stride %d (%llu bytes) not a multiple of 16", i + 1, (unsigned long long)gstr[i]);
       return BUDDY_ERR_INVALID;
     }
-  CUresult r = fn(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  const CUtensorMapDataType dt = esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                 : (esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+  CUresult r = fn(m, dt, rank, const_cast<void*>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -487,7 +633,14 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   p.a_wrap2 = d->a2 ? d->a2_c / kBlockK : 1;
   p.b_batched = d->b_batched;
   const int stage_bytes = kStageA + d->n_tile * 128;
-  int stages = (227 * 1024 - 2048) / stage_bytes;
+  // staged epilogue (TMA stores of 128x32 fp32 chunks): dense fp32 output whose tile columns are whole chunks
+  p.staged = (!d->out_fp16 && d->ldc == d->n_total && d->col_off == 0 && d->n_tile % 32 == 0 &&
+              d->n_total % d->n_tile == 0 && (!d->resid || d->ld_res == d->n_total) && !d->no_staged_epilogue)
+                 ? 1
+                 : 0;
+  p.res_staged = (p.staged && d->resid) ? 1 : 0;
+  const int epi_bytes = p.staged ? 2 * kChunkBytes + 1024 : 0;
+  int stages = (227 * 1024 - 2048 - epi_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
     set_last_error("buddy_conv_gemm: not enough shared memory for 2 stages");
@@ -505,7 +658,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   p.scale = d->scale;
   p.stats = d->stats;
 
-  CUtensorMap tmA, tmB, tmA2, tmB2, tmA8, tmB8, tmA82, tmB82;
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmA8, tmB8, tmA82, tmB82, tmOut, tmRes;
   p.kchunks8_1 = 0;
   p.kchunks8_2 = 0;
   if (d->a8) {
@@ -577,8 +730,24 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     tmA82 = tmA;
     tmB82 = tmB;
   }
+  if (p.staged) {
+    uint64_t dims[4] = {(uint64_t)d->n_total, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
+    uint64_t str[4] = {1, (uint64_t)d->n_total, (uint64_t)d->n_total * d->W, (uint64_t)d->n_total * d->W * d->H};
+    uint32_t box[4] = {32, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    int e = encode_map(&tmOut, d->out, 4, dims, str, box, 4);
+    if (e) return e;
+    if (p.res_staged) {
+      e = encode_map(&tmRes, d->resid, 4, dims, str, box, 4);
+      if (e) return e;
+    } else {
+      tmRes = tmOut;
+    }
+  } else {
+    tmOut = tmA;
+    tmRes = tmA;
+  }
 
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + epi_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
     int e = check_cuda(
@@ -591,7 +760,8 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   int grid = num_sms();
   if (d->max_ctas > 0 && d->max_ctas < grid) grid = d->max_ctas;
   if (total_tiles < grid) grid = (int)total_tiles;
-  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmA2, tmB2, tmA8, tmB8, tmA82, tmB82, p);
+  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmA2, tmB2, tmA8, tmB8, tmA82, tmB82, tmOut,
+                                                           tmRes, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   BUDDY_CHECK_LAUNCH("conv_gemm_kernel");
   return 0;

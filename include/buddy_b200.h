@@ -102,6 +102,9 @@ typedef struct buddy_gemm_desc {
   int32_t a8_2_c;
   int64_t a8_2_stride_w, a8_2_stride_h, a8_2_stride_b;
   const void* b8_2;
+  /* 1 = force the direct (register -> global) epilogue even where the staged TMA-store epilogue applies
+   * (dense fp32 output, n_tile %% 32 == 0); testing / A-B timing only. */
+  int32_t no_staged_epilogue;
 } buddy_gemm_desc;
 
 int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream);
