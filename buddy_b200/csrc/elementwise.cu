@@ -21,11 +21,14 @@ extern std::atomic<long long> g_launches;
   BUDDY_CHECK_LAUNCH(name);                               \
   return 0;
 
-__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+// SiLU and its derivative with MUFU.EX2 + MUFU.RCP (no IEEE-division slow path): <= 2 ulp, far inside the fp32 budget
+__device__ __forceinline__ float silu_f(float z) { return __fdividef(z, 1.f + __expf(-z)); }
 __device__ __forceinline__ float dsilu_f(float z) {
-  const float s = 1.f / (1.f + __expf(-z));
-  return s * (1.f + z * (1.f - s));
+  const float s = __fdividef(1.f, 1.f + __expf(-z));
+  return s * fmaf(z, 1.f - s, 1.f);
 }
+// p / d for p * d < 2^32 with magic = ceil(2^32 / d) (d >= 2; magic 0 encodes d == 1)
+__device__ __forceinline__ uint32_t fast_div(uint32_t p, uint32_t magic) { return magic ? __umulhi(p, magic) : p; }
 
 struct GnSrc {
   const float* xa;
@@ -168,6 +171,7 @@ struct GnApplyArgs {
   int split;
   uint8_t* out8;
   uint8_t* out_raw8;
+  uint32_t magic;  // fast_div constant for the row length the pixel index is split by (modes 1, 2)
 };
 
 __device__ __forceinline__ float4 ld4(const GnSrc& s, long long pix, int c) {
@@ -188,7 +192,7 @@ __device__ __forceinline__ uint32_t pack4_e4m3(float a, float b, float c, float 
 }
 // fp16 operand store of 4 channels.  split 1: row = [hi (C) | lo (C)] fp16.
 // split 2: fp16 hi in `base` (row C) + e4m3 pair in `base8` (row 2C bytes) = [e4m3(lo * 2^9) | e4m3(hi)].
-__device__ __forceinline__ void store_op4(__half* base, uint8_t* base8, long long pix, int C, int c, int split,
+__device__ __forceinline__ void store_op4(__half* base, uint8_t* base8, size_t pix, int C, int c, int split,
                                           float4 v) {
   if (split == 2) {
     const float hx = __half2float(__float2half_rn(v.x)), hy = __half2float(__float2half_rn(v.y));
@@ -221,7 +225,7 @@ __device__ __forceinline__ float4 act4(float4 x, const float (&sc)[4], const flo
   return y;
 }
 
-__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyArgs a) {
+__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyArgs a) {
   __shared__ float s_mean[64], s_rstd[64];
   const int b = blockIdx.y;
   const int C = a.s.Ca + a.s.Cb;
@@ -229,8 +233,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyArgs a) {
   __syncthreads();
   const int c4n = C >> 2;  // blockDim.x is a multiple of c4n
   const int c = (threadIdx.x % c4n) * 4;
-  const int lane_p = threadIdx.x / c4n;
-  const int ppb = blockDim.x / c4n;
+  const uint32_t lane_p = threadIdx.x / c4n;
+  const uint32_t ppb = blockDim.x / c4n;
   float sc[4], sh[4];
   {
     const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
@@ -243,51 +247,71 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyArgs a) {
       sh[j] = bv[j] - s_mean[grp] * sc[j];
     }
   }
-  const int Ho = (a.mode == 1) ? a.H * 2 : (a.mode == 2 ? a.H / 2 : a.H);
-  const int Wo = (a.mode == 1) ? a.W * 2 : (a.mode == 2 ? a.W / 2 : a.W);
-  const long long Pwork = (a.mode == 2) ? static_cast<long long>(Ho) * Wo : static_cast<long long>(a.H) * a.W;
-  const long long in_img = static_cast<long long>(b) * a.H * a.W;
-  const long long out_img = static_cast<long long>(b) * Ho * Wo;
-  const long long stride = static_cast<long long>(gridDim.x) * ppb;
-  for (long long p0 = static_cast<long long>(blockIdx.x) * ppb + lane_p; p0 < Pwork; p0 += 2 * stride) {
-    const long long p1 = p0 + stride;
-    const bool has1 = p1 < Pwork;
-    if (a.mode == 0) {
-      const float4 x0 = ld4(a.s, in_img + p0, c);
-      const float4 x1 = has1 ? ld4(a.s, in_img + p1, c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      store_op4(a.out, a.out8, out_img + p0, C, c, a.split, act4(x0, sc, sh, a.silu));
-      if (a.out_raw) store_op4(a.out_raw, a.out_raw8, out_img + p0, C, c, a.split, x0);
-      if (has1) {
-        store_op4(a.out, a.out8, out_img + p1, C, c, a.split, act4(x1, sc, sh, a.silu));
-        if (a.out_raw) store_op4(a.out_raw, a.out_raw8, out_img + p1, C, c, a.split, x1);
+  const uint32_t Ho = (a.mode == 1) ? a.H * 2 : (a.mode == 2 ? a.H / 2 : a.H);
+  const uint32_t Wo = (a.mode == 1) ? a.W * 2 : (a.mode == 2 ? a.W / 2 : a.W);
+  const uint32_t Pin = static_cast<uint32_t>(a.H) * a.W, Pout = Ho * Wo;
+  const uint32_t Pwork = (a.mode == 2) ? Pout : Pin;
+  // per-thread image bases (all further indexing is 32-bit pixel index * row length)
+  const bool in_a = c < a.s.Ca;
+  const int Cl = in_a ? a.s.Ca : a.s.Cb;
+  const float* xin = (in_a ? a.s.xa + static_cast<size_t>(b) * Pin * Cl + c
+                           : a.s.xb + static_cast<size_t>(b) * Pin * Cl + (c - a.s.Ca));
+  const int row16 = (a.split == 1) ? 2 * C : C;
+  __half* o16 = a.out + static_cast<size_t>(b) * Pout * row16;
+  __half* r16 = a.out_raw ? a.out_raw + static_cast<size_t>(b) * Pout * row16 : nullptr;
+  uint8_t* o8 = a.out8 ? a.out8 + static_cast<size_t>(b) * Pout * (2 * C) : nullptr;
+  uint8_t* r8 = a.out_raw8 ? a.out_raw8 + static_cast<size_t>(b) * Pout * (2 * C) : nullptr;
+  const uint32_t stride = gridDim.x * ppb;
+  const uint32_t pstart = blockIdx.x * ppb + lane_p;
+#define LDX(p) __ldg(reinterpret_cast<const float4*>(xin + static_cast<size_t>(p) * Cl))
+  if (a.mode == 0) {
+    for (uint32_t p0 = pstart; p0 < Pwork; p0 += 4 * stride) {
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t p = p0 + u * stride;
+        x[u] = (p < Pwork) ? LDX(p) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    } else if (a.mode == 1) {
-      const float4 x0 = ld4(a.s, in_img + p0, c);
-      const float4 x1 = has1 ? ld4(a.s, in_img + p1, c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (u == 1 && !has1) break;
-        const long long p = u ? p1 : p0;
-        const float4 x = u ? x1 : x0;
-        const float4 y = act4(x, sc, sh, a.silu);
-        const int h = static_cast<int>(p / a.W), w = static_cast<int>(p - static_cast<long long>(h) * a.W);
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          const long long po = out_img + static_cast<long long>(2 * h + (d >> 1)) * Wo + (2 * w + (d & 1));
-          store_op4(a.out, a.out8, po, C, c, a.split, y);
-          if (a.out_raw) store_op4(a.out_raw, a.out_raw8, po, C, c, a.split, x);
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t p = p0 + u * stride;
+        if (p < Pwork) {
+          store_op4(o16, o8, p, C, c, a.split, act4(x[u], sc, sh, a.silu));
+          if (r16) store_op4(r16, r8, p, C, c, a.split, x[u]);
         }
       }
-    } else {
+    }
+  } else if (a.mode == 1) {
+    for (uint32_t p0 = pstart; p0 < Pwork; p0 += 2 * stride) {
+      const uint32_t p1 = p0 + stride;
+      const bool has1 = p1 < Pwork;
+      const float4 x0 = LDX(p0);
+      const float4 x1 = has1 ? LDX(p1) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         if (u == 1 && !has1) break;
-        const long long p = u ? p1 : p0;
-        const int ho = static_cast<int>(p / Wo), wo = static_cast<int>(p - static_cast<long long>(ho) * Wo);
+        const uint32_t p = u ? p1 : p0;
+        const float4 x = u ? x1 : x0;
+        const float4 y = act4(x, sc, sh, a.silu);
+        const uint32_t h = fast_div(p, a.magic), w = p - h * a.W;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const uint32_t po = (2 * h + (d >> 1)) * Wo + (2 * w + (d & 1));
+          store_op4(o16, o8, po, C, c, a.split, y);
+          if (r16) store_op4(r16, r8, po, C, c, a.split, x);
+        }
+      }
+    }
+  } else {
+    for (uint32_t p0 = pstart; p0 < Pwork; p0 += 2 * stride) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t p = p0 + u * stride;
+        if (p >= Pwork) break;
+        const uint32_t ho = fast_div(p, a.magic), wo = p - ho * Wo;
         float4 xs[4];
 #pragma unroll
-        for (int d = 0; d < 4; ++d)
-          xs[d] = ld4(a.s, in_img + static_cast<long long>(2 * ho + (d >> 1)) * a.W + (2 * wo + (d & 1)), c);
+        for (int d = 0; d < 4; ++d) xs[d] = LDX((2 * ho + (d >> 1)) * a.W + (2 * wo + (d & 1)));
         float4 ya = make_float4(0.f, 0.f, 0.f, 0.f), xa = ya;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
@@ -297,11 +321,12 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyArgs a) {
         }
         ya = make_float4(ya.x * 0.25f, ya.y * 0.25f, ya.z * 0.25f, ya.w * 0.25f);
         xa = make_float4(xa.x * 0.25f, xa.y * 0.25f, xa.z * 0.25f, xa.w * 0.25f);
-        store_op4(a.out, a.out8, out_img + p, C, c, a.split, ya);
-        if (a.out_raw) store_op4(a.out_raw, a.out_raw8, out_img + p, C, c, a.split, xa);
+        store_op4(o16, o8, p, C, c, a.split, ya);
+        if (r16) store_op4(r16, r8, p, C, c, a.split, xa);
       }
     }
   }
+#undef LDX
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -334,33 +359,34 @@ struct GnBwdArgs {
   int split;
   uint8_t* g8a;
   uint8_t* g8b;
+  uint32_t magic;  // fast_div constant for W (modes 1, 2)
 };
 
-// gradient w.r.t. the activation output pulled back through the resample, for x-pixel (h,w), channels c..c+4
-__device__ __forceinline__ float4 pull_back4(const float* __restrict__ t, int mode, int b, int h, int w, int H, int W,
-                                             int C, int c) {
+// gradient w.r.t. the activation output pulled back through the resample, for x-pixel p = h*W + w of one image
+// (t points at the image's first pixel of the conv-resolution tensor, already offset to channel c; row length C)
+__device__ __forceinline__ float4 pull_back4(const float* __restrict__ t, int mode, uint32_t p, uint32_t h, uint32_t w,
+                                             uint32_t W, int C) {
   if (mode == 0) {
-    return __ldg(reinterpret_cast<const float4*>(t + ((static_cast<long long>(b) * H + h) * W + w) * C + c));
+    return __ldg(reinterpret_cast<const float4*>(t + static_cast<size_t>(p) * C));
   } else if (mode == 1) {  // forward was nearest x2: sum the 4 children
-    const int Wc = 2 * W;
+    const uint32_t Wc = 2 * W;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(
-          t + ((static_cast<long long>(b) * 2 * H + 2 * h + (d >> 1)) * Wc + 2 * w + (d & 1)) * C + c));
+          t + static_cast<size_t>((2 * h + (d >> 1)) * Wc + 2 * w + (d & 1)) * C));
       g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
     }
     return g;
   } else {  // forward was 2x2 mean: a quarter of the parent
-    const int Hc = H / 2, Wc = W / 2;
-    const float4 v =
-        __ldg(reinterpret_cast<const float4*>(t + ((static_cast<long long>(b) * Hc + (h >> 1)) * Wc + (w >> 1)) * C + c));
+    const uint32_t Wc = W / 2;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(t + static_cast<size_t>((h >> 1) * Wc + (w >> 1)) * C));
     return make_float4(v.x * 0.25f, v.y * 0.25f, v.z * 0.25f, v.w * 0.25f);
   }
 }
 
 template <bool kPass2>
-__global__ void __launch_bounds__(256, 4) gn_bwd_kernel(const GnBwdArgs a) {
+__global__ void __launch_bounds__(256, kPass2 ? 3 : 4) gn_bwd_kernel(const GnBwdArgs a) {
   __shared__ float s_mean[64], s_rstd[64];
   __shared__ float s_acc[64][2];
   const int b = blockIdx.y;
@@ -373,8 +399,8 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_kernel(const GnBwdArgs a) {
   const int c4n = C >> 2;  // blockDim.x is a multiple of c4n -> each thread keeps one channel bundle
   const int c = (threadIdx.x % c4n) * 4;
   const int grp = c / a.cpg;
-  const long long P = static_cast<long long>(a.H) * a.W;
-  const int ppb = blockDim.x / c4n;
+  const uint32_t P = static_cast<uint32_t>(a.H) * a.W;
+  const uint32_t ppb = blockDim.x / c4n;
   const float rstd = s_rstd[grp], nmr = -s_mean[grp] * rstd;  // xh = x*rstd + nmr
   float gam[4], bet[4];
   {
@@ -391,43 +417,71 @@ __global__ void __launch_bounds__(256, 4) gn_bwd_kernel(const GnBwdArgs a) {
   const bool in_a = c < a.s.Ca;
   const int cl = in_a ? c : c - a.s.Ca;
   const int Cl = in_a ? a.s.Ca : a.s.Cb;
+  // per-thread image bases, pre-offset to this thread's channel bundle
+  const size_t img_l = static_cast<size_t>(b) * P * Cl;
+  const float* xin = (in_a ? a.s.xa : a.s.xb) + img_l + cl;
+  const uint32_t Pc = (a.mode == 1) ? 4 * P : (a.mode == 2 ? P / 4 : P);  // pixels of the conv-resolution tensors
+  const float* da = a.da + static_cast<size_t>(b) * Pc * C + c;
+  const float* dsk = (kPass2 && a.dskip) ? a.dskip + static_cast<size_t>(b) * Pc * C + c : nullptr;
   const float* ex = in_a ? a.extra_a : a.extra_b;
+  if (ex) ex += img_l + cl;
   float* o32 = in_a ? a.dxa : a.dxb;
+  if (o32) o32 += img_l + cl;
   __half* o16 = in_a ? a.g16a : a.g16b;
   uint8_t* o8 = in_a ? a.g8a : a.g8b;
+  if (o16) o16 += static_cast<size_t>(b) * P * (a.split == 1 ? 2 * Cl : Cl);
+  if (o8) o8 += static_cast<size_t>(b) * P * (2 * Cl);
+  const uint32_t stride = gridDim.x * ppb;
   float p1 = 0.f, p2 = 0.f;
-  for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / c4n; p < P;
-       p += static_cast<long long>(gridDim.x) * ppb) {
-    const int h = static_cast<int>(p / a.W), w = static_cast<int>(p - static_cast<long long>(h) * a.W);
-    const long long pix = static_cast<long long>(b) * P + p;
-    const float4 x4 = ld4(a.s, pix, c);
-    const float4 g4 = pull_back4(a.da, a.mode, b, h, w, a.H, a.W, C, c);
-    float4 sk4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = sk4;
-    if (kPass2) {
-      if (a.dskip) sk4 = pull_back4(a.dskip, a.mode, b, h, w, a.H, a.W, C, c);
-      if (ex) e4 = __ldg(reinterpret_cast<const float4*>(ex + pix * Cl + cl));
-    }
-    const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
-    const float sv[4] = {sk4.x, sk4.y, sk4.z, sk4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
-    float dx[4];
+  constexpr int U = 2;
+  for (uint32_t p0 = blockIdx.x * ppb + threadIdx.x / c4n; p0 < P; p0 += U * stride) {
+    float4 x4[U], g4[U], sk4[U], e4[U];
+    bool ok[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float xh = fmaf(xv[j], rstd, nmr);
-      float dz = gv[j];
-      if (a.silu) dz *= dsilu_f(fmaf(xh, gam[j], bet[j]));
-      const float dxh = dz * gam[j];
-      if (!kPass2) {
-        p1 += dxh;
-        p2 = fmaf(dxh, xh, p2);
-      } else {
-        dx[j] = rstd * (dxh - m1 - xh * m2) + sv[j] * a.skip_scale + ev[j];
+    for (int u = 0; u < U; ++u) {
+      const uint32_t p = p0 + u * stride;
+      ok[u] = p < P;
+      x4[u] = g4[u] = sk4[u] = e4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok[u]) {
+        uint32_t h = 0, w = 0;
+        if (a.mode != 0) {
+          h = fast_div(p, a.magic);
+          w = p - h * a.W;
+        }
+        x4[u] = __ldg(reinterpret_cast<const float4*>(xin + static_cast<size_t>(p) * Cl));
+        g4[u] = pull_back4(da, a.mode, p, h, w, a.W, C);
+        if (kPass2) {
+          if (dsk) sk4[u] = pull_back4(dsk, a.mode, p, h, w, a.W, C);
+          if (ex) e4[u] = __ldg(reinterpret_cast<const float4*>(ex + static_cast<size_t>(p) * Cl));
+        }
       }
     }
-    if (kPass2) {
-      if (o32) *reinterpret_cast<float4*>(o32 + pix * Cl + cl) = make_float4(dx[0], dx[1], dx[2], dx[3]);
-      if (o16)
-        store_op4(o16, o8, pix, Cl, cl, a.split,
-                  make_float4(dx[0] * a.g16_scale, dx[1] * a.g16_scale, dx[2] * a.g16_scale, dx[3] * a.g16_scale));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      const uint32_t p = p0 + u * stride;
+      const float xv[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w}, gv[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+      const float sv[4] = {sk4[u].x, sk4[u].y, sk4[u].z, sk4[u].w}, ev[4] = {e4[u].x, e4[u].y, e4[u].z, e4[u].w};
+      float dx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = fmaf(xv[j], rstd, nmr);
+        float dz = gv[j];
+        if (a.silu) dz *= dsilu_f(fmaf(xh, gam[j], bet[j]));
+        const float dxh = dz * gam[j];
+        if (!kPass2) {
+          p1 += dxh;
+          p2 = fmaf(dxh, xh, p2);
+        } else {
+          dx[j] = fmaf(rstd, dxh - m1 - xh * m2, fmaf(sv[j], a.skip_scale, ev[j]));
+        }
+      }
+      if (kPass2) {
+        if (o32) *reinterpret_cast<float4*>(o32 + static_cast<size_t>(p) * Cl) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+        if (o16)
+          store_op4(o16, o8, p, Cl, cl, a.split,
+                    make_float4(dx[0] * a.g16_scale, dx[1] * a.g16_scale, dx[2] * a.g16_scale, dx[3] * a.g16_scale));
+      }
     }
   }
   if (!kPass2) {
@@ -756,11 +810,20 @@ extern "C" int buddy_gn_apply(const buddy_gn_desc* d, void* stream) {
     set_last_error("buddy_gn_apply: split 2 needs the fp8 output buffers");
     return BUDDY_ERR_INVALID;
   }
+  {
+    const long long rowlen = d->mode == 2 ? d->W / 2 : d->W;
+    if (static_cast<long long>(d->H) * d->W * (d->mode == 1 ? 4 : 1) >= (1LL << 31) ||
+        static_cast<long long>(d->H) * d->W * rowlen >= (1LL << 32)) {
+      set_last_error("buddy_gn_apply: image too large for 32-bit pixel indexing (H %d W %d)", d->H, d->W);
+      return BUDDY_ERR_UNSUPPORTED;
+    }
+    a.magic = rowlen >= 2 ? static_cast<uint32_t>(((1ULL << 32) + rowlen - 1) / rowlen) : 0u;
+  }
   const int c4n = (d->Ca + d->Cb) / 4;
   const int threads = c4n * (256 / c4n > 0 ? 256 / c4n : 1);
   const long long ppb = threads / c4n;
   const long long Pw = static_cast<long long>(d->mode == 2 ? (d->H / 2) * (d->W / 2) : d->H * d->W);
-  long long gx = (Pw + ppb * 8 - 1) / (ppb * 8);   // ~8 pixels per thread
+  long long gx = (Pw + ppb * 16 - 1) / (ppb * 16);   // ~16 pixels per thread
   if (gx > 148 * 16) gx = 148 * 16;
   if (gx < 1) gx = 1;
   gn_apply_kernel<<<dim3((unsigned)gx, d->batch), threads, 0, STREAM>>>(a);
@@ -800,11 +863,17 @@ extern "C" int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, 
     set_last_error("buddy_gn_bwd: split 2 needs the fp8 output buffers");
     return BUDDY_ERR_INVALID;
   }
+  if (static_cast<long long>(d->H) * d->W * (d->mode == 1 ? 4 : 1) >= (1LL << 31) ||
+      static_cast<long long>(d->H) * d->W * d->W >= (1LL << 32)) {
+    set_last_error("buddy_gn_bwd: image too large for 32-bit pixel indexing (H %d W %d)", d->H, d->W);
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  a.magic = d->W >= 2 ? static_cast<uint32_t>(((1ULL << 32) + d->W - 1) / d->W) : 0u;
   const int c4n = C / 4;
   const int threads = c4n * (256 / c4n > 0 ? 256 / c4n : 1);
   const long long ppb = threads / c4n;
   const long long P = static_cast<long long>(d->H) * d->W;
-  long long gx = (P + ppb * 8 - 1) / (ppb * 8);
+  long long gx = (P + ppb * 16 - 1) / (ppb * 16);
   if (gx > 148 * 16) gx = 148 * 16;
   if (gx < 1) gx = 1;
   e = check_cuda(cudaMemsetAsync(g->gsum, 0, sizeof(double) * 2 * d->groups * d->batch, STREAM), "memset gsum");

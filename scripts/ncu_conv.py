@@ -36,6 +36,10 @@ for (H, W, ci, co, mode) in SHAPES:
         kw = dict(a8=e4m3(torch.randn(B, H, W, 2 * ci, device=dev, generator=g)),
                   w8=e4m3(torch.randn(9, co, 2 * ci, device=dev, generator=g)))
     bias = torch.zeros(co, device=dev)
+    if os.environ.get("NOSTATS"):
+        stats = None
+    if os.environ.get("DIRECT"):
+        kw["direct_epilogue"] = True
     run = lambda: ops.conv_gemm(a, w, out, taps=9, n_total=co, passes=p, bias=bias, stats=stats, **kw)
     run()
     torch.cuda.synchronize()
