@@ -226,6 +226,7 @@ def run_ours(args):
                               blind_args(T_run) if blind else informed_args(T_STEPS))
     smp.utterance_offset = rank * B
     smp.micro_batch = args.micro_batch
+    smp.n_streams = args.streams
     if blind:
         # reference initialisation (tester.py:149-151): T60 = 0.1 s, weight 2, phases of coherent noise, per utterance
         from buddy_b200.blind import BlindEngine
@@ -374,7 +375,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--micro-batch", type=int, default=16)
-    ap.add_argument("--precision", default=os.environ.get("BUDDY_PRECISION", "fp16c8"))
+    ap.add_argument("--streams", type=int, default=2, help="micro-batches in flight on separate CUDA streams")
+    ap.add_argument("--precision", default=os.environ.get("BUDDY_PRECISION", "mixed"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="informed", choices=["informed", "blind"],
                     help="informed = BASELINE configs[1] (default, the bench line); blind = configs[2] (order 1, T=60, "

@@ -103,6 +103,7 @@ class BlindEngine:
         self.steps = {}
         self.state = None
         self.buf = None
+        self._bufs = {}
         return st
 
     def select(self, sl):
@@ -112,8 +113,12 @@ class BlindEngine:
         self.state["B"] = nb
         self.state["key"] = sl.start or 0
         self.steps.setdefault(self.state["key"], 0)
-        if self.buf is None or self.buf["u"].shape[0] != nb:
+        # scratch is per (micro-batch size, CUDA stream): micro-batches may run concurrently on different streams
+        key = (nb, torch.cuda.current_stream().cuda_stream)
+        if key not in self._bufs:
             self._alloc(nb)
+            self._bufs[key] = self.buf
+        self.buf = self._bufs[key]
 
     def _alloc(self, B):
         dev, N = self.device, self.N_BIG

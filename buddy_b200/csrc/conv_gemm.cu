@@ -63,9 +63,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmA82, const __grid_constant__ CUtensorMap tmB82,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const GemmParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem base is only guaranteed 16B aligned by the runtime: round up to 1024 (swizzle-128B atoms)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // SWIZZLE_128B atoms need a 1024-byte aligned base.  The kernel has no static shared memory, so the dynamic
+  // window starts right after the 1 KB the system reserves per CTA and the declared alignment holds; no slack is
+  // allocated for a run-time round-up (every spare KB is left to co-resident GroupNorm CTAs of another stream).
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int stage_bytes = kStageA + p.n_tile * 128;
   // [pipeline stages][2 staged epilogue chunks (if staged)][bias row 1 KB (if staged)][barriers]
   uint8_t* stage_out = smem + p.stages * stage_bytes;
@@ -640,7 +642,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
                  : 0;
   p.res_staged = (p.staged && d->resid) ? 1 : 0;
   const int epi_bytes = p.staged ? 2 * kChunkBytes + 1024 : 0;
-  int stages = (227 * 1024 - 2048 - epi_bytes) / stage_bytes;
+  int stages = (227 * 1024 - 1536 - epi_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
     set_last_error("buddy_conv_gemm: not enough shared memory for 2 stages");
@@ -747,7 +749,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     tmRes = tmA;
   }
 
-  const size_t smem_bytes = (size_t)stages * stage_bytes + epi_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + epi_bytes + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
     int e = check_cuda(

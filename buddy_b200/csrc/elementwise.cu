@@ -226,7 +226,7 @@ __device__ __forceinline__ float4 act4(float4 x, const float (&sc)[4], const flo
 }
 
 __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const GnApplyArgs a) {
-  __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float s_mean[32], s_rstd[32];
   const int b = blockIdx.y;
   const int C = a.s.Ca + a.s.Cb;
   group_stats_to_smem(s_mean, s_rstd, a.s, b, a.G, a.cpg, static_cast<double>(a.cpg) * a.H * a.W, a.eps);
@@ -387,8 +387,8 @@ __device__ __forceinline__ float4 pull_back4(const float* __restrict__ t, int mo
 
 template <bool kPass2>
 __global__ void __launch_bounds__(256, kPass2 ? 3 : 4) gn_bwd_kernel(const GnBwdArgs a) {
-  __shared__ float s_mean[64], s_rstd[64];
-  __shared__ float s_acc[64][2];
+  __shared__ float s_mean[32], s_rstd[32];
+  __shared__ float s_acc[32][2];
   const int b = blockIdx.y;
   const int C = a.s.Ca + a.s.Cb;
   const double n = static_cast<double>(a.cpg) * a.H * a.W;
@@ -776,7 +776,7 @@ extern "C" int buddy_gn_stats(const float* x, int B, int64_t P, int C, double* s
 
 static int check_gn(int Ca, int Cb, int G, const char* who) {
   const int C = Ca + Cb;
-  if (Ca % 8 || Cb % 8 || C <= 0 || C > 1024 || G <= 0 || G > 64 || C % G || (C / G) % 4) {
+  if (Ca % 8 || Cb % 8 || C <= 0 || C > 1024 || G <= 0 || G > 32 || C % G || (C / G) % 4) {
     set_last_error("%s: unsupported channel/group configuration Ca=%d Cb=%d G=%d", who, Ca, Cb, G);
     return BUDDY_ERR_UNSUPPORTED;
   }

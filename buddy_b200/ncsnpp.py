@@ -55,7 +55,7 @@ class NCSNpp(nn.Module):
     def __init__(self, init_scale=0., fourier_scale=16, fir_kernel=(1, 3, 3, 1), precision=None, **kwargs):
         super().__init__()
         import os
-        self.precision = precision or os.environ.get("BUDDY_PRECISION", "fp16c8")
+        self.precision = precision or os.environ.get("BUDDY_PRECISION", "mixed")
         for k, v in kwargs.items():
             if k in _SUPPORTED:
                 want = _SUPPORTED[k]

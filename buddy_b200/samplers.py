@@ -42,7 +42,33 @@ class Sampler:
         self.seed_base = 3000             # Philox stream of utterance b = seed_base + utterance_offset + b
         self.utterance_offset = 0         # global index of this rank's first utterance (multi-GPU shards)
         self.micro_batch = 16             # utterances per network evaluation
+        self.n_streams = 2                # micro-batches in flight: the HBM-bound GroupNorm/elementwise kernels of
+        #                                   one overlap the tensor-core convolutions of the other (results identical)
+        self._streams = None
         self._draw = 0
+
+    def _for_micro_batches(self, B, body):
+        """Run body(slice) for every micro-batch, round-robin over `n_streams` CUDA streams forked from / joined
+        to the current stream.  Micro-batches touch disjoint utterances, so the order of execution is free."""
+        slices = [slice(s, min(B, s + self.micro_batch)) for s in range(0, B, self.micro_batch)]
+        ns = min(self.n_streams, len(slices))
+        if ns <= 1:
+            for sl in slices:
+                body(sl)
+            return
+        main = torch.cuda.current_stream()
+        if self._streams is None or len(self._streams) < ns or self._streams[0].device != main.device:
+            self._streams = [torch.cuda.Stream(device=main.device) for _ in range(ns)]
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for k, sl in enumerate(slices):
+            st = self._streams[k % ns]
+            if k < ns:
+                st.wait_event(fork)
+            with torch.cuda.stream(st):
+                body(sl)
+        for st in self._streams[:ns]:
+            main.wait_stream(st)
 
     # ---- schedule (Sampler.py:39-56) -----------------------------------------------------------------
     def create_schedule(self, sigma_min=None, sigma_max=None, rho=None, T=None):
@@ -153,13 +179,15 @@ class EulerHeunSampler(Sampler):
         B, dev = x.shape[0], x.device
         d = torch.empty_like(x)
         x_den = torch.empty_like(x)
-        for s in range(0, B, self.micro_batch):
-            sl = slice(s, min(B, s + self.micro_batch))
+
+        def body(sl):
             xd, _ = self._denoise(x[sl].contiguous(), sigma, save=False)
             x_den[sl] = xd
             nb = xd.shape[0]
             d[sl] = ops.lincomb3(torch.empty_like(xd), x[sl].contiguous(), _vec(1.0 / sigma, nb, dev), xd,
                                  _vec(-1.0 / sigma, nb, dev))
+
+        self._for_micro_batches(B, body)
         return d, x_den
 
     def predict(self, shape, device, blind=False):
@@ -241,22 +269,25 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
             raise ValueError("operator has no RIR (`.params`): call operator.update_params(rir) first")
         self._rir = RirConv(rir.detach().to(dev), n, dev)
 
-    def get_likelihood_score(self, x_den, ctx, x_hat, sigma):
-        """zeta/(||g||/sqrt(audio_len)+1e-8) * g with g = d rec_loss / d x_hat through the denoiser; per utterance."""
+    def get_likelihood_score(self, x_den, ctx, x_hat, sigma, Y=None, first=0):
+        """zeta/(||g||/sqrt(audio_len)+1e-8) * g with g = d rec_loss / d x_hat through the denoiser; per utterance.
+        `Y` = observation spectra of these utterances (default: the whole bound batch), `first` = their offset."""
+        if Y is None:
+            Y = self._Y[first:first + x_den.shape[0]]
         B, n = x_den.shape
         dev = x_den.device
         cskip, cout, cin, _ = self._edm_scalars(sigma)
         net = self.model
         eng, st = net.engine(), net.stft_engine()
         if self._is_blind:
-            gd, loss = self._blind.likelihood_grad(x_den, self._Y_mb, self._loss_w, self._loss_c)
+            gd, loss = self._blind.likelihood_grad(x_den, Y, self._loss_w, self._loss_c)
         else:
-            y_hat = self._rir.forward(x_den)
+            y_hat = self._rir.forward(x_den, first)
             Yh = self._loss_stft.forward(y_hat)
             loss = torch.empty(B, device=dev, dtype=torch.float64)
             G = torch.empty_like(Yh)
-            ops.comp_loss(self._Y_mb, Yh, Yh.shape[2], self._loss_c, self._loss_w, loss, G)
-            gd = self._rir.adjoint(self._loss_stft.adjoint(G, n))           # d loss / d x_den
+            ops.comp_loss(Y, Yh, Yh.shape[2], self._loss_c, self._loss_w, loss, G)
+            gd = self._rir.adjoint(self._loss_stft.adjoint(G, n), first)    # d loss / d x_den
         dspec = eng.vjp(ctx, st.inverse_adjoint(gd))
         v = st.forward_adjoint(dspec, n, scale_b=_vec(cin * cout, B, dev))
         g = ops.lincomb3(torch.empty_like(gd), gd, _vec(cskip, B, dev), v, _vec(1.0, B, dev))
@@ -272,15 +303,13 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
         x_den = torch.empty_like(x)
         ps = self.args.tester.posterior_sampling
         rescale = bool(ps.constraint_speech_magnitude.use)
-        for s in range(0, B, self.micro_batch):
-            sl = slice(s, min(B, s + self.micro_batch))
+        def body(sl):
             xs = x[sl].contiguous()
             nb = xs.shape[0]
-            self._Y_mb = self._Y[sl]
             xd, ctx = self._denoise(xs, sigma, save=True)
             if self._is_blind:
                 self.optimize_op(xd, sigma, sl)
-            g, coef, loss = self.get_likelihood_score(xd, ctx, xs, sigma)
+            g, coef, loss = self.get_likelihood_score(xd, ctx, xs, sigma, self._Y[sl], sl.start or 0)
             del ctx
             if rescale:
                 st = ops.row_stats(xd)
@@ -292,6 +321,8 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
             d[sl] = ops.lincomb3(torch.empty_like(xd), xs, _vec(1.0 / sigma, nb, dev), xd, _vec(-1.0 / sigma, nb, dev),
                                  g, coef)
             self.rec_loss_value = loss
+
+        self._for_micro_batches(B, body)
         self._eval_index += 1
         return d, x_den
 

@@ -149,18 +149,23 @@ class RirConv:
         self.tw = torch.stack([torch.cos(2 * math.pi * k / 512), -torch.sin(2 * math.pi * k / 512)], -1).float().to(device)
         self.H = torch.empty(hb.shape[0], self.L, 2, device=device)
         ops.fftconv(hb.contiguous(), m, self.log2_n2, self.tw, self.H, None, 0, 0, None, 0)
-        self._work = None
 
-    def _apply(self, x, mode):
+    def _apply(self, x, mode, first):
         B = x.shape[0]
-        if self._work is None or self._work.shape[0] != B:
-            self._work = torch.empty(B, self.L, 2, device=x.device)
+        work = torch.empty(B, self.L, 2, device=x.device)     # per call: stream-ordered, safe across streams
         y = torch.empty(B, self.n, device=x.device)
         stride = self.L * 2 if self.per_utt else 0
-        return ops.fftconv(x, x.shape[1], self.log2_n2, self.tw, self._work, self.H, stride, mode, y, self.n)
+        if self.per_utt:
+            if first + B > self.H.shape[0]:
+                raise ValueError(f"RirConv: utterances [{first}, {first + B}) but only {self.H.shape[0]} RIRs")
+            H = self.H[first:first + B]
+        else:
+            H = self.H
+        return ops.fftconv(x, x.shape[1], self.log2_n2, self.tw, work, H, stride, mode, y, self.n)
 
-    def forward(self, x):
-        return self._apply(x, 1)
+    def forward(self, x, first=0):
+        """x: [B, n] = utterances first .. first+B-1 of the batch the RIRs were given for."""
+        return self._apply(x, 1, first)
 
-    def adjoint(self, g):
-        return self._apply(g, 2)
+    def adjoint(self, g, first=0):
+        return self._apply(g, 2, first)

@@ -53,16 +53,25 @@ def qe2m1_block(x, dim=1, block=32):
 
 QS = {"e4m3": qe4m3, "e2m1": qe2m1_block, "f16": lambda x, dim=1: q16(x), "none": None}
 
-SCHEME = {"corr_a": "none", "corr_w": "none", "bwd_same": True}
+SCHEME = {"corr_a": "none", "corr_w": "none", "bwd_same": True, "policy": None}
+COST = {"flops": 0.0, "passes": 0.0}
+PASS_COST = {"none": 0.0, "e4m3": 0.5, "e2m1": 0.25, "f16": 1.0}
 
 
-def _emul(a, w, conv, kdim_a, kdim_w):
+def _emul(a, w, conv, kdim_a, kdim_w, H, direction):
+    ca, cw = SCHEME["corr_a"], SCHEME["corr_w"]
+    if SCHEME["policy"] is not None:
+        SCHEME["w_shape"] = tuple(w.shape[:2])      # (Cout, Cin) of the conv weight, both directions
+        ca, cw = SCHEME["policy"](H, direction)
     ah, wh = q16(a), q16(w)
     out = conv(ah, wh)
-    qa = QS[SCHEME["corr_a"]]
+    fl = float(out.numel()) * w.shape[1 if kdim_w == 1 else 0] * w.shape[2] * w.shape[3]
+    COST["flops"] += fl
+    COST["passes"] += fl * (1.0 + PASS_COST[ca] + PASS_COST[cw])
+    qa = QS[ca]
     if qa is not None:
         out = out + conv(qa(a - ah, kdim_a), qa(wh, kdim_w))
-    qw = QS[SCHEME["corr_w"]]
+    qw = QS[cw]
     if qw is not None:
         out = out + conv(qw(ah, kdim_a), qw(w - wh, kdim_w))
     return out
@@ -76,7 +85,7 @@ class QConv(torch.autograd.Function):
         ctx.xshape = x.shape
         if SCHEME.get("exact"):
             return F.conv2d(x, w, b, padding=padding)
-        out = _emul(x, w, lambda a, ww: F.conv2d(a, ww, None, padding=padding), 1, 1)
+        out = _emul(x, w, lambda a, ww: F.conv2d(a, ww, None, padding=padding), 1, 1, x.shape[2], 'fwd')
         return out + b[None, :, None, None] if b is not None else out
 
     @staticmethod
@@ -87,7 +96,7 @@ class QConv(torch.autograd.Function):
             return F.conv_transpose2d(g, w, None, padding=p), None, None, None
         # normalise like the engine (per-tensor power of two) so fp16 range is no issue
         s = 2.0 ** math.floor(math.log2(1.0 / g.abs().max().clamp_min(1e-30).item())) * 64.0
-        dx = _emul(g * s, w, lambda a, ww: F.conv_transpose2d(a, ww, None, padding=p), 1, 0) / s
+        dx = _emul(g * s, w, lambda a, ww: F.conv_transpose2d(a, ww, None, padding=p), 1, 0, g.shape[2], 'bwd') / s
         return dx, None, None, None
 
 
@@ -123,13 +132,27 @@ def run(frames=80):
     SCHEME["exact"] = False
     onet.F = _FShim()
     rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()
-    for name, ca, cw in [("fp16 1-pass", "none", "none"), ("act corr e4m3", "e4m3", "none"),
-                         ("wgt corr e4m3", "none", "e4m3"), ("both e4m3 (fp16c8)", "e4m3", "e4m3"),
-                         ("both e2m1 block32", "e2m1", "e2m1"), ("act e2m1 only", "e2m1", "none"),
-                         ("both f16 (fp16x3)", "f16", "f16")]:
-        SCHEME["corr_a"], SCHEME["corr_w"] = ca, cw
+    c8 = ("e4m3", "e4m3")
+    x1 = ("none", "none")
+    a8 = ("e4m3", "none")
+    w8 = ("none", "e4m3")
+    BIG = {(256, 256, 256), (256, 128, 384), (256, 128, 256), (128, 256, 512)}        # (H, Cout, Cin)
+    MID = {(128, 256, 384), (128, 256, 256), (256, 128, 128)}
+    big = lambda H: (H,) + SCHEME["w_shape"] in BIG
+    mid = lambda H: (H,) + SCHEME["w_shape"] in MID
+    policies = {
+        "A: top5 x1, rest c8": lambda H, d: x1 if big(H) else c8,
+        "A2: top5 a8, rest c8": lambda H, d: a8 if big(H) else c8,
+        "B: top5 x1, mid a8, rest c8": lambda H, d: x1 if big(H) else (a8 if mid(H) else c8),
+        "C: top5 x1 fwd / a8 bwd, rest c8": lambda H, d: (x1 if d == "fwd" else a8) if big(H) else c8,
+        "D: top5+mid x1, rest c8": lambda H, d: x1 if (big(H) or mid(H)) else c8,
+    }
+    for name, pol in policies.items():
+        SCHEME["policy"] = pol
+        COST["flops"] = COST["passes"] = 0.0
         o, gr = evaluate()
-        print(f"{name:24s} fwd {rel(o, ref_o):.2e}  vjp {rel(gr, ref_g):.2e}", flush=True)
+        print(f"{name:32s} fwd {rel(o, ref_o):.2e}  vjp {rel(gr, ref_g):.2e}  passes {COST['passes'] / COST['flops']:.3f}",
+              flush=True)
     onet.F = F
 
 

@@ -12,9 +12,9 @@ TOL = 1e-3
 
 
 def tol(net):
-    # fp16c8 (the default) and fp16x3 must meet the north-star 1e-3; the single-pass modes are opt-in speed modes
-    # with TF32-class (11-bit) operands and are only required to stay in that class
-    return TOL if net.precision in ("fp16c8", "fp16x3") else 3e-3
+    # mixed (the default), fp16c8 and fp16x3 must meet the north-star 1e-3; the single-pass modes are opt-in speed
+    # modes with TF32-class (11-bit) operands and are only required to stay in that class
+    return TOL if net.precision in ("mixed", "fp16c8", "fp16x3") else 3e-3
 
 
 def rel(a, b):
@@ -37,7 +37,7 @@ def sd():
     return make_state_dict(0)
 
 
-@pytest.fixture(scope="module", params=["fp16c8", "fp16x3", "fp16x2", "fp16"])
+@pytest.fixture(scope="module", params=["mixed", "fp16c8", "fp16x3", "fp16x2", "fp16"])
 def net(sd, request):
     from buddy_b200.ncsnpp import NCSNppTime
     m = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2],
