@@ -375,7 +375,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--micro-batch", type=int, default=16)
-    ap.add_argument("--streams", type=int, default=2, help="micro-batches in flight on separate CUDA streams")
+    ap.add_argument("--streams", type=int, default=1, help="micro-batches in flight on separate CUDA streams")
     ap.add_argument("--precision", default=os.environ.get("BUDDY_PRECISION", "mixed"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="informed", choices=["informed", "blind"],

@@ -147,12 +147,16 @@ __global__ void design_fwd_kernel(const float* __restrict__ decays, const float*
     }
   }
 }
-// backward: G = dL/dH0 [B][F][Nf+2] -> dphases [B][F][Nf], ddecays/dweights [B][25] (atomics; zero them first)
+// backward: G = dL/dH0 [B][F][Nf+2] -> dphases [B][F][Nf] and per-tap partials of ddecays/dweights
+// part[b][2][25][Nf]; design_bwd_reduce_kernel sums the taps in a fixed order (no atomics anywhere: the operator
+// gradients feed Adam, whose sign-like first steps amplify any run-to-run difference).
+constexpr int kMaxF = 1024;
 __global__ void design_bwd_kernel(const float* __restrict__ decays, const float* __restrict__ weights,
                                   const float* __restrict__ phases, const float* __restrict__ A, DesignTabs tb,
                                   const float2* __restrict__ G, int F, int Nf, float* __restrict__ dphases,
-                                  float* __restrict__ ddecays, float* __restrict__ dweights) {
+                                  float* __restrict__ part) {
   __shared__ float sL[kBands], sD[kBands], sdL[kBands];
+  __shared__ float s_dlf[kMaxF];
   const int n = blockIdx.x, b = blockIdx.y;
   if (threadIdx.x < kBands) {
     const int e = threadIdx.x;
@@ -161,7 +165,6 @@ __global__ void design_bwd_kernel(const float* __restrict__ decays, const float*
       D = weights[b * (kBands - 2) + e - 1] * powf(expf(decays[b * (kBands - 2) + e - 1]), -static_cast<float>(n));
     sD[e] = D;
     sL[e] = logf(D + 1e-6f);
-    sdL[e] = 0.f;
   }
   __syncthreads();
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
@@ -175,11 +178,20 @@ __global__ void design_bwd_kernel(const float* __restrict__ decays, const float*
     float dA = tr;
     if (n < 3) dA /= tb.corr[n];
     const int k = tb.kidx[f];
-    const float fr = tb.frac[f];
-    const float lf = sL[k] + fr * (sL[k + 1] - sL[k]);
-    const float dlf = dA * expf(lf);
-    atomicAdd(&sdL[k], (1.f - fr) * dlf);
-    atomicAdd(&sdL[k + 1], fr * dlf);
+    const float lf = sL[k] + tb.frac[f] * (sL[k + 1] - sL[k]);
+    s_dlf[f] = dA * expf(lf);
+  }
+  __syncthreads();
+  if (threadIdx.x < kBands) {
+    // knot e collects (1-frac) of the bins in segment e and frac of the bins in segment e-1, in bin order
+    const int e = threadIdx.x;
+    float acc = 0.f;
+    for (int f = 0; f < F; ++f) {
+      const int k = tb.kidx[f];
+      if (k == e) acc += (1.f - tb.frac[f]) * s_dlf[f];
+      else if (k + 1 == e) acc += tb.frac[f] * s_dlf[f];
+    }
+    sdL[e] = acc;
   }
   __syncthreads();
   if (threadIdx.x >= 1 && threadIdx.x <= kBands - 2) {
@@ -187,9 +199,21 @@ __global__ void design_bwd_kernel(const float* __restrict__ decays, const float*
     const float dD = sdL[e] / (sD[e] + 1e-6f);
     const float w = weights[b * (kBands - 2) + e - 1];
     const float ex = (w != 0.f) ? sD[e] / w : powf(expf(decays[b * (kBands - 2) + e - 1]), -static_cast<float>(n));
-    atomicAdd(&dweights[b * (kBands - 2) + e - 1], dD * ex);
-    atomicAdd(&ddecays[b * (kBands - 2) + e - 1], dD * sD[e] * (-static_cast<float>(n)));
+    float* pb = part + static_cast<long long>(b) * 2 * (kBands - 2) * Nf;
+    pb[(e - 1) * Nf + n] = dD * ex;                                                   // d weights
+    pb[((kBands - 2) + e - 1) * Nf + n] = dD * sD[e] * (-static_cast<float>(n));      // d decays
   }
+}
+// ddecays / dweights [B][25] = sum over the Nf taps of the partials, tap order
+__global__ void design_bwd_reduce_kernel(const float* __restrict__ part, int Nf, float* __restrict__ ddecays,
+                                         float* __restrict__ dweights) {
+  const int b = blockIdx.x, e = threadIdx.x;
+  if (e >= 2 * (kBands - 2)) return;
+  const float* p = part + (static_cast<long long>(b) * 2 * (kBands - 2) + e) * Nf;
+  float acc = 0.f;
+  for (int n = 0; n < Nf; ++n) acc += p[n];
+  if (e < kBands - 2) dweights[b * (kBands - 2) + e] = acc;
+  else ddecays[b * (kBands - 2) + e - (kBands - 2)] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------ mixed-radix FFT
@@ -371,16 +395,18 @@ extern "C" int buddy_blind_design_fwd(const float* decays, const float* weights,
 extern "C" int buddy_blind_design_bwd(const float* decays, const float* weights, const float* phases, const float* A,
                                       const int* kidx, const float* frac, const float* corr, const float* dpmag,
                                       const float* G, int batch, int F, int Nf, float* dphases, float* ddecays,
-                                      float* dweights, void* stream) {
+                                      float* dweights, float* scratch, void* stream) {
   DesignTabs tb{kidx, frac, corr, dpmag};
-  int e = check_cuda(cudaMemsetAsync(ddecays, 0, sizeof(float) * 25 * batch, STREAM), "memset ddecays");
-  if (e) return e;
-  e = check_cuda(cudaMemsetAsync(dweights, 0, sizeof(float) * 25 * batch, STREAM), "memset dweights");
-  if (e) return e;
+  if (F > kMaxF || !scratch) {
+    set_last_error("buddy_blind_design_bwd: F must be <= %d and scratch [batch][50][Nf] must be given", kMaxF);
+    return BUDDY_ERR_INVALID;
+  }
   design_bwd_kernel<<<dim3(Nf, batch), 256, 0, STREAM>>>(decays, weights, phases, A, tb,
-                                                         reinterpret_cast<const float2*>(G), F, Nf, dphases, ddecays,
-                                                         dweights);
-  LAUNCH_END("design_bwd_kernel");
+                                                         reinterpret_cast<const float2*>(G), F, Nf, dphases, scratch);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  BUDDY_CHECK_LAUNCH("design_bwd_kernel");
+  design_bwd_reduce_kernel<<<batch, 64, 0, STREAM>>>(scratch, Nf, ddecays, dweights);
+  LAUNCH_END("design_bwd_reduce_kernel");
 }
 extern "C" int buddy_fft_mixed(const float* in, int in_real, float* work, float* out, int batch, int N1, int sign,
                                const float* tw512, void* stream) {

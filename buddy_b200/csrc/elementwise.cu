@@ -91,7 +91,7 @@ __device__ __forceinline__ uint32_t pack4_e4m3(float a, float b, float c, float 
 // fp16 operand store; split: row = [hi (C) | lo (C)], lo = fp16(v - float(hi)); split 2: fp16 hi + e4m3 pair (base8)
 __device__ __forceinline__ void store_op8(__half* base, long long pix, int C, int c, int split, const float (&v)[8],
                                           uint8_t* base8 = nullptr) {
-  if (split == 2) {
+  if (split == 2 && base8) {
     float hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -106,7 +106,7 @@ __device__ __forceinline__ void store_op8(__half* base, long long pix, int C, in
         make_uint2(pack4_e4m3(hi[0], hi[1], hi[2], hi[3]), pack4_e4m3(hi[4], hi[5], hi[6], hi[7]));
     return;
   }
-  if (!split) {
+  if (!split || split == 2) {
     store8h(base + pix * C + c, v);
     return;
   }
@@ -194,7 +194,7 @@ __device__ __forceinline__ uint32_t pack4_e4m3(float a, float b, float c, float 
 // split 2: fp16 hi in `base` (row C) + e4m3 pair in `base8` (row 2C bytes) = [e4m3(lo * 2^9) | e4m3(hi)].
 __device__ __forceinline__ void store_op4(__half* base, uint8_t* base8, size_t pix, int C, int c, int split,
                                           float4 v) {
-  if (split == 2) {
+  if (split == 2 && base8) {
     const float hx = __half2float(__float2half_rn(v.x)), hy = __half2float(__float2half_rn(v.y));
     const float hz = __half2float(__float2half_rn(v.z)), hw = __half2float(__float2half_rn(v.w));
     *reinterpret_cast<uint2*>(base + pix * C + c) = pack4h(hx, hy, hz, hw);
@@ -204,7 +204,7 @@ __device__ __forceinline__ void store_op4(__half* base, uint8_t* base8, size_t p
     *reinterpret_cast<uint32_t*>(r8 + C + c) = pack4_e4m3(hx, hy, hz, hw);
     return;
   }
-  if (!split) {
+  if (!split || split == 2) {   // split 2 without an fp8 buffer: the consumer runs a single fp16 pass
     *reinterpret_cast<uint2*>(base + pix * C + c) = pack4h(v.x, v.y, v.z, v.w);
     return;
   }
@@ -388,13 +388,11 @@ __device__ __forceinline__ float4 pull_back4(const float* __restrict__ t, int mo
 template <bool kPass2>
 __global__ void __launch_bounds__(256, kPass2 ? 3 : 4) gn_bwd_kernel(const GnBwdArgs a) {
   __shared__ float s_mean[32], s_rstd[32];
-  __shared__ float s_acc[32][2];
+  __shared__ float s_part[kPass2 ? 1 : 256][2];   // pass 0: per-thread partials, reduced in a fixed order
   const int b = blockIdx.y;
   const int C = a.s.Ca + a.s.Cb;
   const double n = static_cast<double>(a.cpg) * a.H * a.W;
   group_stats_to_smem(s_mean, s_rstd, a.s, b, a.G, a.cpg, n, a.eps);
-  if (!kPass2)
-    for (int g = threadIdx.x; g < a.G; g += blockDim.x) s_acc[g][0] = s_acc[g][1] = 0.f;
   __syncthreads();
   const int c4n = C >> 2;  // blockDim.x is a multiple of c4n -> each thread keeps one channel bundle
   const int c = (threadIdx.x % c4n) * 4;
@@ -485,12 +483,23 @@ __global__ void __launch_bounds__(256, kPass2 ? 3 : 4) gn_bwd_kernel(const GnBwd
     }
   }
   if (!kPass2) {
-    atomicAdd(&s_acc[grp][0], p1);
-    atomicAdd(&s_acc[grp][1], p2);
+    // CTA reduction in a fixed order (no floating-point atomics in shared memory): thread g sums the partials of
+    // group g's bundles over the CTA's pixel lanes; the fp64 global atomics that follow add fp32 values almost
+    // exactly, so the statistics — and with them every fp16 rounding decision downstream — repeat run to run.
+    s_part[threadIdx.x][0] = p1;
+    s_part[threadIdx.x][1] = p2;
     __syncthreads();
+    const int bpg = a.cpg >> 2;  // bundles (threads) per group within one pixel lane
     for (int g = threadIdx.x; g < a.G; g += blockDim.x) {
-      atomicAdd(a.gsum + (static_cast<long long>(b) * a.G + g) * 2, static_cast<double>(s_acc[g][0]));
-      atomicAdd(a.gsum + (static_cast<long long>(b) * a.G + g) * 2 + 1, static_cast<double>(s_acc[g][1]));
+      float s1 = 0.f, s2 = 0.f;
+      for (uint32_t lp = 0; lp < ppb; ++lp)
+        for (int j = 0; j < bpg; ++j) {
+          const int t = lp * c4n + g * bpg + j;
+          s1 += s_part[t][0];
+          s2 += s_part[t][1];
+        }
+      atomicAdd(a.gsum + (static_cast<long long>(b) * a.G + g) * 2, static_cast<double>(s1));
+      atomicAdd(a.gsum + (static_cast<long long>(b) * a.G + g) * 2 + 1, static_cast<double>(s2));
     }
   }
 }
@@ -806,10 +815,6 @@ extern "C" int buddy_gn_apply(const buddy_gn_desc* d, void* stream) {
   a.split = d->split;
   a.out8 = static_cast<uint8_t*>(d->out8);
   a.out_raw8 = static_cast<uint8_t*>(d->out_raw8);
-  if (d->split == 2 && (!d->out8 || (d->out_raw && !d->out_raw8))) {
-    set_last_error("buddy_gn_apply: split 2 needs the fp8 output buffers");
-    return BUDDY_ERR_INVALID;
-  }
   {
     const long long rowlen = d->mode == 2 ? d->W / 2 : d->W;
     if (static_cast<long long>(d->H) * d->W * (d->mode == 1 ? 4 : 1) >= (1LL << 31) ||
@@ -859,10 +864,6 @@ extern "C" int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, 
   a.split = d->split;
   a.g8a = static_cast<uint8_t*>(g->g8a);
   a.g8b = static_cast<uint8_t*>(g->g8b);
-  if (d->split == 2 && ((g->g16a && !g->g8a) || (g->g16b && !g->g8b))) {
-    set_last_error("buddy_gn_bwd: split 2 needs the fp8 output buffers");
-    return BUDDY_ERR_INVALID;
-  }
   if (static_cast<long long>(d->H) * d->W * (d->mode == 1 ? 4 : 1) >= (1LL << 31) ||
       static_cast<long long>(d->H) * d->W * d->W >= (1LL << 32)) {
     set_last_error("buddy_gn_bwd: image too large for 32-bit pixel indexing (H %d W %d)", d->H, d->W);

@@ -183,14 +183,20 @@ class Engine:
         dgr = w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, ci, co)
         return self._pack(fwd, x1), self._pack(dgr, x1)
 
-    def _operand(self, B, H, W, C, gs=1.0):
+    def _operand(self, B, H, W, C, gs=1.0, need8=True):
+        """need8 = False: every consumer of this operand runs a single fp16 pass (no e4m3 correction pair)."""
         t16 = torch.empty(B, H, W, C * self.am, device=self.device, dtype=torch.float16)
-        t8 = torch.empty(B, H, W, 2 * C, device=self.device, dtype=torch.uint8) if self.c8 else None
+        t8 = torch.empty(B, H, W, 2 * C, device=self.device, dtype=torch.uint8) if (self.c8 and need8) else None
         return Opnd(t16, t8, gs)
+
+    def _x1(self, i, k):
+        """True if convolution k (0/1; the fused skip conv follows 1) of ResBlock i runs single-pass."""
+        return i is not None and (i, k) in self.x1_convs
 
     def _conv(self, A, Wp, out, *, taps, n_total, A2=None, W2=None, scale=1.0, **kw):
         """Split-precision conv/GEMM launch: undoes the operand's extra scale in the epilogue."""
         c8 = Wp.w8 is not None      # weights packed without corrections -> single fp16 pass
+        assert not c8 or (A.t8 is not None and (A2 is None or A2.t8 is not None)), "operand lacks its e4m3 pair"
         return ops.conv_gemm(A.t16, Wp.w16, out, taps=taps, n_total=n_total, passes=self.np,
                              a2=A2.t16 if A2 is not None else None, w2=W2.w16[0] if W2 is not None else None,
                              a8=A.t8 if c8 else None, w8=Wp.w8, a8_2=A2.t8 if (A2 is not None and c8) else None,
@@ -236,7 +242,7 @@ class Engine:
         if r.has_skip_conv:
             w2 = sd[p + "Conv_2.weight"].reshape(r.cout, r.cin)
             r.w2 = self._pack(w2[None], r.x1[1])                    # [1, Cout, p*Cin] (fused into conv 1's launch)
-            r.wd2 = self._pack(w2.t().contiguous()[None])           # [1, Cin, p*Cout]
+            r.wd2 = self._pack(w2.t().contiguous()[None], r.x1[1])  # [1, Cin, p*Cout]
             r.bias1 = (sd[p + "Conv_1.bias"] + sd[p + "Conv_2.bias"]).contiguous()
         else:
             r.bias1 = sd[p + "Conv_1.bias"].contiguous()
@@ -307,15 +313,15 @@ class Engine:
         assert C == r.cin, (i, C, r.cin)
         Ho, Wo = (2 * H, 2 * W) if mode == MODE_UP else ((H // 2, W // 2) if mode == MODE_DOWN else (H, W))
         dev = self.device
-        a0 = self._operand(B, Ho, Wo, C)
-        raw = self._operand(B, Ho, Wo, C) if r.has_skip_conv else None
+        a0 = self._operand(B, Ho, Wo, C, need8=not r.x1[0])
+        raw = self._operand(B, Ho, Wo, C, need8=not r.x1[1]) if r.has_skip_conv else None
         ops.gn_apply(xa, sa, r.g0, r.b0, a0.t16, xb=xb, sb=sb, silu=True, mode=mode,
                      out_raw=raw.t16 if raw else None, split=self.split, out8=a0.t8, out_raw8=raw.t8 if raw else None)
         h1 = torch.empty(B, Ho, Wo, r.cout, device=dev)
         s1 = self._zeros_stats(B, r.cout)
         self._conv(a0, r.w0, h1, taps=9, n_total=r.cout, bias=r.bias0, bias_b=tb[i], stats=s1)
         del a0
-        a1 = self._operand(B, Ho, Wo, r.cout)
+        a1 = self._operand(B, Ho, Wo, r.cout, need8=not r.x1[1])
         ops.gn_apply(h1, s1, r.g1, r.b1, a1.t16, silu=True, split=self.split, out8=a1.t8)
         out = torch.empty(B, Ho, Wo, r.cout, device=dev)
         so = self._zeros_stats(B, r.cout)
@@ -328,8 +334,10 @@ class Engine:
             save[i] = (xa, sa, xb, sb, h1, s1, mode)
         return out, so
 
-    def _rb_bwd(self, i, saved, g16, dout32, extra_a=None, want_a32=True, want_a16=True, a16_scale=INV_SQRT2):
-        """g16 = fp16(dout/sqrt2); returns (dxa32, g16a, dxb32)."""
+    def _rb_bwd(self, i, saved, g16, dout32, extra_a=None, want_a32=True, want_a16=True, a16_scale=INV_SQRT2,
+                consumer=None):
+        """g16 = fp16(dout/sqrt2); returns (dxa32, g16a, dxb32).  `consumer` = ResBlock whose conv-1 / skip dgrad
+        reads the returned g16a (decides whether it needs the e4m3 correction pair)."""
         r = self.rb[i]
         xa, sa, xb, sb, h1, s1, mode = saved[i]
         B, Ho, Wo, _ = h1.shape
@@ -337,7 +345,7 @@ class Engine:
         gsum = self._scratch_gsum(B)
         da1 = torch.empty(B, Ho, Wo, r.cout, device=dev)
         self._conv(g16, r.wd1, da1, taps=9, n_total=r.cout)
-        dh1 = self._operand(B, Ho, Wo, r.cout, self._gscale(("h1", i)))
+        dh1 = self._operand(B, Ho, Wo, r.cout, self._gscale(("h1", i)), need8=not r.x1[0])
         ops.gn_bwd(h1, s1, r.g1, r.b1, da1, gsum, silu=True, g16a=dh1.t16, g16_scale=dh1.gs, split=self.split,
                    g8a=dh1.t8)
         self._record(("h1", i), dh1)
@@ -353,7 +361,8 @@ class Engine:
             dsk, skip_scale = dout32, INV_SQRT2
         Ca = xa.shape[3]
         dxa = torch.empty_like(xa) if want_a32 else None
-        g16a = self._operand(*xa.shape[:3], Ca, self._gscale(("x", i))) if want_a16 else None
+        g16a = (self._operand(*xa.shape[:3], Ca, self._gscale(("x", i)), need8=not self._x1(consumer, 1))
+                if want_a16 else None)
         dxb = torch.empty_like(xb) if xb is not None else None
         ops.gn_bwd(xa, sa, r.g0, r.b0, da0, gsum, xb=xb, sb=sb, silu=True, mode=mode, dskip=dsk, skip_scale=skip_scale,
                    extra_a=extra_a, dxa=dxa, dxb=dxb, g16a=g16a.t16 if g16a else None,
@@ -390,7 +399,7 @@ class Engine:
             save["attn"] = (x, sx, qkv, P)
         return out, so
 
-    def _attn_bwd(self, saved, g16, dout32):
+    def _attn_bwd(self, saved, g16, dout32, consumer=None):
         a = self.attn
         x, sx, qkv, P = saved["attn"]
         B, H, W, C = x.shape
@@ -423,7 +432,7 @@ class Engine:
         dhn = torch.empty(B, H, W, C, device=dev)
         ops.conv_gemm(dqkv.view(B, H, W, 3 * C), a.wqkv_d, dhn, taps=1, n_total=C)
         dx = torch.empty_like(x)
-        g16x = self._operand(B, H, W, C, self._gscale(("attn",)))
+        g16x = self._operand(B, H, W, C, self._gscale(("attn",)), need8=not self._x1(consumer, 1))
         ops.gn_bwd(x, sx, a.g, a.b, dhn, self._scratch_gsum(B), silu=False, dskip=dout32, skip_scale=INV_SQRT2, dxa=dx,
                    g16a=g16x.t16, g16_scale=INV_SQRT2 * g16x.gs, split=self.split, g8a=g16x.t8)
         self._record(("attn",), g16x)
@@ -439,7 +448,7 @@ class Engine:
         self._conv(a, hd.w, out, taps=9, n_total=2, n_tile=16, bias=hd.bias)
         return out
 
-    def _head_bwd(self, i, h, sh, dP, extra, want32):
+    def _head_bwd(self, i, h, sh, dP, extra, want32, consumer=None):
         """dP fp32 [B,H,W,2] -> gradient w.r.t. h (plus `extra`), fp32 (optional) and fp16/sqrt2."""
         hd = self.heads[i]
         B, H, W, C = h.shape
@@ -450,7 +459,7 @@ class Engine:
         da = torch.empty(B, H, W, C, device=dev)
         self._conv(col, hd.wd, da, taps=1, n_total=C)
         dx = torch.empty_like(h) if want32 else None
-        g16 = self._operand(B, H, W, C, self._gscale(("hx", i)))
+        g16 = self._operand(B, H, W, C, self._gscale(("hx", i)), need8=not self._x1(consumer, 1))
         ops.gn_bwd(h, sh, hd.g, hd.b, da, self._scratch_gsum(B), silu=True, extra_a=extra, dxa=dx, g16a=g16.t16,
                    g16_scale=INV_SQRT2 * g16.gs, split=self.split, g8a=g16.t8)
         self._record(("hx", i), g16)
@@ -544,31 +553,37 @@ class Engine:
                 carry32 = None
             h, sh = ctx["head_in"][head]
             # the tensor under the head is produced by blocks[1] (has a skip conv): fp16 only is enough
-            _, g16 = self._head_bwd(head, h, sh, dP[3 - lvl_pos], carry32, want32=False)
+            _, g16 = self._head_bwd(head, h, sh, dP[3 - lvl_pos], carry32, want32=False, consumer=blocks[1])
             for bi in reversed(blocks):
                 first_of_level = (bi == blocks[0])
                 # producer of the h-part: blocks[0] for blocks[1]; for blocks[0]: the previous level's `up` block
                 # (skip conv) or, at the bottleneck level, ResBlock 16 (identity skip -> needs fp32 as well)
                 need32 = first_of_level and lvl_pos == 0
-                d32, g16, dxb = self._rb_bwd(bi, ctx, g16, None, want_a32=need32, want_a16=True)
+                if not first_of_level:
+                    cons = blocks[0]
+                else:
+                    cons = self.up_levels[lvl_pos - 1][2] if lvl_pos > 0 else self.attn_idx + 1
+                d32, g16, dxb = self._rb_bwd(bi, ctx, g16, None, want_a32=need32, want_a16=True, consumer=cons)
                 partial_hs[hs_idx] = dxb
                 hs_idx += 1
         # bottleneck: RB16 <- attention <- RB14
         i16 = self.attn_idx + 1
-        d32, g16, _ = self._rb_bwd(i16, ctx, g16, d32, want_a32=True)
-        d32, g16 = self._attn_bwd(ctx, g16, d32)
-        d32, g16, _ = self._rb_bwd(self.attn_idx - 1, ctx, g16, d32, extra_a=partial_hs[7], want_a32=True)
+        d32, g16, _ = self._rb_bwd(i16, ctx, g16, d32, want_a32=True)      # consumed by the attention block (c8 pair unused there, kept)
+        d32, g16 = self._attn_bwd(ctx, g16, d32, consumer=self.attn_idx - 1)
+        d32, g16, _ = self._rb_bwd(self.attn_idx - 1, ctx, g16, d32, extra_a=partial_hs[7], want_a32=True,
+                                   consumer=self.attn_idx - 2)
         # down path, backwards.  hs index k: 7 = RB13 out, 6 = Combine12, 5 = RB10, 4 = Combine9, 3 = RB7,
         # 2 = Combine6, 1 = RB4, 0 = input conv
         dpyr = {}
         i = self.attn_idx - 2       # 13
         for lvl in (3, 2, 1):
             # plain block at this level: input is the Combine output hs[2*lvl]
-            d32, g16, _ = self._rb_bwd(i, ctx, g16, d32, extra_a=partial_hs[2 * lvl], want_a32=True)
+            d32, g16, _ = self._rb_bwd(i, ctx, g16, d32, extra_a=partial_hs[2 * lvl], want_a32=True, consumer=i - 2)
             w, _ = self.comb[i - 1]
             dpyr[lvl] = ops.combine_bwd(d32, w, torch.empty(B, d32.shape[1], d32.shape[2], 2, device=dev))
             # down block (has skip conv): input hs[2*lvl-1]
-            d32, g16, _ = self._rb_bwd(i - 2, ctx, g16, None, extra_a=partial_hs[2 * lvl - 1], want_a32=True)
+            d32, g16, _ = self._rb_bwd(i - 2, ctx, g16, None, extra_a=partial_hs[2 * lvl - 1], want_a32=True,
+                                       consumer=i - 3)
             i -= 3
         # RB4 (identity skip) : input hs[0]; its producer is the input conv -> fp16 at scale 1
         _, g16, _ = self._rb_bwd(4, ctx, g16, d32, extra_a=partial_hs[0], want_a32=False, a16_scale=1.0)

@@ -435,10 +435,11 @@ def blind_design_fwd(decays, weights, phases, tabs, A, H0):
 
 def blind_design_bwd(decays, weights, phases, A, tabs, G, dphases, ddecays, dweights):
     B, F, Nf = phases.shape
+    scratch = torch.empty(B, 50, Nf, device=phases.device)
     check(lib().buddy_blind_design_bwd(ptr(decays), ptr(weights), ptr(phases), ptr(A), ptr(tabs["kidx"]),
                                        ptr(tabs["frac"]), ptr(tabs["corr"]), ptr(tabs["dpmag"]), ptr(G), c_int(B),
-                                       c_int(F), c_int(Nf), ptr(dphases), ptr(ddecays), ptr(dweights), stream_ptr()),
-          "buddy_blind_design_bwd")
+                                       c_int(F), c_int(Nf), ptr(dphases), ptr(ddecays), ptr(dweights), ptr(scratch),
+                                       stream_ptr()), "buddy_blind_design_bwd")
 
 
 def fft_mixed(x, in_real, work, out, N1, sign, tw512):

@@ -42,8 +42,10 @@ class Sampler:
         self.seed_base = 3000             # Philox stream of utterance b = seed_base + utterance_offset + b
         self.utterance_offset = 0         # global index of this rank's first utterance (multi-GPU shards)
         self.micro_batch = 16             # utterances per network evaluation
-        self.n_streams = 2                # micro-batches in flight: the HBM-bound GroupNorm/elementwise kernels of
-        #                                   one overlap the tensor-core convolutions of the other (results identical)
+        self.n_streams = 1                # micro-batches in flight on separate CUDA streams (results identical).  >1
+        #                                   overlaps one micro-batch's HBM-bound kernels with another's convolutions;
+        #                                   measured gain on B200 is <1 % because the convolutions already run at the
+        #                                   board power cap, so the default stays 1 (half the activation memory)
         self._streams = None
         self._draw = 0
 

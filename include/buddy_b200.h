@@ -259,7 +259,9 @@ int buddy_blind_design_fwd(const float* decays, const float* weights, const floa
                            float* A, float* H0, void* stream);
 int buddy_blind_design_bwd(const float* decays, const float* weights, const float* phases, const float* A,
                            const int* kidx, const float* frac, const float* corr, const float* dpmag, const float* G,
-                           int batch, int F, int Nf, float* dphases, float* ddecays, float* dweights, void* stream);
+                           int batch, int F, int Nf, float* dphases, float* ddecays, float* dweights,
+                           float* scratch /* [batch][50][Nf], fixed-order reduction of the per-tap partials */,
+                           void* stream);
 int buddy_fft_mixed(const float* in, int in_real, float* work, float* out, int batch, int N1, int sign,
                     const float* tw512, void* stream);
 int buddy_minphase_pw(int mode, const float* c0, const float* c1, const float* r0, const float* r1, float* oc,
