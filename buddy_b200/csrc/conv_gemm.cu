@@ -49,6 +49,7 @@ struct GemmParams {
   long long ld_res;
   float scale;
   double* stats;
+  int dbg;         // profiling experiments only: 1 = epilogue only hands the accumulator back, 2 = + TMEM loads
   int staged;      // 1: epilogue stages 128x32 fp32 chunks in shared memory and writes them with TMA stores
   int res_staged;  // 1: the residual is TMA-loaded into the staging buffer (needs staged)
 };
@@ -56,6 +57,10 @@ struct GemmParams {
 constexpr int kChunkBytes = kTileM * 128;   // one staged epilogue chunk: 128 rows x 32 fp32
 constexpr int kEpiThreads = 128;
 
+// kPair: two CTAs of a cluster work on one 256-row tile pair with tcgen05 cta_group::2 — each CTA loads its own 128
+// pixel rows of A and HALF of the weight tile, the leader CTA issues M=256 MMAs that read both halves, each CTA
+// drains its own 128 accumulator lanes.  Halves the L2->SM weight traffic and the shared-memory reads per MMA.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -68,7 +73,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // allocated for a run-time round-up (every spare KB is left to co-resident GroupNorm CTAs of another stream).
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  const int stage_bytes = kStageA + p.n_tile * 128;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader CTA of the pair
+  const int b_rows = kPair ? (p.n_tile >> 1) : p.n_tile;   // weight-tile rows this CTA loads
+  const int stage_bytes = kStageA + b_rows * 128;
   // [pipeline stages][2 staged epilogue chunks (if staged)][bias row 1 KB (if staged)][barriers]
   uint8_t* stage_out = smem + p.stages * stage_bytes;
   float* bias_s = reinterpret_cast<float*>(stage_out + 2 * kChunkBytes);
@@ -91,12 +98,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tma_prefetch_desc(&tmB2);
     }
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], kPair ? 2 : 1);   // pair: one expect_tx arrival per CTA, on the leader's barrier
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[s], kPair ? 8 : 4);  // one arrival per epilogue warp (of both CTAs, on the leader's)
       mbar_init(&res_bar[s], 1);
     }
     if (p.staged) {
@@ -106,16 +113,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_2sm(tmem_slot, 512);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();   // the peer's barriers are initialised before anything signals them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_per_img = p.tiles_h * p.tiles_w;
-  const int total_tiles = p.batch * tiles_per_img * p.n_tiles;
+  const int pix_tiles = p.batch * tiles_per_img;
+  // work items: (pixel tile | pixel-tile pair) x n-tile; a pair's second tile may lie past the end (b == batch):
+  // its TMA loads are zero-filled, its stores clipped, its statistics skipped
+  const int total_tiles = (kPair ? ((pix_tiles + 1) >> 1) : pix_tiles) * p.n_tiles;
+  const int t_first = kPair ? (blockIdx.x >> 1) : blockIdx.x;
+  const int t_step = kPair ? (gridDim.x >> 1) : gridDim.x;
   // k-block order: [fp8 correction: conv taps | skip conv] then [fp16: conv taps | skip conv]
   const int kb8_1 = p.taps * p.kchunks8_1;
   const int kb8 = kb8_1 + p.kchunks8_2;
@@ -127,49 +145,57 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_step) {
         const int nt = t % p.n_tiles;
-        const int pt = t / p.n_tiles;
+        const int pt = kPair ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
         const int b = pt / tiles_per_img;
         const int r = pt - b * tiles_per_img;
         const int h0 = (r / p.tiles_w) * p.bh;
         const int w0 = (r % p.tiles_w) * p.bw;
+        const int brow = nt * p.n_tile + static_cast<int>(rank) * b_rows;   // first weight row this CTA loads
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kStageA;
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          // select the operand pair and coordinates of this k-block
+          const CUtensorMap* ma;
+          const CUtensorMap* mb;
+          int ac, bc, dy = 0, dx = 0, b3 = 0;
           if (kb < kb8) {
             if (kb < kb8_1) {
               const int tap = kb / p.kchunks8_1;
               const int kc = kb - tap * p.kchunks8_1;
-              int dy = 0, dx = 0;
               if (p.taps == 9) {
                 dy = tap / 3 - 1;
                 dx = tap % 3 - 1;
               }
-              tma_load_4d(&tmA8, sa, &full_bar[stage], kc * 128, w0 + dx, h0 + dy, b);
-              tma_load_3d(&tmB8, sb, &full_bar[stage], kc * 128, nt * p.n_tile, tap);
+              ma = &tmA8; mb = &tmB8; ac = kc * 128; bc = kc * 128; b3 = tap;
             } else {
               const int kc = kb - kb8_1;
-              tma_load_4d(&tmA82, sa, &full_bar[stage], kc * 128, w0, h0, b);
-              tma_load_3d(&tmB82, sb, &full_bar[stage], kc * 128, nt * p.n_tile, 0);
+              ma = &tmA82; mb = &tmB82; ac = kc * 128; bc = kc * 128;
             }
           } else if (kb - kb8 < kb_phase1) {
             const int kk = kb - kb8;
             const int tap = kk / p.kchunks1;
             const int kc = kk - tap * p.kchunks1;
-            int dy = 0, dx = 0;
             if (p.taps == 9) {
               dy = tap / 3 - 1;
               dx = tap % 3 - 1;
             }
-            tma_load_4d(&tmA, sa, &full_bar[stage], (kc % p.a_wrap1) * kBlockK, w0 + dx, h0 + dy, b);
-            tma_load_3d(&tmB, sb, &full_bar[stage], kc * kBlockK, nt * p.n_tile, p.b_batched ? b : tap);
+            ma = &tmA; mb = &tmB; ac = (kc % p.a_wrap1) * kBlockK; bc = kc * kBlockK; b3 = p.b_batched ? b : tap;
           } else {
             const int kc = kb - kb8 - kb_phase1;
-            tma_load_4d(&tmA2, sa, &full_bar[stage], (kc % p.a_wrap2) * kBlockK, w0, h0, b);
-            tma_load_3d(&tmB2, sb, &full_bar[stage], kc * kBlockK, nt * p.n_tile, 0);
+            ma = &tmA2; mb = &tmB2; ac = (kc % p.a_wrap2) * kBlockK; bc = kc * kBlockK;
+          }
+          if (kPair) {
+            const uint32_t fb = mapa_u32(&full_bar[stage], 0);   // the leader's barrier collects both CTAs' bytes
+            mbar_expect_tx_cluster(fb, stage_bytes);
+            tma_load_4d_2sm(ma, sa, fb, ac, w0 + dx, h0 + dy, b);
+            tma_load_3d_2sm(mb, sb, fb, bc, brow, b3);
+          } else {
+            mbar_expect_tx(&full_bar[stage], stage_bytes);
+            tma_load_4d(ma, sa, &full_bar[stage], ac, w0 + dx, h0 + dy, b);
+            tma_load_3d(mb, sb, &full_bar[stage], bc, brow, b3);
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -179,15 +205,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (single thread)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kTileM, p.n_tile);
-      const uint32_t idesc8 = make_idesc_e4m3(kTileM, p.n_tile);
+    // ================================================================ MMA issuer (single thread; pair: leader CTA only)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_f16(kPair ? 2 * kTileM : kTileM, p.n_tile);
+      const uint32_t idesc8 = make_idesc_e4m3(kPair ? 2 * kTileM : kTileM, p.n_tile);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
@@ -200,23 +226,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // each MMA consumes 32 bytes of K per row (16 fp16 or 32 e4m3): +2 in (addr >> 4) units
           if (kb < kb8) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc8, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              if (kPair) umma_f8_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc8, (kb > 0 || k > 0) ? 1u : 0u);
+              else umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc8, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           } else if (kb == kb8 && kb8 > 0) {
             // first fp16 block after the corrections: fold their 2^14 scale away (D = A*B + D * 2^-14)
-            umma_f16_scale_d14(d_tmem, da, db, idesc);
+            if (kPair) umma_f16_scale_d14_2sm(d_tmem, da, db, idesc);
+            else umma_f16_scale_d14(d_tmem, da, db, idesc);
 #pragma unroll
-            for (int k = 1; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+            for (int k = 1; k < 4; ++k) {
+              if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+              else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+            }
           } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if (kPair) umma_commit_2sm(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs of a pair)
+        if (kPair) umma_commit_2sm(&tmem_full[acc]);
+        else umma_commit(&tmem_full[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -241,21 +281,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t cc = 0;                 // running chunk counter -> staging buffer parity
     uint32_t res_phase = 0;          // bit s = parity to wait for on res_bar[s]
     const int sw = (m & 7);          // swizzle phase of this thread's staging row
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const uint32_t tmem_empty_leader = kPair ? mapa_u32(tmem_empty, 0) : 0u;
+    for (int t = t_first; t < total_tiles; t += t_step) {
       const int nt = t % p.n_tiles;
-      const int pt = t / p.n_tiles;
+      const int pt = kPair ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
       const int b = pt / tiles_per_img;
       const int r = pt - b * tiles_per_img;
       const int h0 = (r / p.tiles_w) * p.bh;
       const int w0 = (r % p.tiles_w) * p.bw;
-      const bool valid = (h0 + hl < p.H) && (w0 + wl < p.W);
+      const bool in_batch = b < p.batch;   // false only for the padding tile of an odd pair count
+      const bool valid = in_batch && (h0 + hl < p.H) && (w0 + wl < p.W);
       const int ncol_base = nt * p.n_tile;
       // bias row of this tile (bias + per-image bias): every reader of the previous tile's row is past its last
       // chunk barrier, so it can be overwritten; the chunk-0 barrier below publishes it
       for (int i = et; i < p.n_tile; i += kEpiThreads) {
         float bv = 0.f;
         if (p.bias) bv += __ldg(p.bias + ncol_base + i);
-        if (p.bias_b) bv += __ldg(p.bias_b + static_cast<long long>(b) * p.n_total + ncol_base + i);
+        if (p.bias_b && in_batch) bv += __ldg(p.bias_b + static_cast<long long>(b) * p.n_total + ncol_base + i);
         bias_s[i] = bv;
       }
       if (p.res_staged && elected) {
@@ -268,6 +310,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * kAccStride;
+      if (p.dbg) {   // profiling experiment: no stores / statistics; dbg 2 still reads the accumulator
+        if (p.dbg == 2) {
+          uint32_t dd[32];
+          for (int c = 0; c < nchunks; ++c) {
+            tmem_ld_32x32(taddr + c * 32, dd);
+            tmem_ld_wait_dep(dd);
+            if (dd[0] == 0x7fc12345u && dd[1] == 0x12345u) bias_s[0] = 1.f;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
       uint32_t rr[32];
       tmem_ld_32x32(taddr, rr);
       tmem_ld_wait_dep(rr);
@@ -283,7 +346,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // every TMEM read of this accumulator has landed in registers: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) {
+            if (kPair) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
+            else mbar_arrive(&tmem_empty[acc]);
+          }
         }
         const float4* bp = reinterpret_cast<const float4*>(bias_s + c * 32);
 #pragma unroll
@@ -323,7 +389,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         h0, b);
           }
         }
-        if (p.stats) {
+        if (p.stats && in_batch) {
           // thread -> (bundle = et & 7, rows 8*(et>>3) .. +8): column sums of the staged chunk
           const int bun = et & 7;
           const uint8_t* sbase = stage_out + sbuf * kChunkBytes + (et >> 3) * 1024;
@@ -360,14 +426,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int wl = m - hl * p.bw;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const uint32_t tmem_empty_leader = kPair ? mapa_u32(tmem_empty, 0) : 0u;
+    for (int t = t_first; t < total_tiles; t += t_step) {
       const int nt = t % p.n_tiles;
-      const int pt = t / p.n_tiles;
+      const int pt = kPair ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
       const int b = pt / tiles_per_img;
       const int r = pt - b * tiles_per_img;
       const int h = (r / p.tiles_w) * p.bh + hl;
       const int w = (r % p.tiles_w) * p.bw + wl;
-      const bool valid = (h < p.H) && (w < p.W);
+      const bool valid = (b < p.batch) && (h < p.H) && (w < p.W);
       const long long pix = (static_cast<long long>(b) * p.H + h) * p.W + w;
 
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -388,7 +455,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 32; ++j)
             if (j < nvalid) v[j] += __ldg(p.bias + ncol0 + j);
         }
-        if (p.bias_b) {
+        if (p.bias_b && b < p.batch) {
           const float* bb = p.bias_b + static_cast<long long>(b) * p.n_total + ncol0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -449,7 +516,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        if (p.stats) {
+        if (p.stats && b < p.batch) {
           // GroupNorm partial statistics of what was just written: per 4-channel bundle, over this warp's
           // 32 pixels, then one fp64 atomic pair per bundle per warp.
           double* sp = p.stats + (static_cast<long long>(b) * (p.n_total >> 2) + (ncol0 >> 2)) * 2;
@@ -475,7 +542,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -485,9 +555,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();   // no CTA leaves while its peer may still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kPair) tmem_dealloc_2sm(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -634,7 +706,11 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   p.a_wrap1 = d->a_c / kBlockK;
   p.a_wrap2 = d->a2 ? d->a2_c / kBlockK : 1;
   p.b_batched = d->b_batched;
-  const int stage_bytes = kStageA + d->n_tile * 128;
+  // CTA pairs (cta_group::2): whenever the weight tile can be split in two swizzle-aligned halves
+  const long long pix_tiles = (long long)p.batch * p.tiles_h * p.tiles_w;
+  const bool pair = !d->b_batched && !d->no_cta_pairs && d->n_tile >= 32 && d->n_tile % 16 == 0 && pix_tiles >= 2;
+  const int b_box_rows = pair ? d->n_tile / 2 : d->n_tile;
+  const int stage_bytes = kStageA + b_box_rows * 128;
   // staged epilogue (TMA stores of 128x32 fp32 chunks): dense fp32 output whose tile columns are whole chunks
   p.staged = (!d->out_fp16 && d->ldc == d->n_total && d->col_off == 0 && d->n_tile % 32 == 0 &&
               d->n_total % d->n_tile == 0 && (!d->resid || d->ld_res == d->n_total) && !d->no_staged_epilogue)
@@ -659,6 +735,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   p.ld_res = d->ld_res;
   p.scale = d->scale;
   p.stats = d->stats;
+  p.dbg = d->debug_flags;
 
   CUtensorMap tmA, tmB, tmA2, tmB2, tmA8, tmB8, tmA82, tmB82, tmOut, tmRes;
   p.kchunks8_1 = 0;
@@ -676,7 +753,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     if (e) return e;
     uint64_t dimsb[3] = {(uint64_t)d->a8_c, (uint64_t)d->b_rows, (uint64_t)d->b_t};
     uint64_t strb[3] = {1, (uint64_t)d->a8_c, (uint64_t)d->a8_c * (uint64_t)d->b_rows};
-    uint32_t boxb[3] = {128, (uint32_t)d->n_tile, 1};
+    uint32_t boxb[3] = {128, (uint32_t)b_box_rows, 1};
     e = encode_map(&tmB8, d->b8, 3, dimsb, strb, boxb, 1);
     if (e) return e;
     if (d->a2) {
@@ -705,7 +782,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   {
     uint64_t dims[3] = {(uint64_t)k1, (uint64_t)d->b_rows, (uint64_t)d->b_t};
     uint64_t str[3] = {1, (uint64_t)d->b_stride_n, (uint64_t)d->b_stride_t};
-    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)d->n_tile, 1};
+    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)b_box_rows, 1};
     int e = encode_map(&tmB, d->b, 3, dims, str, box);
     if (e) return e;
   }
@@ -717,7 +794,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     if (e) return e;
     uint64_t dimsb[3] = {(uint64_t)k2, (uint64_t)d->b2_rows, 1};
     uint64_t strb[3] = {1, (uint64_t)d->b2_stride_n, (uint64_t)d->b2_stride_n * (uint64_t)d->b2_rows};
-    uint32_t boxb[3] = {(uint32_t)kBlockK, (uint32_t)d->n_tile, 1};
+    uint32_t boxb[3] = {(uint32_t)kBlockK, (uint32_t)b_box_rows, 1};
     e = encode_map(&tmB2, d->b2, 3, dimsb, strb, boxb);
     if (e) return e;
   } else {
@@ -753,17 +830,45 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   static bool attr_set = false;
   if (!attr_set) {
     int e = check_cuda(
-        cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+        cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
         "cudaFuncSetAttribute(conv_gemm_kernel)");
+    if (e) return e;
+    e = check_cuda(
+        cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+        "cudaFuncSetAttribute(conv_gemm_kernel<pair>)");
     if (e) return e;
     attr_set = true;
   }
-  const long long total_tiles = (long long)p.batch * p.tiles_h * p.tiles_w * p.n_tiles;
-  int grid = num_sms();
-  if (d->max_ctas > 0 && d->max_ctas < grid) grid = d->max_ctas;
-  if (total_tiles < grid) grid = (int)total_tiles;
-  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmA2, tmB2, tmA8, tmB8, tmA82, tmB82, tmOut,
-                                                           tmRes, p);
+  if (!pair) {
+    const long long total_tiles = pix_tiles * p.n_tiles;
+    int grid = num_sms();
+    if (d->max_ctas > 0 && d->max_ctas < grid) grid = d->max_ctas;
+    if (total_tiles < grid) grid = (int)total_tiles;
+    conv_gemm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmA2, tmB2, tmA8, tmB8, tmA82, tmB82,
+                                                                    tmOut, tmRes, p);
+  } else {
+    const long long work = ((pix_tiles + 1) / 2) * p.n_tiles;
+    int clusters = num_sms() / 2;
+    if (d->max_ctas > 0 && d->max_ctas / 2 < clusters) clusters = d->max_ctas / 2 > 0 ? d->max_ctas / 2 : 1;
+    if (work < clusters) clusters = (int)work;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int e = check_cuda(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, tmA, tmB, tmA2, tmB2, tmA8, tmB8, tmA82, tmB82,
+                                          tmOut, tmRes, p),
+                       "cudaLaunchKernelEx(conv_gemm_kernel<pair>)");
+    if (e) return e;
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   BUDDY_CHECK_LAUNCH("conv_gemm_kernel");
   return 0;

@@ -105,6 +105,11 @@ typedef struct buddy_gemm_desc {
   /* 1 = force the direct (register -> global) epilogue even where the staged TMA-store epilogue applies
    * (dense fp32 output, n_tile %% 32 == 0); testing / A-B timing only. */
   int32_t no_staged_epilogue;
+  /* 1 = never pair CTAs (tcgen05 cta_group::2 over a 2-CTA cluster, the default whenever n_tile >= 32 and B is not
+   * per-image); testing / A-B timing only. */
+  int32_t no_cta_pairs;
+  /* profiling experiments only (results are NOT written): 1 = skip the epilogue body, 2 = only read the accumulator */
+  int32_t debug_flags;
 } buddy_gemm_desc;
 
 int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream);

@@ -13,9 +13,9 @@ from buddy_b200 import ops
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 dev = "cuda"
-SHAPES = [  # (H, W, Cin, Cout, mode)
-    (256, 528, 256, 256, "c8"), (256, 528, 128, 128, "c8"), (128, 264, 256, 256, "c8"), (256, 528, 384, 128, "c8"),
-    (256, 528, 256, 256, "x1"), (256, 528, 128, 128, "x1"), (256, 528, 256, 256, "x3"),
+SHAPES = [  # (H, W, Cin, Cout, mode) — the mixed policy's dominant launches first
+    (256, 528, 256, 256, "x1"), (256, 528, 384, 128, "x1"), (128, 264, 256, 256, "c8"), (256, 528, 128, 128, "c8"),
+    (256, 528, 256, 256, "c8"), (128, 264, 512, 256, "x1"), (256, 528, 256, 256, "x3"),
 ]
 
 
@@ -38,6 +38,10 @@ for (H, W, ci, co, mode) in SHAPES:
     bias = torch.zeros(co, device=dev)
     if os.environ.get("NOSTATS"):
         stats = None
+    if os.environ.get("DBG"):
+        kw["debug_flags"] = int(os.environ["DBG"])
+    if os.environ.get("NOPAIR"):
+        kw["no_pairs"] = True
     if os.environ.get("DIRECT"):
         kw["direct_epilogue"] = True
     run = lambda: ops.conv_gemm(a, w, out, taps=9, n_total=co, passes=p, bias=bias, stats=stats, **kw)

@@ -187,3 +187,40 @@ def test_staged_epilogue_matches_direct(B, H, W, C, N, with_res):
     assert rel(sts[1], sts[0]) < 1e-6
     ref = (ref_conv(a, w, 9) + bias + bias_b[:, None, None, :] + (resid if with_res else 0.0)) * 0.5
     assert rel(outs[1], ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,C,N,c8", [(2, 16, 24, 64, 128, False), (3, 19, 37, 64, 256, True),
+                                          (1, 8, 8, 128, 64, False), (1, 40, 50, 128, 384, True),
+                                          (5, 8, 16, 64, 32, False), (1, 256, 528, 64, 128, True)])
+def test_cta_pairs_match_single_cta(B, H, W, C, N, c8):
+    """cta_group::2 (two CTAs share one 256-row tile pair, each loads half the weight tile) against the single-CTA
+    path: same products in the same order -> identical output; odd pixel-tile counts exercise the padding tile."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(8)
+    a = torch.randn(B, H, W, C, device="cuda", generator=g).half()
+    w = (torch.randn(9, N, C, device="cuda", generator=g) * 0.05).half()
+    a2 = torch.randn(B, H, W, 64, device="cuda", generator=g).half()
+    w2 = (torch.randn(N, 64, device="cuda", generator=g) * 0.1).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    bias_b = torch.randn(B, N, device="cuda", generator=g)
+    kw = {}
+    if c8:
+        e4 = lambda t: t.clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)
+        kw = dict(a8=e4(torch.randn(B, H, W, 2 * C, device="cuda", generator=g)),
+                  w8=e4(torch.randn(9, N, 2 * C, device="cuda", generator=g)),
+                  a8_2=e4(torch.randn(B, H, W, 128, device="cuda", generator=g)),
+                  w8_2=e4(torch.randn(N, 128, device="cuda", generator=g)))
+    outs, sts = [], []
+    for no_pairs in (True, False):
+        out = torch.full((B, H, W, N), float("nan"), device="cuda")
+        stats = torch.zeros(B, N // 4, 2, device="cuda", dtype=torch.float64)
+        for _ in range(2):
+            stats.zero_()
+            ops.conv_gemm(a, w, out, taps=9, n_total=N, a2=a2, w2=w2, bias=bias, bias_b=bias_b, scale=0.5,
+                          stats=stats, no_pairs=no_pairs, **kw)
+        torch.cuda.synchronize()
+        outs.append(out)
+        sts.append(stats)
+    assert not torch.isnan(outs[1]).any()
+    assert torch.equal(outs[0], outs[1])
+    assert rel(sts[1], sts[0]) < 1e-9
