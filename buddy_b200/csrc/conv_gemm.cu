@@ -26,8 +26,8 @@ namespace buddy {
 
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;            // fp16 elements per k-block = 128 bytes = one swizzle row
-constexpr int kStageA = kTileM * 128;  // bytes
-constexpr int kMaxStages = 8;
+constexpr int kMaxStagesA = 4;         // A ring (activation patches)
+constexpr int kMaxStagesB = 8;         // B ring (weight tiles)
 constexpr int kAccStride = 256;        // TMEM columns per accumulator stage
 constexpr int kThreads = 192;
 
@@ -38,7 +38,11 @@ struct GemmParams {
   int taps, kchunks1, kchunks2, b_batched;
   int a_wrap1, a_wrap2;  // A-side channel chunk = k-chunk % a_wrap (split-precision operands re-read the hi half)
   int kchunks8_1, kchunks8_2;  // fp8 correction phases (128-byte chunks per tap / for the skip conv); 0 = none
-  int stages;
+  // A ring: one stage = the activation patch(es) of ONE 64-channel chunk.  3x3 convs (halo = 1): three column-
+  // shifted patches of (bh + 2) rows x bw = 8 pixels; the nine taps are MMA-descriptor offsets into them (row shift
+  // = whole 1024-byte swizzle atoms), so a chunk is read from L2 3.4x instead of 9x.  B ring: one weight tile per
+  // (chunk, tap).
+  int halo, patch_bytes, stages_a, stages_b;
   float* out32;
   __half* out16;
   long long ldc;
@@ -75,14 +79,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader CTA of the pair
   const int b_rows = kPair ? (p.n_tile >> 1) : p.n_tile;   // weight-tile rows this CTA loads
-  const int stage_bytes = kStageA + b_rows * 128;
-  // [pipeline stages][2 staged epilogue chunks (if staged)][bias row 1 KB (if staged)][barriers]
-  uint8_t* stage_out = smem + p.stages * stage_bytes;
+  const int a_stage_bytes = (p.halo ? 3 : 1) * p.patch_bytes;
+  const int b_stage_bytes = b_rows * 128;
+  // [A ring][B ring][2 staged epilogue chunks (if staged)][bias row 1 KB (if staged)][barriers]
+  uint8_t* smem_b = smem + p.stages_a * a_stage_bytes;
+  uint8_t* stage_out = smem_b + p.stages_b * b_stage_bytes;
   float* bias_s = reinterpret_cast<float*>(stage_out + 2 * kChunkBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + (p.staged ? 2 * kChunkBytes + 1024 : 0));
-  uint64_t* full_bar = bars;                     // [kMaxStages]
-  uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
-  uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
+  uint64_t* a_full = bars;                       // [kMaxStagesA]
+  uint64_t* a_empty = a_full + kMaxStagesA;      // [kMaxStagesA]
+  uint64_t* b_full = a_empty + kMaxStagesA;      // [kMaxStagesB]
+  uint64_t* b_empty = b_full + kMaxStagesB;      // [kMaxStagesB]
+  uint64_t* tmem_full = b_empty + kMaxStagesB;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint64_t* res_bar = tmem_empty + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
@@ -97,9 +105,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tma_prefetch_desc(&tmA2);
       tma_prefetch_desc(&tmB2);
     }
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], kPair ? 2 : 1);   // pair: one expect_tx arrival per CTA, on the leader's barrier
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < p.stages_a; ++s) {
+      mbar_init(&a_full[s], kPair ? 2 : 1);   // pair: one expect_tx arrival per CTA, on the leader's barrier
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < p.stages_b; ++s) {
+      mbar_init(&b_full[s], kPair ? 2 : 1);
+      mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -134,17 +146,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int total_tiles = (kPair ? ((pix_tiles + 1) >> 1) : pix_tiles) * p.n_tiles;
   const int t_first = kPair ? (blockIdx.x >> 1) : blockIdx.x;
   const int t_step = kPair ? (gridDim.x >> 1) : gridDim.x;
-  // k-block order: [fp8 correction: conv taps | skip conv] then [fp16: conv taps | skip conv]
-  const int kb8_1 = p.taps * p.kchunks8_1;
-  const int kb8 = kb8_1 + p.kchunks8_2;
-  const int kb_phase1 = p.taps * p.kchunks1;
-  const int num_kb = kb8 + kb_phase1 + p.kchunks2;
+  // contraction order: phases [fp8 conv | fp8 skip conv | fp16 conv | fp16 skip conv]; inside a phase: channel chunk
+  // outer (one A stage each), tap inner (one B stage each)
 
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+    // The whole warp runs the loop (warp-uniform control flow and addresses stay on the uniform datapath); only the
+    // TMA / expect_tx instructions themselves are issued by one elected lane.
+    if (!(p.dbg & 4)) {   // dbg 4 (profiling): no loads at all, the MMA loop runs on stale smem
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       for (int t = t_first; t < total_tiles; t += t_step) {
         const int nt = t % p.n_tiles;
         const int pt = kPair ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
@@ -153,110 +164,156 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int h0 = (r / p.tiles_w) * p.bh;
         const int w0 = (r % p.tiles_w) * p.bw;
         const int brow = nt * p.n_tile + static_cast<int>(rank) * b_rows;   // first weight row this CTA loads
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * stage_bytes;
-          uint8_t* sb = sa + kStageA;
-          // select the operand pair and coordinates of this k-block
-          const CUtensorMap* ma;
-          const CUtensorMap* mb;
-          int ac, bc, dy = 0, dx = 0, b3 = 0;
-          if (kb < kb8) {
-            if (kb < kb8_1) {
-              const int tap = kb / p.kchunks8_1;
-              const int kc = kb - tap * p.kchunks8_1;
-              if (p.taps == 9) {
-                dy = tap / 3 - 1;
-                dx = tap % 3 - 1;
+        for (int ph = 0; ph < 4; ++ph) {
+          const int nch = ph == 0 ? p.kchunks8_1 : (ph == 1 ? p.kchunks8_2 : (ph == 2 ? p.kchunks1 : p.kchunks2));
+          if (nch == 0) continue;
+          const CUtensorMap* ma = ph == 0 ? &tmA8 : (ph == 1 ? &tmA82 : (ph == 2 ? &tmA : &tmA2));
+          const CUtensorMap* mb = ph == 0 ? &tmB8 : (ph == 1 ? &tmB82 : (ph == 2 ? &tmB : &tmB2));
+          const int ptaps = (ph & 1) ? 1 : p.taps;
+          const int unit = ph < 2 ? 128 : kBlockK;                       // coordinate units per chunk (128 B)
+          const int wrap = ph == 2 ? p.a_wrap1 : (ph == 3 ? p.a_wrap2 : 0x7fffffff);
+          const int nload = ptaps == 9 ? 3 : 1;
+          for (int kc = 0; kc < nch; ++kc) {
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            uint8_t* abase = smem + sa * a_stage_bytes;
+            const int ac = (kc % wrap) * unit;
+            if (elect_one()) {
+              if (kPair) {
+                const uint32_t fb = mapa_u32(&a_full[sa], 0);   // the leader's barrier collects both CTAs' bytes
+                mbar_expect_tx_cluster(fb, nload * p.patch_bytes);
+                for (int j = 0; j < nload; ++j)
+                  tma_load_4d_2sm(ma, abase + j * p.patch_bytes, fb, ac, w0 + (nload == 3 ? j - 1 : 0), h0 - p.halo,
+                                  b);
+              } else {
+                mbar_expect_tx(&a_full[sa], nload * p.patch_bytes);
+                for (int j = 0; j < nload; ++j)
+                  tma_load_4d(ma, abase + j * p.patch_bytes, &a_full[sa], ac, w0 + (nload == 3 ? j - 1 : 0),
+                              h0 - p.halo, b);
               }
-              ma = &tmA8; mb = &tmB8; ac = kc * 128; bc = kc * 128; b3 = tap;
-            } else {
-              const int kc = kb - kb8_1;
-              ma = &tmA82; mb = &tmB82; ac = kc * 128; bc = kc * 128;
             }
-          } else if (kb - kb8 < kb_phase1) {
-            const int kk = kb - kb8;
-            const int tap = kk / p.kchunks1;
-            const int kc = kk - tap * p.kchunks1;
-            if (p.taps == 9) {
-              dy = tap / 3 - 1;
-              dx = tap % 3 - 1;
+            __syncwarp();
+            if (++sa == p.stages_a) {
+              sa = 0;
+              pa ^= 1;
             }
-            ma = &tmA; mb = &tmB; ac = (kc % p.a_wrap1) * kBlockK; bc = kc * kBlockK; b3 = p.b_batched ? b : tap;
-          } else {
-            const int kc = kb - kb8 - kb_phase1;
-            ma = &tmA2; mb = &tmB2; ac = (kc % p.a_wrap2) * kBlockK; bc = kc * kBlockK;
-          }
-          if (kPair) {
-            const uint32_t fb = mapa_u32(&full_bar[stage], 0);   // the leader's barrier collects both CTAs' bytes
-            mbar_expect_tx_cluster(fb, stage_bytes);
-            tma_load_4d_2sm(ma, sa, fb, ac, w0 + dx, h0 + dy, b);
-            tma_load_3d_2sm(mb, sb, fb, bc, brow, b3);
-          } else {
-            mbar_expect_tx(&full_bar[stage], stage_bytes);
-            tma_load_4d(ma, sa, &full_bar[stage], ac, w0 + dx, h0 + dy, b);
-            tma_load_3d(mb, sb, &full_bar[stage], bc, brow, b3);
-          }
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
+            for (int tap = 0; tap < ptaps; ++tap) {
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              uint8_t* bbase = smem_b + sb * b_stage_bytes;
+              const int b3 = (ph & 1) ? 0 : (p.b_batched ? b : tap);
+              if (elect_one()) {
+                if (kPair) {
+                  const uint32_t fb = mapa_u32(&b_full[sb], 0);
+                  mbar_expect_tx_cluster(fb, b_stage_bytes);
+                  tma_load_3d_2sm(mb, bbase, fb, kc * unit, brow, b3);
+                } else {
+                  mbar_expect_tx(&b_full[sb], b_stage_bytes);
+                  tma_load_3d(mb, bbase, &b_full[sb], kc * unit, brow, b3);
+                }
+              }
+              __syncwarp();
+              if (++sb == p.stages_b) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (single thread; pair: leader CTA only)
-    if (lane == 0 && rank == 0) {
+    // ================================================================ MMA issuer (pair: leader CTA only)
+    // All 32 lanes run the loop so that barrier indices, descriptors and addresses are warp-uniform (uniform
+    // registers feed tcgen05.mma directly — issued from a divergent single-lane branch every descriptor needs a
+    // vector->uniform move and the issue loop, not the tensor pipe, bounds N = 128 layers); the MMAs and commits of a
+    // k-block are issued by one elected lane.
+    if (rank == 0) {
       const uint32_t idesc = make_idesc_f16(kPair ? 2 * kTileM : kTileM, p.n_tile);
       const uint32_t idesc8 = make_idesc_e4m3(kPair ? 2 * kTileM : kTileM, p.n_tile);
-      int stage = 0;
-      uint32_t phase = 0;
+      const int row_pitch = p.bw * 128;   // bytes between patch rows (halo launches: bw = 8 -> one swizzle atom)
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = t_first; t < total_tiles; t += t_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint64_t da = make_sw128_kmajor_desc(sa);
-          const uint64_t db = make_sw128_kmajor_desc(sa + kStageA);
-          // each MMA consumes 32 bytes of K per row (16 fp16 or 32 e4m3): +2 in (addr >> 4) units
-          if (kb < kb8) {
+        bool fresh = true;       // no MMA issued into this accumulator yet
+        bool unscaled8 = false;  // fp8 corrections accumulated (x 2^14) and not yet folded
+        for (int ph = 0; ph < 4; ++ph) {
+          const int nch = ph == 0 ? p.kchunks8_1 : (ph == 1 ? p.kchunks8_2 : (ph == 2 ? p.kchunks1 : p.kchunks2));
+          if (nch == 0) continue;
+          const int ptaps = (ph & 1) ? 1 : p.taps;
+          const bool f8 = ph < 2;
+          for (int kc = 0; kc < nch; ++kc) {
+            if (!(p.dbg & 4)) mbar_wait(&a_full[sa], pa);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + sa * a_stage_bytes);
+            for (int tap = 0; tap < ptaps; ++tap) {
+              if (!(p.dbg & 4)) mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              // tap (dy, dx): patch dx+1, shifted down by dy+1 rows; a 1x1 phase of a 3x3 launch reads the centre rows
+              int a_off = p.halo ? row_pitch : 0;
+              if (ptaps == 9) a_off = (tap % 3) * p.patch_bytes + (tap / 3) * row_pitch;
+              const uint64_t da = make_sw128_kmajor_desc(a_addr + a_off);
+              const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + sb * b_stage_bytes));
+              const bool last_tap = (tap == ptaps - 1);
+              // each MMA consumes 32 bytes of K per row (16 fp16 or 32 e4m3): +2 in (addr >> 4) units
+              if (elect_one()) {
+              if (f8) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (kPair) umma_f8_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc8, (kb > 0 || k > 0) ? 1u : 0u);
-              else umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc8, (kb > 0 || k > 0) ? 1u : 0u);
-            }
-          } else if (kb == kb8 && kb8 > 0) {
-            // first fp16 block after the corrections: fold their 2^14 scale away (D = A*B + D * 2^-14)
-            if (kPair) umma_f16_scale_d14_2sm(d_tmem, da, db, idesc);
-            else umma_f16_scale_d14(d_tmem, da, db, idesc);
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t accu = (fresh && k == 0) ? 0u : 1u;
+                  if (kPair) umma_f8_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc8, accu);
+                  else umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc8, accu);
+                }
+              } else if (unscaled8) {
+                // first fp16 block after the corrections: fold their 2^14 scale away (D = A*B + D * 2^-14)
+                if (kPair) umma_f16_scale_d14_2sm(d_tmem, da, db, idesc);
+                else umma_f16_scale_d14(d_tmem, da, db, idesc);
 #pragma unroll
-            for (int k = 1; k < 4; ++k) {
-              if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
-              else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
-            }
-          } else {
+                for (int k = 1; k < 4; ++k) {
+                  if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+                  else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+                }
+              } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t accu = (fresh && k == 0) ? 0u : 1u;
+                  if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
+                  else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
+                }
+              }
+              // frees the weight stage (in both CTAs of a pair) once the MMAs above have read it
+              if (kPair) umma_commit_2sm(&b_empty[sb]);
+              else umma_commit(&b_empty[sb]);
+              // all taps of this chunk issued: the patch stage is free once they complete
+              if (last_tap) {
+                if (kPair) umma_commit_2sm(&a_empty[sa]);
+                else umma_commit(&a_empty[sa]);
+              }
+              }  // elect_one
+              __syncwarp();
+              if (f8) unscaled8 = true;
+              else unscaled8 = false;
+              fresh = false;
+              if (++sb == p.stages_b) {
+                sb = 0;
+                pb ^= 1;
+              }
             }
-          }
-          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
-          if (kPair) umma_commit_2sm(&empty_bar[stage]);
-          else umma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
+            if (++sa == p.stages_a) {
+              sa = 0;
+              pa ^= 1;
+            }
           }
         }
         // accumulator complete -> epilogue (of both CTAs of a pair)
-        if (kPair) umma_commit_2sm(&tmem_full[acc]);
-        else umma_commit(&tmem_full[acc]);
+        if (elect_one()) {
+          if (kPair) umma_commit_2sm(&tmem_full[acc]);
+          else umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -310,8 +367,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * kAccStride;
-      if (p.dbg) {   // profiling experiment: no stores / statistics; dbg 2 still reads the accumulator
-        if (p.dbg == 2) {
+      if (p.dbg & 3) {   // profiling experiment: no stores / statistics; dbg 2 still reads the accumulator
+        if (p.dbg & 2) {
           uint32_t dd[32];
           for (int c = 0; c < nchunks; ++c) {
             tmem_ld_32x32(taddr + c * 32, dd);
@@ -688,7 +745,17 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   p.batch = d->batch;
   p.H = d->H;
   p.W = d->W;
-  choose_patch(d->H, d->W, &p.bh, &p.bw);
+  // 3x3: fixed 16 x 8 pixel tiles — patch rows of 8 pixels are whole 1024-byte swizzle atoms, so a tap's row shift is
+  // an aligned descriptor offset into the (bh + 2)-row patch; 1x1 / GEMM: the patch shape that wastes least
+  p.halo = d->taps == 9 ? 1 : 0;
+  if (p.halo) {
+    p.bh = 16;
+    p.bw = 8;
+  } else {
+    choose_patch(d->H, d->W, &p.bh, &p.bw);
+  }
+  const int patch_rows = p.bh + 2 * p.halo;
+  p.patch_bytes = patch_rows * p.bw * 128;
   p.tiles_h = (d->H + p.bh - 1) / p.bh;
   p.tiles_w = (d->W + p.bw - 1) / p.bw;
   p.n_tile = d->n_tile;
@@ -710,7 +777,8 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   const long long pix_tiles = (long long)p.batch * p.tiles_h * p.tiles_w;
   const bool pair = !d->b_batched && !d->no_cta_pairs && d->n_tile >= 32 && d->n_tile % 16 == 0 && pix_tiles >= 2;
   const int b_box_rows = pair ? d->n_tile / 2 : d->n_tile;
-  const int stage_bytes = kStageA + b_box_rows * 128;
+  const int a_stage_bytes = (p.halo ? 3 : 1) * p.patch_bytes;
+  const int b_stage_bytes = b_box_rows * 128;
   // staged epilogue (TMA stores of 128x32 fp32 chunks): dense fp32 output whose tile columns are whole chunks
   p.staged = (!d->out_fp16 && d->ldc == d->n_total && d->col_off == 0 && d->n_tile % 32 == 0 &&
               d->n_total % d->n_tile == 0 && (!d->resid || d->ld_res == d->n_total) && !d->no_staged_epilogue)
@@ -718,13 +786,20 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
                  : 0;
   p.res_staged = (p.staged && d->resid) ? 1 : 0;
   const int epi_bytes = p.staged ? 2 * kChunkBytes + 1024 : 0;
-  int stages = (227 * 1024 - 1536 - epi_bytes) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) {
-    set_last_error("buddy_conv_gemm: not enough shared memory for 2 stages");
+  const int ring_bytes = 227 * 1024 - 1536 - epi_bytes;
+  if (p.halo) {
+    // a patch stage lasts nine weight stages: two of them, the rest of the shared memory goes to the weight ring
+    p.stages_a = 2;
+    p.stages_b = (ring_bytes - 2 * a_stage_bytes) / b_stage_bytes;
+  } else {
+    p.stages_a = p.stages_b = ring_bytes / (a_stage_bytes + b_stage_bytes);
+  }
+  if (p.stages_a > kMaxStagesA) p.stages_a = kMaxStagesA;
+  if (p.stages_b > kMaxStagesB) p.stages_b = kMaxStagesB;
+  if (p.stages_a < 2 || p.stages_b < 2) {
+    set_last_error("buddy_conv_gemm: not enough shared memory for 2 pipeline stages (n_tile %d)", d->n_tile);
     return BUDDY_ERR_UNSUPPORTED;
   }
-  p.stages = stages;
   p.out32 = d->out_fp16 ? nullptr : static_cast<float*>(d->out);
   p.out16 = d->out_fp16 ? static_cast<__half*>(d->out) : nullptr;
   p.ldc = d->ldc;
@@ -748,7 +823,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     p.kchunks8_1 = d->a8_c / 128;
     uint64_t dims[4] = {(uint64_t)d->a8_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
     uint64_t str[4] = {1, (uint64_t)d->a8_stride_w, (uint64_t)d->a8_stride_h, (uint64_t)d->a8_stride_b};
-    uint32_t box[4] = {128, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    uint32_t box[4] = {128, (uint32_t)p.bw, (uint32_t)patch_rows, 1};
     int e = encode_map(&tmA8, d->a8, 4, dims, str, box, 1);
     if (e) return e;
     uint64_t dimsb[3] = {(uint64_t)d->a8_c, (uint64_t)d->b_rows, (uint64_t)d->b_t};
@@ -775,7 +850,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   {
     uint64_t dims[4] = {(uint64_t)d->a_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
     uint64_t str[4] = {1, (uint64_t)d->a_stride_w, (uint64_t)d->a_stride_h, (uint64_t)d->a_stride_b};
-    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bw, (uint32_t)patch_rows, 1};
     int e = encode_map(&tmA, d->a, 4, dims, str, box);
     if (e) return e;
   }
@@ -789,7 +864,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   if (d->a2) {
     uint64_t dims[4] = {(uint64_t)d->a2_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
     uint64_t str[4] = {1, (uint64_t)d->a2_stride_w, (uint64_t)d->a2_stride_h, (uint64_t)d->a2_stride_b};
-    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bw, (uint32_t)patch_rows, 1};
     int e = encode_map(&tmA2, d->a2, 4, dims, str, box);
     if (e) return e;
     uint64_t dimsb[3] = {(uint64_t)k2, (uint64_t)d->b2_rows, 1};
@@ -826,7 +901,8 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     tmRes = tmA;
   }
 
-  const size_t smem_bytes = (size_t)stages * stage_bytes + epi_bytes + 256 /*barriers*/;
+  const size_t smem_bytes = (size_t)p.stages_a * a_stage_bytes + (size_t)p.stages_b * b_stage_bytes + epi_bytes +
+                            256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
     int e = check_cuda(

@@ -8,14 +8,15 @@ namespace buddy { void set_last_error(const char*, ...) {} int check_cuda(cudaEr
 using namespace buddy;
 
 template <bool kPair, bool kF8>
-__global__ void __launch_bounds__(128, 1) probe(int N, int iters, long long* out) {
+__global__ void __launch_bounds__(128, 1) probe(int N, int iters, long long* out, int mode) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[8];
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = kPair ? cluster_ctarank() : 0;
   for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&bar2[i], 1); fence_barrier_init(); }
   if (warp == 0) { if (kPair) { tmem_alloc_2sm(&slot, 512); tmem_relinquish_2sm(); } else { tmem_alloc(&slot, 512); tmem_relinquish(); } }
   fence_proxy_async();
   tc_fence_before();
@@ -28,12 +29,17 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int iters, long long* out
     const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem));
     const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem) + 16384);
     const long long t0 = clock64();
+    int st = 0; uint32_t ph = 0;
     for (int i = 0; i < iters; ++i) {
+      if (mode & 2) tc_fence_after();
+      if ((mode & 4) && i >= 8) { mbar_wait(&bar2[st], ph ^ 1); }   // wait for the commit of 8 groups ago (always done)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (kPair) { if (kF8) umma_f8_2sm(d, da + 2 * k, db + 2 * k, idesc, 1u); else umma_f16_2sm(d, da + 2 * k, db + 2 * k, idesc, 1u); }
         else { if (kF8) umma_f8(d, da + 2 * k, db + 2 * k, idesc, 1u); else umma_f16(d, da + 2 * k, db + 2 * k, idesc, 1u); }
       }
+      if (mode & 1) { if (kPair) umma_commit_2sm(&bar2[st]); else umma_commit(&bar2[st]); }
+      if (++st == 8) { st = 0; ph ^= 1; }
     }
     if (kPair) umma_commit_2sm(&bar); else umma_commit(&bar);
     mbar_wait(&bar, 0);
@@ -49,7 +55,7 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int iters, long long* out
 }
 
 template <bool kPair, bool kF8>
-void run(const char* name, int N, int grid) {
+void run(const char* name, int N, int grid, int mode = 0) {
   long long* out;
   cudaMalloc(&out, 8);
   const int iters = 4000;
@@ -63,7 +69,7 @@ void run(const char* name, int N, int grid) {
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k, N, iters, out);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, N, iters, out, mode);
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -71,7 +77,7 @@ void run(const char* name, int N, int grid) {
     if (rep == 1) {
       const double per = double(cyc) / (iters * 4.0);
       const double flop = 2.0 * (kPair ? 256 : 128) * N * (kF8 ? 32 : 16) * iters * 4.0 * (kPair ? grid / 2 : grid);
-      printf("%-28s N=%3d grid %3d: %7.1f cycles/MMA, %.3f ms, %.0f TFLOP/s (%s) err=%d\n", name, N, grid, per, ms,
+      printf("mode %d %-24s N=%3d grid %3d: %7.1f cycles/MMA, %.3f ms, %.0f TFLOP/s (%s) err=%d\n", mode, name, N, grid, per, ms,
              flop / (ms * 1e-3) / 1e12, kF8 ? "fp8" : "fp16", (int)e);
     }
   }
@@ -79,13 +85,11 @@ void run(const char* name, int N, int grid) {
 }
 
 int main() {
-  for (int grid : {148, 2}) {
-    run<false, false>("cta_group::1 f16 M128", 256, grid);
-    run<false, false>("cta_group::1 f16 M128", 128, grid);
-    run<false, true>("cta_group::1 f8  M128", 256, grid);
-    run<true, false>("cta_group::2 f16 M256", 256, grid);
-    run<true, false>("cta_group::2 f16 M256", 128, grid);
-    run<true, true>("cta_group::2 f8  M256", 256, grid);
+  for (int mode : {0, 1, 3, 5, 7}) {
+    run<false, false>("cta_group::1 f16 M128", 256, 148, mode);
+    run<false, false>("cta_group::1 f16 M128", 128, 148, mode);
+    run<true, false>("cta_group::2 f16 M256", 128, 148, mode);
+    run<true, true>("cta_group::2 f8  M256", 128, 148, mode);
   }
   return 0;
 }
