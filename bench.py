@@ -3,7 +3,7 @@
 
 Workload (BASELINE.json configs[1]): batch = 32 synthetic utterances of 4.096 s @ 16 kHz per GPU, informed DPS
 (EulerHeunSamplerDPS + RIROperator, conf/tester/informed_dereverberation_DPS.yaml), T = 35, order 2, NCSN++ with
-random (non-degenerate) weights.  One bench "step" = one Euler-Heun sampler step over the whole batch = 2 DPS
+random (non-degenerate) weights, default operand precision ("mixed", DESIGN.md §4: <= 1e-3 vs the fp32 reference).  One bench "step" = one Euler-Heun sampler step over the whole batch = 2 DPS
 network evaluations (forward + data-gradient) per utterance.  value = utterance-steps per second, whole job.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -326,9 +326,32 @@ def run_ours(args):
     calls, conv_ms, conv_flops = summ.get("conv_gemm", (0, 0.0, 0.0))
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None
     eng = net.engine()
-    np_ = 2.0 if eng.c8 else float(eng.np)     # fp16-pass equivalents issued per algorithmic product
-    dtype_s = ("f16 products + 2 e4m3 correction passes (2 fp16-pass equivalents)" if eng.c8
-               else f"f16 operands x{eng.np} passes") + " / f32 accumulate+activations"
+    np_ = (kt.issued_flops / conv_flops) if conv_flops else 1.0   # fp16-pass equivalents issued per algorithmic product
+    if eng.mixed:
+        dtype_s = (f"f16 tensor-core operands, f32 accumulate: {len(eng.x1_convs)} largest convolutions single-pass, "
+                   "the rest + 2 e4m3 correction passes; f32 activations / statistics / sampler")
+    elif eng.c8:
+        dtype_s = "f16 products + 2 e4m3 correction passes (2 fp16-pass equivalents) / f32 accumulate+activations"
+    else:
+        dtype_s = f"f16 operands x{eng.np} passes / f32 accumulate+activations"
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", "conv_gemm_r01_final_ncu_full.txt")
+    if os.path.exists(tp) and B >= 16 and args.micro_batch == 16 and not blind:
+        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (256->256 3x3 @256x528, 16 utterances,
+        # single pass) from the committed `ncu --set full` capture of this kernel
+        try:
+            rd = wr = None
+            for ln in open(tp):
+                if ln.startswith("dram__bytes_read.sum"):
+                    rd = float(ln.split(":")[1].split("|")[0])
+                if ln.startswith("dram__bytes_write.sum"):
+                    wr = float(ln.split(":")[1].split("|")[0])
+            traffic = (rd + wr) * 1e9
+            traffic_note = ("DRAM bytes per launch of the dominant shape (conv 256->256 3x3 @256x528, 16 utterances): "
+                            "ncu capture in profiles/conv_gemm_r01_final_ncu_full.txt; algorithmic bytes of that launch "
+                            "= fp16 input 1.107e9 + fp32 output 2.215e9 + weights 1.2e6 = 3.323e9")
+        except Exception:
+            traffic = None
     total_ms_ops = sum(v[1] for v in summ.values())
     line = {
         "metric": "sampler_steps_per_sec", "value": value, "unit": "utterance-steps/s", "n_gpus": world,
@@ -344,10 +367,12 @@ def run_ours(args):
         "clocks": clk.result(),
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv, all conv/NIN/attention "
                      "launches of the timed region)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": (achieved / peak_tf) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
+                     "traffic_note": traffic_note, "peak_source": peak_src,
                      "achieved_definition": "algorithmic FLOPs (2*M*N*K of the convolution, split-precision passes "
                                             "NOT counted) / summed CUDA-event duration of the launches",
-                     "issued_mma_tflops": (achieved * np_) if achieved else None, "launches": calls,
+                     "issued_mma_tflops": (achieved * np_) if achieved else None,
+                     "fp16_pass_equivalents_per_product": np_, "launches": calls,
                      "share_of_step": conv_ms / total_ms_ops if total_ms_ops else None},
         "kernel_time_share": {k: round(v[1] / total_ms_ops, 4) for k, v in
                               sorted(summ.items(), key=lambda kv: -kv[1][1])[:6]},

@@ -172,23 +172,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int ptaps = (ph & 1) ? 1 : p.taps;
           const int unit = ph < 2 ? 128 : kBlockK;                       // coordinate units per chunk (128 B)
           const int wrap = ph == 2 ? p.a_wrap1 : (ph == 3 ? p.a_wrap2 : 0x7fffffff);
-          const int nload = ptaps == 9 ? 3 : 1;
-          for (int kc = 0; kc < nch; ++kc) {
+          // A stage = 3 patches: the dx = -1/0/+1 patches of ONE chunk (3x3 phase), or the centre patches of up to
+          // THREE consecutive chunks (1x1 phase of a 3x3 launch, so the short skip-conv phase keeps the ring busy)
+          const int group = (p.halo && ptaps == 1) ? 3 : 1;
+          for (int kc = 0; kc < nch; kc += group) {
+            const int g = min(group, nch - kc);
+            const int nload = ptaps == 9 ? 3 : g;
             mbar_wait(&a_empty[sa], pa ^ 1);
             uint8_t* abase = smem + sa * a_stage_bytes;
-            const int ac = (kc % wrap) * unit;
             if (elect_one()) {
-              if (kPair) {
-                const uint32_t fb = mapa_u32(&a_full[sa], 0);   // the leader's barrier collects both CTAs' bytes
-                mbar_expect_tx_cluster(fb, nload * p.patch_bytes);
-                for (int j = 0; j < nload; ++j)
-                  tma_load_4d_2sm(ma, abase + j * p.patch_bytes, fb, ac, w0 + (nload == 3 ? j - 1 : 0), h0 - p.halo,
-                                  b);
-              } else {
-                mbar_expect_tx(&a_full[sa], nload * p.patch_bytes);
-                for (int j = 0; j < nload; ++j)
-                  tma_load_4d(ma, abase + j * p.patch_bytes, &a_full[sa], ac, w0 + (nload == 3 ? j - 1 : 0),
-                              h0 - p.halo, b);
+              const uint32_t fb = kPair ? mapa_u32(&a_full[sa], 0) : 0u;   // pair: the leader's barrier collects both
+              if (kPair) mbar_expect_tx_cluster(fb, nload * p.patch_bytes);
+              else mbar_expect_tx(&a_full[sa], nload * p.patch_bytes);
+              for (int j = 0; j < nload; ++j) {
+                const int ac = ((ptaps == 9 ? kc : kc + j) % wrap) * unit;
+                const int wx = w0 + (ptaps == 9 ? j - 1 : 0);
+                if (kPair) tma_load_4d_2sm(ma, abase + j * p.patch_bytes, fb, ac, wx, h0 - p.halo, b);
+                else tma_load_4d(ma, abase + j * p.patch_bytes, &a_full[sa], ac, wx, h0 - p.halo, b);
               }
             }
             __syncwarp();
@@ -196,7 +196,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               sa = 0;
               pa ^= 1;
             }
-            for (int tap = 0; tap < ptaps; ++tap) {
+            const int nsteps = ptaps == 9 ? 9 : g;
+            for (int st = 0; st < nsteps; ++st) {
+              const int tap = ptaps == 9 ? st : 0;
+              const int kcb = ptaps == 9 ? kc : kc + st;
               mbar_wait(&b_empty[sb], pb ^ 1);
               uint8_t* bbase = smem_b + sb * b_stage_bytes;
               const int b3 = (ph & 1) ? 0 : (p.b_batched ? b : tap);
@@ -204,10 +207,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (kPair) {
                   const uint32_t fb = mapa_u32(&b_full[sb], 0);
                   mbar_expect_tx_cluster(fb, b_stage_bytes);
-                  tma_load_3d_2sm(mb, bbase, fb, kc * unit, brow, b3);
+                  tma_load_3d_2sm(mb, bbase, fb, kcb * unit, brow, b3);
                 } else {
                   mbar_expect_tx(&b_full[sb], b_stage_bytes);
-                  tma_load_3d(mb, bbase, &b_full[sb], kc * unit, brow, b3);
+                  tma_load_3d(mb, bbase, &b_full[sb], kcb * unit, brow, b3);
                 }
               }
               __syncwarp();
@@ -245,57 +248,59 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (nch == 0) continue;
           const int ptaps = (ph & 1) ? 1 : p.taps;
           const bool f8 = ph < 2;
-          for (int kc = 0; kc < nch; ++kc) {
+          const int group = (p.halo && ptaps == 1) ? 3 : 1;
+          for (int kc = 0; kc < nch; kc += group) {
+            const int nsteps = ptaps == 9 ? 9 : min(group, nch - kc);
             if (!(p.dbg & 4)) mbar_wait(&a_full[sa], pa);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + sa * a_stage_bytes);
-            for (int tap = 0; tap < ptaps; ++tap) {
+            for (int st = 0; st < nsteps; ++st) {
               if (!(p.dbg & 4)) mbar_wait(&b_full[sb], pb);
               tc_fence_after();
-              // tap (dy, dx): patch dx+1, shifted down by dy+1 rows; a 1x1 phase of a 3x3 launch reads the centre rows
-              int a_off = p.halo ? row_pitch : 0;
-              if (ptaps == 9) a_off = (tap % 3) * p.patch_bytes + (tap / 3) * row_pitch;
+              // 3x3 phase, tap (dy, dx): patch dx+1 shifted down dy+1 rows; 1x1 phase of a 3x3 launch: patch `st`
+              // (one per chunk of the group), centre rows; plain 1x1 / GEMM launch: the only patch, no halo
+              const int a_off = ptaps == 9 ? (st % 3) * p.patch_bytes + (st / 3) * row_pitch
+                                           : st * p.patch_bytes + (p.halo ? row_pitch : 0);
               const uint64_t da = make_sw128_kmajor_desc(a_addr + a_off);
               const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + sb * b_stage_bytes));
-              const bool last_tap = (tap == ptaps - 1);
+              const bool last_step = (st == nsteps - 1);
               // each MMA consumes 32 bytes of K per row (16 fp16 or 32 e4m3): +2 in (addr >> 4) units
               if (elect_one()) {
-              if (f8) {
+                if (f8) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t accu = (fresh && k == 0) ? 0u : 1u;
-                  if (kPair) umma_f8_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc8, accu);
-                  else umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc8, accu);
+                  for (int k = 0; k < 4; ++k) {
+                    const uint32_t accu = (fresh && k == 0) ? 0u : 1u;
+                    if (kPair) umma_f8_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc8, accu);
+                    else umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc8, accu);
+                  }
+                } else if (unscaled8) {
+                  // first fp16 block after the corrections: fold their 2^14 scale away (D = A*B + D * 2^-14)
+                  if (kPair) umma_f16_scale_d14_2sm(d_tmem, da, db, idesc);
+                  else umma_f16_scale_d14(d_tmem, da, db, idesc);
+#pragma unroll
+                  for (int k = 1; k < 4; ++k) {
+                    if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+                    else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint32_t accu = (fresh && k == 0) ? 0u : 1u;
+                    if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
+                    else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
+                  }
                 }
-              } else if (unscaled8) {
-                // first fp16 block after the corrections: fold their 2^14 scale away (D = A*B + D * 2^-14)
-                if (kPair) umma_f16_scale_d14_2sm(d_tmem, da, db, idesc);
-                else umma_f16_scale_d14(d_tmem, da, db, idesc);
-#pragma unroll
-                for (int k = 1; k < 4; ++k) {
-                  if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
-                  else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
-                }
-              } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t accu = (fresh && k == 0) ? 0u : 1u;
-                  if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
-                  else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
+                // frees the weight stage (in both CTAs of a pair) once the MMAs above have read it
+                if (kPair) umma_commit_2sm(&b_empty[sb]);
+                else umma_commit(&b_empty[sb]);
+                // every step of this patch stage issued: it is free once they complete
+                if (last_step) {
+                  if (kPair) umma_commit_2sm(&a_empty[sa]);
+                  else umma_commit(&a_empty[sa]);
                 }
               }
-              // frees the weight stage (in both CTAs of a pair) once the MMAs above have read it
-              if (kPair) umma_commit_2sm(&b_empty[sb]);
-              else umma_commit(&b_empty[sb]);
-              // all taps of this chunk issued: the patch stage is free once they complete
-              if (last_tap) {
-                if (kPair) umma_commit_2sm(&a_empty[sa]);
-                else umma_commit(&a_empty[sa]);
-              }
-              }  // elect_one
               __syncwarp();
-              if (f8) unscaled8 = true;
-              else unscaled8 = false;
+              unscaled8 = f8;
               fresh = false;
               if (++sb == p.stages_b) {
                 sb = 0;

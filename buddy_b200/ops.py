@@ -335,6 +335,7 @@ class KernelTimer:
 
     def __init__(self):
         self.records = []
+        self.issued_flops = 0.0     # conv launches: algorithmic FLOPs x fp16-pass equivalents actually issued
 
     def __enter__(self):
         global _timer
@@ -377,6 +378,11 @@ def _conv_flops(args, kwargs):
     return flops / kwargs.get("passes", 1)   # algorithmic FLOPs: split-precision passes are not useful work
 
 
+def _conv_pass_equiv(kwargs):
+    """fp16-pass equivalents issued per algorithmic product (e4m3 correction MMAs carry twice the K per instruction)."""
+    return 2.0 if kwargs.get("a8") is not None else float(kwargs.get("passes", 1))
+
+
 def _conv_tag(args, kwargs):
     a, w = args[0], args[1]
     B, H, W, C = a.shape
@@ -400,7 +406,10 @@ def _timed(fn, work_fn=None, tag_fn=_shape_tag):
         e0.record()
         r = fn(*args, **kwargs)
         e1.record()
-        _timer.records.append((fn.__name__, e0, e1, work_fn(args, kwargs) if work_fn else 0.0, tag_fn(args, kwargs)))
+        work = work_fn(args, kwargs) if work_fn else 0.0
+        _timer.records.append((fn.__name__, e0, e1, work, tag_fn(args, kwargs)))
+        if fn.__name__ == "conv_gemm":
+            _timer.issued_flops += work * _conv_pass_equiv(kwargs)
         return r
     wrapper.__name__ = fn.__name__
     wrapper.__doc__ = fn.__doc__

@@ -16,6 +16,7 @@ dev = "cuda"
 SHAPES = [  # (H, W, Cin, Cout, mode) — the mixed policy's dominant launches first
     (256, 528, 256, 256, "x1"), (256, 528, 384, 128, "x1"), (128, 264, 256, 256, "c8"), (256, 528, 128, 128, "c8"),
     (256, 528, 256, 256, "c8"), (128, 264, 512, 256, "x1"), (256, 528, 256, 256, "x3"),
+    (256, 528, 128, 128, "c8", 384), (256, 528, 256, 256, "x1", 256),
 ]
 
 
@@ -23,7 +24,9 @@ def e4m3(t):
     return t.clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)
 
 
-for (H, W, ci, co, mode) in SHAPES:
+for shp in SHAPES:
+    H, W, ci, co, mode = shp[:5]
+    cs = shp[5] if len(shp) > 5 else 0
     g = torch.Generator(device=dev).manual_seed(0)
     p = {"c8": 1, "x1": 1, "x3": 3}[mode]
     am = 1 if mode != "x3" else 2
@@ -35,6 +38,12 @@ for (H, W, ci, co, mode) in SHAPES:
     if mode == "c8":
         kw = dict(a8=e4m3(torch.randn(B, H, W, 2 * ci, device=dev, generator=g)),
                   w8=e4m3(torch.randn(9, co, 2 * ci, device=dev, generator=g)))
+    if cs:
+        kw["a2"] = torch.randn(B, H, W, cs, device=dev, generator=g).half()
+        kw["w2"] = (torch.randn(co, cs, device=dev, generator=g) * 0.05).half()
+        if mode == "c8":
+            kw["a8_2"] = e4m3(torch.randn(B, H, W, 2 * cs, device=dev, generator=g))
+            kw["w8_2"] = e4m3(torch.randn(co, 2 * cs, device=dev, generator=g))
     bias = torch.zeros(co, device=dev)
     if os.environ.get("NOSTATS"):
         stats = None
@@ -54,7 +63,7 @@ for (H, W, ci, co, mode) in SHAPES:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    alg = 2.0 * B * H * W * co * ci * 9
+    alg = 2.0 * B * H * W * co * (ci * 9 + cs)
     pe = {"c8": 2, "x1": 1, "x3": 3}[mode]
-    print(f"{H}x{W} {ci}->{co} {mode}: {ms:.3f} ms  alg {alg / ms / 1e9:.0f} TF/s  issued(fp16-equiv) {alg * pe / ms / 1e9:.0f} TF/s",
+    print(f"{H}x{W} {ci}->{co}{"+skip" + str(cs) if cs else ""} {mode}: {ms:.3f} ms  alg {alg / ms / 1e9:.0f} TF/s  issued(fp16-equiv) {alg * pe / ms / 1e9:.0f} TF/s",
           flush=True)
