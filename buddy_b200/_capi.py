@@ -36,7 +36,7 @@ class GemmDesc(ctypes.Structure):
         ("a8", c_void_p), ("a8_c", c_int), ("a8_stride_w", c_i64), ("a8_stride_h", c_i64), ("a8_stride_b", c_i64),
         ("b8", c_void_p),
         ("a8_2", c_void_p), ("a8_2_c", c_int), ("a8_2_stride_w", c_i64), ("a8_2_stride_h", c_i64),
-        ("a8_2_stride_b", c_i64), ("b8_2", c_void_p), ("no_staged_epilogue", c_int), ("no_cta_pairs", c_int), ("debug_flags", c_int),
+        ("a8_2_stride_b", c_i64), ("b8_2", c_void_p), ("no_staged_epilogue", c_int), ("no_cta_pairs", c_int), ("debug_flags", c_int), ("one_tap_per_stage", c_int),
     ]
 
 

@@ -43,6 +43,8 @@ struct GemmParams {
   // = whole 1024-byte swizzle atoms), so a chunk is read from L2 3.4x instead of 9x.  B ring: one weight tile per
   // (chunk, tap).
   int halo, patch_bytes, stages_a, stages_b;
+  int tpb;  // taps per B-ring stage (3x3 phases): 3 = one kernel row of weights per stage (one TMA load, one wait, one
+            // commit per 12 MMAs — the issue loop, not the tensor pipe, bounds layers with N <= 128), else 1
   float* out32;
   __half* out16;
   long long ldc;
@@ -80,7 +82,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader CTA of the pair
   const int b_rows = kPair ? (p.n_tile >> 1) : p.n_tile;   // weight-tile rows this CTA loads
   const int a_stage_bytes = (p.halo ? 3 : 1) * p.patch_bytes;
-  const int b_stage_bytes = b_rows * 128;
+  const int b_tile_bytes = b_rows * 128;              // one weight tile (one tap, one 64-wide chunk)
+  const int b_stage_bytes = p.tpb * b_tile_bytes;     // one B-ring stage
   // [A ring][B ring][2 staged epilogue chunks (if staged)][bias row 1 KB (if staged)][barriers]
   uint8_t* smem_b = smem + p.stages_a * a_stage_bytes;
   uint8_t* stage_out = smem_b + p.stages_b * b_stage_bytes;
@@ -197,7 +200,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               pa ^= 1;
             }
             const int nsteps = ptaps == 9 ? 9 : g;
-            for (int st = 0; st < nsteps; ++st) {
+            const int tstep = ptaps == 9 ? p.tpb : 1;   // taps covered by one B stage (one TMA box over the tap dim)
+            for (int st = 0; st < nsteps; st += tstep) {
               const int tap = ptaps == 9 ? st : 0;
               const int kcb = ptaps == 9 ? kc : kc + st;
               mbar_wait(&b_empty[sb], pb ^ 1);
@@ -206,10 +210,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (elect_one()) {
                 if (kPair) {
                   const uint32_t fb = mapa_u32(&b_full[sb], 0);
-                  mbar_expect_tx_cluster(fb, b_stage_bytes);
+                  mbar_expect_tx_cluster(fb, tstep * b_tile_bytes);
                   tma_load_3d_2sm(mb, bbase, fb, kcb * unit, brow, b3);
                 } else {
-                  mbar_expect_tx(&b_full[sb], b_stage_bytes);
+                  mbar_expect_tx(&b_full[sb], tstep * b_tile_bytes);
                   tma_load_3d(mb, bbase, &b_full[sb], kcb * unit, brow, b3);
                 }
               }
@@ -254,40 +258,46 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (!(p.dbg & 4)) mbar_wait(&a_full[sa], pa);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + sa * a_stage_bytes);
-            for (int st = 0; st < nsteps; ++st) {
+            const int tstep = ptaps == 9 ? p.tpb : 1;
+            for (int st = 0; st < nsteps; st += tstep) {
               if (!(p.dbg & 4)) mbar_wait(&b_full[sb], pb);
               tc_fence_after();
-              // 3x3 phase, tap (dy, dx): patch dx+1 shifted down dy+1 rows; 1x1 phase of a 3x3 launch: patch `st`
-              // (one per chunk of the group), centre rows; plain 1x1 / GEMM launch: the only patch, no halo
-              const int a_off = ptaps == 9 ? (st % 3) * p.patch_bytes + (st / 3) * row_pitch
-                                           : st * p.patch_bytes + (p.halo ? row_pitch : 0);
-              const uint64_t da = make_sw128_kmajor_desc(a_addr + a_off);
-              const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + sb * b_stage_bytes));
-              const bool last_step = (st == nsteps - 1);
-              // each MMA consumes 32 bytes of K per row (16 fp16 or 32 e4m3): +2 in (addr >> 4) units
+              const uint32_t b_addr = smem_u32(smem_b + sb * b_stage_bytes);
+              const bool last_step = (st + tstep >= nsteps);
               if (elect_one()) {
-                if (f8) {
+                for (int tt = 0; tt < tstep; ++tt) {
+                  const int s1 = st + tt;
+                  // 3x3 phase, tap (dy, dx): patch dx+1 shifted down dy+1 rows; 1x1 phase of a 3x3 launch: patch
+                  // `s1` (one per chunk of the group), centre rows; plain 1x1 / GEMM launch: the only patch, no halo
+                  const int a_off = ptaps == 9 ? (s1 % 3) * p.patch_bytes + (s1 / 3) * row_pitch
+                                               : s1 * p.patch_bytes + (p.halo ? row_pitch : 0);
+                  const uint64_t da = make_sw128_kmajor_desc(a_addr + a_off);
+                  const uint64_t db = make_sw128_kmajor_desc(b_addr + tt * b_tile_bytes);
+                  const bool first = fresh && tt == 0;
+                  // each MMA consumes 32 bytes of K per row (16 fp16 or 32 e4m3): +2 in (addr >> 4) units
+                  if (f8) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const uint32_t accu = (fresh && k == 0) ? 0u : 1u;
-                    if (kPair) umma_f8_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc8, accu);
-                    else umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc8, accu);
-                  }
-                } else if (unscaled8) {
-                  // first fp16 block after the corrections: fold their 2^14 scale away (D = A*B + D * 2^-14)
-                  if (kPair) umma_f16_scale_d14_2sm(d_tmem, da, db, idesc);
-                  else umma_f16_scale_d14(d_tmem, da, db, idesc);
+                    for (int k = 0; k < 4; ++k) {
+                      const uint32_t accu = (first && k == 0) ? 0u : 1u;
+                      if (kPair) umma_f8_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc8, accu);
+                      else umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc8, accu);
+                    }
+                  } else if (unscaled8 && tt == 0) {
+                    // first fp16 block after the corrections: fold their 2^14 scale away (D = A*B + D * 2^-14)
+                    if (kPair) umma_f16_scale_d14_2sm(d_tmem, da, db, idesc);
+                    else umma_f16_scale_d14(d_tmem, da, db, idesc);
 #pragma unroll
-                  for (int k = 1; k < 4; ++k) {
-                    if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
-                    else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
-                  }
-                } else {
+                    for (int k = 1; k < 4; ++k) {
+                      if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+                      else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+                    }
+                  } else {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const uint32_t accu = (fresh && k == 0) ? 0u : 1u;
-                    if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
-                    else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
+                    for (int k = 0; k < 4; ++k) {
+                      const uint32_t accu = (first && k == 0) ? 0u : 1u;
+                      if (kPair) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
+                      else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
+                    }
                   }
                 }
                 // frees the weight stage (in both CTAs of a pair) once the MMAs above have read it
@@ -792,10 +802,13 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   p.res_staged = (p.staged && d->resid) ? 1 : 0;
   const int epi_bytes = p.staged ? 2 * kChunkBytes + 1024 : 0;
   const int ring_bytes = 227 * 1024 - 1536 - epi_bytes;
+  p.tpb = 1;
   if (p.halo) {
-    // a patch stage lasts nine weight stages: two of them, the rest of the shared memory goes to the weight ring
+    // a patch stage lasts nine weight tiles: two of them, the rest of the shared memory goes to the weight ring —
+    // as kernel rows of three taps per stage when at least three such stages fit (N <= 128 in pair mode)
     p.stages_a = 2;
-    p.stages_b = (ring_bytes - 2 * a_stage_bytes) / b_stage_bytes;
+    if (!d->one_tap_per_stage && (ring_bytes - 2 * a_stage_bytes) / (3 * b_stage_bytes) >= 3) p.tpb = 3;
+    p.stages_b = (ring_bytes - 2 * a_stage_bytes) / (p.tpb * b_stage_bytes);
   } else {
     p.stages_a = p.stages_b = ring_bytes / (a_stage_bytes + b_stage_bytes);
   }
@@ -833,8 +846,9 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     if (e) return e;
     uint64_t dimsb[3] = {(uint64_t)d->a8_c, (uint64_t)d->b_rows, (uint64_t)d->b_t};
     uint64_t strb[3] = {1, (uint64_t)d->a8_c, (uint64_t)d->a8_c * (uint64_t)d->b_rows};
+    uint32_t boxb8[3] = {128, (uint32_t)b_box_rows, (uint32_t)p.tpb};
     uint32_t boxb[3] = {128, (uint32_t)b_box_rows, 1};
-    e = encode_map(&tmB8, d->b8, 3, dimsb, strb, boxb, 1);
+    e = encode_map(&tmB8, d->b8, 3, dimsb, strb, boxb8, 1);
     if (e) return e;
     if (d->a2) {
       if (!d->a8_2 || !d->b8_2 || d->a8_2_c % 128) {
@@ -862,7 +876,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   {
     uint64_t dims[3] = {(uint64_t)k1, (uint64_t)d->b_rows, (uint64_t)d->b_t};
     uint64_t str[3] = {1, (uint64_t)d->b_stride_n, (uint64_t)d->b_stride_t};
-    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)b_box_rows, 1};
+    uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)b_box_rows, (uint32_t)p.tpb};
     int e = encode_map(&tmB, d->b, 3, dims, str, box);
     if (e) return e;
   }
@@ -906,7 +920,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     tmRes = tmA;
   }
 
-  const size_t smem_bytes = (size_t)p.stages_a * a_stage_bytes + (size_t)p.stages_b * b_stage_bytes + epi_bytes +
+  const size_t smem_bytes = (size_t)p.stages_a * a_stage_bytes + (size_t)p.stages_b * p.tpb * b_stage_bytes + epi_bytes +
                             256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {

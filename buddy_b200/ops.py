@@ -24,7 +24,7 @@ def _pick_n_tile(n_total):
 
 def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=None, bias_b=None, resid=None,
               scale=1.0, stats=None, b_batched=False, col_off=0, ldc=None, max_ctas=0, passes=1, a8=None, w8=None,
-              a8_2=None, w8_2=None, direct_epilogue=False, no_pairs=False, debug_flags=0):
+              a8_2=None, w8_2=None, direct_epilogue=False, no_pairs=False, debug_flags=0, one_tap_per_stage=False):
     """out[b,h,w,n] = scale*(sum_{tap,k} a[b,h+dy,w+dx,k] w[tap,n,k] + sum_k a2[b,h,w,k] w2[n,k] + bias + bias_b + resid).
 
     a, a2 : fp16 [B,H,W,C] (channel stride 1, other strides arbitrary multiples of 8 elements)
@@ -75,6 +75,7 @@ def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=N
     d.no_staged_epilogue = 1 if direct_epilogue else 0
     d.no_cta_pairs = 1 if no_pairs else 0
     d.debug_flags = int(debug_flags)
+    d.one_tap_per_stage = 1 if one_tap_per_stage else 0
     if a8 is not None:
         assert a8.dtype == torch.uint8 and w8.dtype == torch.uint8 and a8.shape[:3] == a.shape[:3]
         assert w8.is_contiguous() and w8.shape[:2] == w.shape[:2] and w8.shape[2] == a8.shape[3]

@@ -110,6 +110,8 @@ typedef struct buddy_gemm_desc {
   int32_t no_cta_pairs;
   /* profiling experiments only (results are NOT written): 1 = skip the epilogue body, 2 = only read the accumulator */
   int32_t debug_flags;
+  /* 1 = one weight tile per pipeline stage even where a kernel row of three fits (testing / A-B timing only) */
+  int32_t one_tap_per_stage;
 } buddy_gemm_desc;
 
 int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream);

@@ -47,6 +47,8 @@ for shp in SHAPES:
     bias = torch.zeros(co, device=dev)
     if os.environ.get("NOSTATS"):
         stats = None
+    if os.environ.get("ONETAP"):
+        kw["one_tap_per_stage"] = True
     if os.environ.get("DBG"):
         kw["debug_flags"] = int(os.environ["DBG"])
     if os.environ.get("NOPAIR"):

@@ -211,16 +211,18 @@ def test_cta_pairs_match_single_cta(B, H, W, C, N, c8):
                   a8_2=e4(torch.randn(B, H, W, 128, device="cuda", generator=g)),
                   w8_2=e4(torch.randn(N, 128, device="cuda", generator=g)))
     outs, sts = [], []
-    for no_pairs in (True, False):
+    # single CTA; CTA pairs (default: a kernel row of three weight tiles per pipeline stage where it fits); pairs
+    # with one tile per stage — the same MMAs in the same order every time
+    for no_pairs, one_tap in ((True, False), (False, False), (False, True)):
         out = torch.full((B, H, W, N), float("nan"), device="cuda")
         stats = torch.zeros(B, N // 4, 2, device="cuda", dtype=torch.float64)
         for _ in range(2):
             stats.zero_()
             ops.conv_gemm(a, w, out, taps=9, n_total=N, a2=a2, w2=w2, bias=bias, bias_b=bias_b, scale=0.5,
-                          stats=stats, no_pairs=no_pairs, **kw)
+                          stats=stats, no_pairs=no_pairs, one_tap_per_stage=one_tap, **kw)
         torch.cuda.synchronize()
         outs.append(out)
         sts.append(stats)
     assert not torch.isnan(outs[1]).any()
-    assert torch.equal(outs[0], outs[1])
-    assert rel(sts[1], sts[0]) < 1e-9
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert rel(sts[1], sts[0]) < 1e-9 and rel(sts[2], sts[0]) < 1e-9
