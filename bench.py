@@ -44,7 +44,7 @@ def informed_args(T):
     sde = AD(sigma_data=0.05, sigma_min=1e-4, sigma_max=0.5, rho=10)
     loss = AD(name="l2_comp_stft_summean", weight=512, frequency_weighting="none", compression_factor=0.667,
               multiple_compression_factors=False)
-    return AD(exp=AD(audio_len=N_SAMPLES, sample_rate=16000),
+    return AD(exp=AD(audio_len=65536, sample_rate=16000),   # (normguide divides by sqrt(exp.audio_len) whatever the length)
               tester=AD(sampling_params=AD(same_as_training=False, sde_hp=sde, Schurn=10, Snoise=1, Stmin=0, Stmax=10,
                                            order=2, T=T, schedule="edm"),
                         posterior_sampling=AD(zeta=2.75, rec_loss=loss, normalization_type="grad_norm",
@@ -52,7 +52,7 @@ def informed_args(T):
                                               constraint_speech_magnitude=AD(use=False))))
 
 
-def synth_batch(first, count):
+def synth_batch(first, count, N_SAMPLES=N_SAMPLES):
     """Speech surrogate + RIR per utterance: seeds 1000+b / 2000+b, host side, fp32."""
     import numpy as np
     from scipy.signal import lfilter
@@ -214,7 +214,9 @@ def run_ours(args):
         for p in net.parameters():
             dist.broadcast(p.data, src=0)
 
-    s_host, h_host = synth_batch(rank * B, B)
+    long_form = args.mode == "long"
+    N_SAMPLES = 480000 if long_form else 65536        # run_ours-local: 30 s long-form (BASELINE configs[4]) or 4.096 s
+    s_host, h_host = synth_batch(rank * B, B, N_SAMPLES)
     op = RIROperator()
     op.update_params(h_host.to(dev))
     y = op.degradation(s_host.to(dev))
@@ -336,7 +338,7 @@ def run_ours(args):
         dtype_s = f"f16 operands x{eng.np} passes / f32 accumulate+activations"
     traffic, traffic_note = None, None
     tp = os.path.join(ROOT, "profiles", "conv_gemm_r01_final_ncu_full.txt")
-    if os.path.exists(tp) and B >= 16 and args.micro_batch == 16 and not blind:
+    if os.path.exists(tp) and B >= 16 and args.micro_batch == 16 and not blind and not long_form:
         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (256->256 3x3 @256x528, 16 utterances,
         # single pass) from the committed `ncu --set full` capture of this kernel
         try:
@@ -377,12 +379,20 @@ def run_ours(args):
         "kernel_time_share": {k: round(v[1] / total_ms_ops, 4) for k, v in
                               sorted(summ.items(), key=lambda kv: -kv[1][1])[:6]},
     }
+    if long_form:
+        line["config"]["workload"] = ("LONG-FORM informed EulerHeunSamplerDPS T=35 order 2, synthetic 30 s @ 16 kHz "
+                                      "(480000 samples -> 256 x 3760 spectrogram, attention over 15040 tokens, "
+                                      "block-wise RIR convolution), BASELINE configs[4]; whole utterances, no tiling "
+                                      "needed at 180 GB (exact global GroupNorm / attention)")
+        line["config"]["samples"] = N_SAMPLES
+        line["config"]["gflop_per_eval"] = 18760.0
+        line["algorithmic_tflops"] = value * 2 * 18760.0 / 1e3
     if blind:
         line["config"]["workload"] = ("blind EulerHeunSamplerDPS T=60 order 1 + 10 operator-Adam iterations per step "
                                       "(BASELINE configs[2]), synthetic 4.096 s @ 16 kHz")
         line["config"]["step_definition"] = "one Euler sampler step over the batch = 1 network fwd+VJP + 10 operator updates"
         line["config"]["T"], line["config"]["order"], line["config"]["evals_per_utterance"] = 60, 1, 60
-    if world == 1 and not args.no_cpu_baseline and not blind:
+    if world == 1 and not args.no_cpu_baseline and not blind and not long_form:
         sec, threads = cpu_reference_step_time(1, 0)
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "utterance-steps/s", "cores": threads, "kind": "port",
                                 "sample": "B=1, ONE Euler-Heun DPS step (2 fwd+VJP evaluations) of the same config, "
@@ -403,10 +413,15 @@ def main():
     ap.add_argument("--streams", type=int, default=1, help="micro-batches in flight on separate CUDA streams")
     ap.add_argument("--precision", default=os.environ.get("BUDDY_PRECISION", "mixed"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="informed", choices=["informed", "blind"],
+    ap.add_argument("--mode", default="informed", choices=["informed", "blind", "long"],
                     help="informed = BASELINE configs[1] (default, the bench line); blind = configs[2] (order 1, T=60, "
-                         "10 operator-Adam iterations per step)")
+                         "10 operator-Adam iterations per step); long = configs[4] (30 s utterances, batch 16)")
     args = ap.parse_args()
+    if args.mode == "long":
+        if args.batch == BATCH_PER_GPU:
+            args.batch = 16
+        if args.micro_batch == 16:
+            args.micro_batch = 4
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -134,7 +134,12 @@ class LossSTFT:
 
 
 class RirConv:
-    """y = (x * h)[:N] by FFT, and its adjoint (correlation).  h: (M,) shared or (B, M) per utterance."""
+    """y = (x * h)[:N] by FFT, and its adjoint (correlation).  h: (M,) shared or (B, M) per utterance.
+
+    One 2^15..2^17-point FFT when N + M - 1 fits (the 4 s case of the reference, reverb_utils.py:25-60); longer signals
+    (BASELINE configs[4], 30 s) run the same kernel block-wise: overlap-add with blocks of 2^17 - M + 1 samples."""
+
+    MAX_LOG2 = 17
 
     def __init__(self, h, n, device):
         h = torch.as_tensor(h, dtype=torch.float32, device=device)
@@ -142,9 +147,13 @@ class RirConv:
         hb = h if self.per_utt else h[None]
         m = hb.shape[-1]
         log2 = max(15, math.ceil(math.log2(n + m - 1)))
-        if log2 > 17:
-            raise ValueError(f"RirConv: FFT of 2^{log2} points unsupported (N={n}, M={m})")
-        self.n, self.log2_n2, self.L = n, log2 - 8, 1 << log2
+        self.block = None
+        if log2 > self.MAX_LOG2:
+            log2 = self.MAX_LOG2
+            self.block = (1 << log2) - m + 1
+            if self.block < m:
+                raise ValueError(f"RirConv: RIR of {m} taps too long for block convolution with 2^{log2}-point FFTs")
+        self.n, self.m, self.log2_n2, self.L = n, m, log2 - 8, 1 << log2
         k = torch.arange(256, dtype=torch.float64)
         self.tw = torch.stack([torch.cos(2 * math.pi * k / 512), -torch.sin(2 * math.pi * k / 512)], -1).float().to(device)
         self.H = torch.empty(hb.shape[0], self.L, 2, device=device)
@@ -153,7 +162,6 @@ class RirConv:
     def _apply(self, x, mode, first):
         B = x.shape[0]
         work = torch.empty(B, self.L, 2, device=x.device)     # per call: stream-ordered, safe across streams
-        y = torch.empty(B, self.n, device=x.device)
         stride = self.L * 2 if self.per_utt else 0
         if self.per_utt:
             if first + B > self.H.shape[0]:
@@ -161,7 +169,28 @@ class RirConv:
             H = self.H[first:first + B]
         else:
             H = self.H
-        return ops.fftconv(x, x.shape[1], self.log2_n2, self.tw, work, H, stride, mode, y, self.n)
+        n, m = self.n, self.m
+        if self.block is None:
+            y = torch.empty(B, n, device=x.device)
+            return ops.fftconv(x, x.shape[1], self.log2_n2, self.tw, work, H, stride, mode, y, n)
+        Lb = self.block
+        if mode == 1:
+            # overlap-add: block k contributes (x_k * h) at offset k*Lb; consecutive blocks overlap by m - 1 samples
+            y = torch.zeros(B, n, device=x.device)
+            tmp = torch.empty(B, Lb + m - 1, device=x.device)
+            for a in range(0, n, Lb):
+                nin = min(Lb, n - a)
+                nout = min(nin + m - 1, n - a)
+                ops.fftconv(x[:, a:a + nin], nin, self.log2_n2, self.tw, work, H, stride, 1, tmp, nout)
+                y[:, a:a + nout] += tmp[:, :nout]
+            return y
+        # adjoint: x_bar block k = correlation of g[k*Lb : k*Lb + Lb + m - 1] with h (blocks do not overlap in x_bar)
+        out = torch.empty(B, n, device=x.device)
+        for a in range(0, n, Lb):
+            nout = min(Lb, n - a)
+            nin = min(nout + m - 1, n - a)
+            ops.fftconv(x[:, a:a + nin], nin, self.log2_n2, self.tw, work, H, stride, 2, out[:, a:a + nout], nout)
+        return out
 
     def forward(self, x, first=0):
         """x: [B, n] = utterances first .. first+B-1 of the batch the RIRs were given for."""

@@ -96,3 +96,27 @@ def test_full_size_forward_and_vjp_vs_oracle(net, sd):
     print(f"\n[{net.precision}]", end="")
     print(f"\n[net full] fwd rel-L2 {e_out:.2e}  vjp rel-L2 {e_vjp:.2e}")
     assert e_out < tol(net) and e_vjp < tol(net)
+
+
+def test_other_lengths_forward_and_vjp_vs_oracle(sd):
+    """The path is fully convolutional in time: a 6.1 s utterance (98304 samples -> 769 frames -> 784
+    padded) and a ragged 1.3 s one (20517 samples) against the oracle on the GPU, default precision."""
+    from buddy_b200.ncsnpp import NCSNppTime
+    from oracle import net as onet
+    net = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    for n in (98304, 20517):
+        x = (randn(8, 1, 1, n) * 0.2).cuda()
+        tc = torch.tensor([0.25 * torch.log(torch.tensor(0.07))]).cuda()
+        cot = randn(9, 1, 1, n).cuda() * 1e-3
+        xr = x.clone().requires_grad_(True)
+        ref = onet.ncsnpp_time_forward(sdc, xr, tc)
+        (gref,) = torch.autograd.grad((ref * cot).sum(), xr)
+        xg = x.clone().requires_grad_(True)
+        out = net(xg, tc)
+        (gout,) = torch.autograd.grad((out * cot).sum(), xg)
+        e_out, e_vjp = rel(out.detach(), ref.detach()), rel(gout, gref)
+        print(f"\n[net n={n}] fwd rel-L2 {e_out:.2e}  vjp rel-L2 {e_vjp:.2e}")
+        assert e_out < TOL and e_vjp < TOL

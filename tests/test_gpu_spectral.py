@@ -67,8 +67,10 @@ def test_loss_stft_and_comp_loss(N):
     assert rel(gx, gref) < 1e-3, rel(gx, gref)
 
 
-@pytest.mark.parametrize("N,M,per_utt", [(8192, 2000, False), (65536, 16000, False), (65536, 40000, True)])
+@pytest.mark.parametrize("N,M,per_utt", [(8192, 2000, False), (65536, 16000, False), (65536, 40000, True),
+                                         (480000, 16000, True), (300001, 37710, False)])
 def test_rir_fftconv(N, M, per_utt):
+    """The last two cases (30 s long-form, BASELINE configs[4]) exceed one 2^17-point FFT: block-wise overlap-add."""
     from buddy_b200.spectral import RirConv
     from oracle import operators as oop
     g = torch.Generator(device="cuda").manual_seed(3)
