@@ -417,6 +417,8 @@ def main():
                     help="informed = BASELINE configs[1] (default, the bench line); blind = configs[2] (order 1, T=60, "
                          "10 operator-Adam iterations per step); long = configs[4] (30 s utterances, batch 16)")
     args = ap.parse_args()
+    if args.mode == "blind" and args.batch == BATCH_PER_GPU:
+        args.batch = 128          # BASELINE configs[2]
     if args.mode == "long":
         if args.batch == BATCH_PER_GPU:
             args.batch = 16

@@ -943,7 +943,30 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
                                                                     tmOut, tmRes, p);
   } else {
     const long long work = ((pix_tiles + 1) / 2) * p.n_tiles;
-    int clusters = num_sms() / 2;
+    // persistent pairs: as many 2-CTA clusters as can be co-resident (74 on a full B200; fewer if a GPC has an odd
+    // number of usable SMs) — queried once with the largest shared-memory footprint
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(num_sms(), 1, 1);
+      q.blockDim = dim3(kThreads, 1, 1);
+      q.dynamicSmemBytes = 227 * 1024;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<true>, &q) != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        n = num_sms() / 2;
+      }
+      max_clusters = n < num_sms() / 2 ? n : num_sms() / 2;
+    }
+    int clusters = max_clusters;
     if (d->max_ctas > 0 && d->max_ctas / 2 < clusters) clusters = d->max_ctas / 2 > 0 ? d->max_ctas / 2 : 1;
     if (work < clusters) clusters = (int)work;
     cudaLaunchConfig_t cfg;
