@@ -105,6 +105,8 @@ class Engine:
         self.c8 = precision in ("fp16c8", "mixed")
         self.mixed = precision == "mixed"
         self.x1_convs = set()   # (module index, conv index) of the single-pass convolutions (mixed mode)
+        self._graphs = {}
+        self.graph_max_batch = 8    # larger batches are GPU-bound: plain launches (no pinned graph memory pool)
         self.split = 2 if self.c8 else (1 if self.np > 1 else 0)
         self.am = 2 if self.split == 1 else 1
         self.gs = {}            # per-call-site power-of-two scales of the gradient operands (fp16c8)
@@ -219,8 +221,8 @@ class Engine:
         tc = torch.full((1,), 0.25 * math.log(0.1), device=self.device)
         dout = torch.randn(1, 256, 80, 2, generator=g).to(self.device)
         self._rms = {}
-        _, ctx = self.forward(spec, tc, save=True)
-        self.vjp(ctx, dout)
+        _, ctx = self._forward_impl(spec, tc, save=True)
+        self._vjp_impl(ctx, dout)
         rms, self._rms = self._rms, None
         self.gs = {k: 2.0 ** round(math.log2(1.0 / max(v, 1e-20))) for k, v in rms.items()}
     def _pack_rb(self, i, level):
@@ -466,7 +468,61 @@ class Engine:
         return dx, g16
 
     # ------------------------------------------------------------------ forward
-    def forward(self, spec, time_cond, save=True):
+    # ------------------------------------------------------------------ CUDA graphs (small batches are launch-bound)
+    def _graph_entry(self, spec, save):
+        """Capture forward (and, with save, the VJP) of this (batch, frames) shape once: two CUDA graphs sharing one
+        memory pool, static input / output buffers.  ~320 kernel launches per evaluation cost ~33 us of host time
+        each; a single 4 s utterance (the reference's own B = 1 usage) is host-bound without this."""
+        B, H, W, _ = spec.shape
+        key = (B, W, bool(save), torch.cuda.current_stream().cuda_stream)
+        ent = self._graphs.get(key)
+        if ent is not None:
+            return ent
+        dev = self.device
+        ent = {"spec": torch.empty_like(spec), "tc": torch.empty(B, device=dev)}
+        ent["spec"].copy_(spec)
+        ent["tc"].fill_(-0.5)
+        # eager warm-up on the capture inputs (lazy one-off initialisation inside the library must not be captured)
+        out, ctx = self._forward_impl(ent["spec"], ent["tc"], save)
+        if save:
+            self._vjp_impl(ctx, torch.ones_like(out))
+        del out, ctx
+        torch.cuda.synchronize()
+        pool = torch.cuda.graph_pool_handle()
+        ent["fwd"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ent["fwd"], pool=pool):
+            ent["out"], ent["ctx"] = self._forward_impl(ent["spec"], ent["tc"], save)
+        if save:
+            ent["dout"] = torch.empty_like(ent["out"])
+            ent["bwd"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ent["bwd"], pool=pool):
+                ent["dx"] = self._vjp_impl(ent["ctx"], ent["dout"])
+        self._graphs[key] = ent
+        return ent
+
+    def forward(self, spec, time_cond, save=True, graph=False):
+        """spec fp32 [B, 256, Tp, 2] (re, im channels-last), time_cond fp32 [B] -> (out [B,256,Tp,2], ctx).
+
+        graph=True (used by the samplers for batches <= `graph_max_batch`): replay a captured CUDA graph.  The returned
+        tensors are the graph's static buffers — valid until the next graphed call of the same shape."""
+        if graph and spec.shape[0] <= self.graph_max_batch and ops._timer is None:
+            ent = self._graph_entry(spec, save)
+            ent["spec"].copy_(spec)
+            ent["tc"].copy_(time_cond)
+            ent["fwd"].replay()
+            return ent["out"], ({"_graph": ent} if save else None)
+        return self._forward_impl(spec, time_cond, save)
+
+    def vjp(self, ctx, dout):
+        """dout fp32 [B,256,Tp,2] (gradient w.r.t. forward's output) -> gradient w.r.t. `spec`."""
+        ent = ctx.get("_graph") if isinstance(ctx, dict) else None
+        if ent is not None:
+            ent["dout"].copy_(dout)
+            ent["bwd"].replay()
+            return ent["dx"]
+        return self._vjp_impl(ctx, dout)
+
+    def _forward_impl(self, spec, time_cond, save=True):
         """spec fp32 [B, 256, Tp, 2] (re, im channels-last), time_cond fp32 [B] -> (out [B,256,Tp,2], ctx)."""
         assert spec.dtype == torch.float32 and spec.is_contiguous() and spec.shape[1] == 256 and spec.shape[3] == 2
         B, H, W, _ = spec.shape
@@ -524,8 +580,7 @@ class Engine:
         return out, ctx
 
     # ------------------------------------------------------------------ data-gradient
-    def vjp(self, ctx, dout):
-        """dout fp32 [B,256,Tp,2] (gradient w.r.t. forward's output) -> gradient w.r.t. `spec`."""
+    def _vjp_impl(self, ctx, dout):
         B, H, W = ctx["shape"]
         dev = self.device
         assert dout.shape == (B, H, W, 2) and dout.is_contiguous()

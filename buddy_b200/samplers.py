@@ -47,6 +47,7 @@ class Sampler:
         #                                   measured gain on B200 is <1 % because the convolutions already run at the
         #                                   board power cap, so the default stays 1 (half the activation memory)
         self._streams = None
+        self.use_graphs = True            # replay captured CUDA graphs of the network forward / VJP for small batches
         self._draw = 0
 
     def _for_micro_batches(self, B, body):
@@ -156,7 +157,7 @@ class EulerHeunSampler(Sampler):
         cskip, cout, cin, cnoise = self._edm_scalars(sigma)
         eng, st = net.engine(), net.stft_engine()
         spec = st.forward(x_hat, scale_b=_vec(cin, B, dev))
-        fspec, ctx = eng.forward(spec, _vec(cnoise, B, dev), save=save)
+        fspec, ctx = eng.forward(spec, _vec(cnoise, B, dev), save=save, graph=self.use_graphs and self.n_streams == 1)
         F = st.inverse(fspec, n)
         x_den = ops.lincomb3(torch.empty_like(x_hat), x_hat, _vec(cskip, B, dev), F, _vec(cout, B, dev))
         return x_den, ctx
