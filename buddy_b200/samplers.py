@@ -41,6 +41,7 @@ class Sampler:
         self.noise_source = None          # iterator of pre-drawn N(0,1) tensors (parity tests)
         self.seed_base = 3000             # Philox stream of utterance b = seed_base + utterance_offset + b
         self.utterance_offset = 0         # global index of this rank's first utterance (multi-GPU shards)
+        self.utterance_ids = None         # or: explicit global index of every utterance of the batch
         self.micro_batch = 16             # utterances per network evaluation
         self.n_streams = 1                # micro-batches in flight on separate CUDA streams (results identical).  >1
         #                                   overlaps one micro-batch's HBM-bound kernels with another's convolutions;
@@ -103,7 +104,12 @@ class Sampler:
             assert tuple(z.shape) == tuple(shape), (z.shape, shape)
             return z.contiguous()
         B, n = shape
-        seeds = torch.arange(B, dtype=torch.int64, device=device) + (self.seed_base + self.utterance_offset + first)
+        if self.utterance_ids is not None:      # explicit global utterance indices (batches that are not contiguous)
+            ids = torch.as_tensor(self.utterance_ids, dtype=torch.int64)[first:first + B]
+            assert ids.numel() == B, "utterance_ids must list one index per utterance of the batch"
+            seeds = ids.to(device) + self.seed_base
+        else:
+            seeds = torch.arange(B, dtype=torch.int64, device=device) + (self.seed_base + self.utterance_offset + first)
         out = torch.empty(B, n, device=device)
         if draw is None:
             draw = self._draw

@@ -117,3 +117,14 @@ def test_sampler_schedule_host_logic():
                              rh.make_args(mode, int(T)))
         t = s.create_schedule()
         assert torch.equal(t, g[key]["t"]) and torch.equal(s.get_gamma(t), g[key]["gamma"])
+
+
+def test_length_buckets():
+    """Front-end bucketing (tester.py:132 loop, batched): equal lengths share a batch, chunks <= max_batch, every index
+    exactly once, input order kept inside a bucket."""
+    from buddy_b200.tester import length_buckets
+    lengths = [100, 200, 100, 100, 300, 200, 100]
+    b = length_buckets(lengths, 2)
+    assert b == [[0, 2], [3, 6], [1, 5], [4]]
+    assert sorted(i for g in b for i in g) == list(range(len(lengths)))
+    assert length_buckets([], 4) == [] and length_buckets([5], 4) == [[0]]
