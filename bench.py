@@ -338,7 +338,7 @@ def run_ours(args):
         dtype_s = f"f16 operands x{eng.np} passes / f32 accumulate+activations"
     traffic, traffic_note = None, None
     tp = os.path.join(ROOT, "profiles", "conv_gemm_r01_final_ncu_full.txt")
-    if os.path.exists(tp) and B >= 16 and args.micro_batch == 16 and not blind and not long_form:
+    if os.path.exists(tp) and B >= 16 and args.micro_batch >= 16 and not blind and not long_form:
         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (256->256 3x3 @256x528, 16 utterances,
         # single pass) from the committed `ncu --set full` capture of this kernel
         try:
@@ -348,10 +348,12 @@ def run_ours(args):
                     rd = float(ln.split(":")[1].split("|")[0])
                 if ln.startswith("dram__bytes_write.sum"):
                     wr = float(ln.split(":")[1].split("|")[0])
-            traffic = (rd + wr) * 1e9
-            traffic_note = ("DRAM bytes per launch of the dominant shape (conv 256->256 3x3 @256x528, 16 utterances): "
-                            "ncu capture in profiles/conv_gemm_r01_final_ncu_full.txt; algorithmic bytes of that launch "
-                            "= fp16 input 1.107e9 + fp32 output 2.215e9 + weights 1.2e6 = 3.323e9")
+            mbs = min(B, args.micro_batch) / 16.0       # the capture is at 16 utterances per launch; bytes scale with it
+            traffic = (rd + wr) * 1e9 * mbs
+            traffic_note = ("DRAM bytes per launch of the dominant shape (conv 256->256 3x3 @256x528): ncu capture at 16 "
+                            "utterances per launch in profiles/conv_gemm_r01_final_ncu_full.txt (3.342e9 B vs "
+                            "algorithmic 3.323e9 B = fp16 input 1.107e9 + fp32 output 2.215e9 + weights 1.2e6), scaled "
+                            "to this run's utterances per launch")
         except Exception:
             traffic = None
     total_ms_ops = sum(v[1] for v in summ.values())
@@ -409,7 +411,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
-    ap.add_argument("--micro-batch", type=int, default=16)
+    ap.add_argument("--micro-batch", type=int, default=32)
     ap.add_argument("--streams", type=int, default=1, help="micro-batches in flight on separate CUDA streams")
     ap.add_argument("--precision", default=os.environ.get("BUDDY_PRECISION", "mixed"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -422,7 +424,7 @@ def main():
     if args.mode == "long":
         if args.batch == BATCH_PER_GPU:
             args.batch = 16
-        if args.micro_batch == 16:
+        if args.micro_batch == 32:
             args.micro_batch = 4
     if args.impl == "reference":
         run_reference(args)

@@ -9,6 +9,7 @@
 #include <cuda_fp8.h>
 
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/buddy_b200.h"
 #include "common.cuh"
@@ -783,6 +784,17 @@ extern "C" int buddy_gn_stats(const float* x, int B, int64_t P, int C, double* s
   LAUNCH_END("gn_stats_kernel");
 }
 
+// pixels per thread of the GroupNorm kernels (tuning knob: BUDDY_GN_PPT, default 32)
+static int gn_ppt() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("BUDDY_GN_PPT");
+    v = e ? atoi(e) : 32;
+    if (v < 1 || v > 1024) v = 32;
+  }
+  return v;
+}
+
 static int check_gn(int Ca, int Cb, int G, const char* who) {
   const int C = Ca + Cb;
   if (Ca % 8 || Cb % 8 || C <= 0 || C > 1024 || G <= 0 || G > 32 || C % G || (C / G) % 4) {
@@ -828,7 +840,7 @@ extern "C" int buddy_gn_apply(const buddy_gn_desc* d, void* stream) {
   const int threads = c4n * (256 / c4n > 0 ? 256 / c4n : 1);
   const long long ppb = threads / c4n;
   const long long Pw = static_cast<long long>(d->mode == 2 ? (d->H / 2) * (d->W / 2) : d->H * d->W);
-  long long gx = (Pw + ppb * 16 - 1) / (ppb * 16);   // ~16 pixels per thread
+  long long gx = (Pw + ppb * gn_ppt() - 1) / (ppb * gn_ppt());   // ~32 pixels per thread
   if (gx > 148 * 16) gx = 148 * 16;
   if (gx < 1) gx = 1;
   gn_apply_kernel<<<dim3((unsigned)gx, d->batch), threads, 0, STREAM>>>(a);
@@ -874,7 +886,7 @@ extern "C" int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, 
   const int threads = c4n * (256 / c4n > 0 ? 256 / c4n : 1);
   const long long ppb = threads / c4n;
   const long long P = static_cast<long long>(d->H) * d->W;
-  long long gx = (P + ppb * 16 - 1) / (ppb * 16);
+  long long gx = (P + ppb * gn_ppt() - 1) / (ppb * gn_ppt());
   if (gx > 148 * 16) gx = 148 * 16;
   if (gx < 1) gx = 1;
   e = check_cuda(cudaMemsetAsync(g->gsum, 0, sizeof(double) * 2 * d->groups * d->batch, STREAM), "memset gsum");
