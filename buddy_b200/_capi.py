@@ -37,6 +37,8 @@ class GemmDesc(ctypes.Structure):
         ("b8", c_void_p),
         ("a8_2", c_void_p), ("a8_2_c", c_int), ("a8_2_stride_w", c_i64), ("a8_2_stride_h", c_i64),
         ("a8_2_stride_b", c_i64), ("b8_2", c_void_p), ("no_staged_epilogue", c_int), ("no_cta_pairs", c_int), ("debug_flags", c_int), ("one_tap_per_stage", c_int),
+        ("gnb_x", c_void_p), ("gnb_stats", c_void_p), ("gnb_gamma", c_void_p), ("gnb_beta", c_void_p),
+        ("gnb_gsum", c_void_p), ("gnb_groups", c_int), ("gnb_eps", c_float), ("gnb_silu", c_int),
     ]
 
 
@@ -100,5 +102,5 @@ class GnBwdDesc(ctypes.Structure):
         ("da", c_void_p), ("dskip", c_void_p), ("skip_scale", c_float),
         ("extra_a", c_void_p), ("extra_b", c_void_p), ("gsum", c_void_p),
         ("dxa", c_void_p), ("dxb", c_void_p), ("g16a", c_void_p), ("g16b", c_void_p), ("g16_scale", c_float),
-        ("g8a", c_void_p), ("g8b", c_void_p),
+        ("g8a", c_void_p), ("g8b", c_void_p), ("pass0_done", c_int),
     ]

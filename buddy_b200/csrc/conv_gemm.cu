@@ -56,6 +56,14 @@ struct GemmParams {
   float scale;
   double* stats;
   int dbg;         // profiling experiments only: 1 = epilogue only hands the accumulator back, 2 = + TMEM loads
+  // fused GroupNorm-backward statistics (see buddy_gemm_desc::gnb_*); gnb_x == nullptr: off
+  const float* gnb_x;
+  const double* gnb_stats;
+  const float* gnb_gamma;
+  const float* gnb_beta;
+  double* gnb_gsum;
+  int gnb_groups, gnb_cpg, gnb_silu;
+  float gnb_eps;
   int staged;      // 1: epilogue stages 128x32 fp32 chunks in shared memory and writes them with TMA stores
   int res_staged;  // 1: the residual is TMA-loaded into the staging buffer (needs staged)
 };
@@ -88,7 +96,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem_b = smem + p.stages_a * a_stage_bytes;
   uint8_t* stage_out = smem_b + p.stages_b * b_stage_bytes;
   float* bias_s = reinterpret_cast<float*>(stage_out + 2 * kChunkBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + (p.staged ? 2 * kChunkBytes + 1024 : 0));
+  float* gnb_s = bias_s + 256;   // [4][n_tile]: rstd, -mean*rstd, gamma, beta per output channel of this tile (gnb)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out +
+                                               (p.staged ? 2 * kChunkBytes + 1024 + (p.gnb_x ? 4096 : 0) : 0));
   uint64_t* a_full = bars;                       // [kMaxStagesA]
   uint64_t* a_empty = a_full + kMaxStagesA;      // [kMaxStagesA]
   uint64_t* b_full = a_empty + kMaxStagesA;      // [kMaxStagesB]
@@ -371,6 +381,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.bias) bv += __ldg(p.bias + ncol_base + i);
         if (p.bias_b && in_batch) bv += __ldg(p.bias_b + static_cast<long long>(b) * p.n_total + ncol_base + i);
         bias_s[i] = bv;
+        if (p.gnb_x) {
+          // GroupNorm statistics of x for this channel's group, from the fp64 bundle sums (as gn_apply does)
+          float rstd = 0.f, nmr = 0.f;
+          if (in_batch) {
+            const int ch = ncol_base + i;
+            const int g0 = (ch / p.gnb_cpg) * p.gnb_cpg;
+            double S = 0.0, Q = 0.0;
+            for (int c = g0; c < g0 + p.gnb_cpg; c += 4) {
+              const double* sp = p.gnb_stats + (static_cast<long long>(b) * (p.n_total >> 2) + (c >> 2)) * 2;
+              S += sp[0];
+              Q += sp[1];
+            }
+            const double n = static_cast<double>(p.gnb_cpg) * p.H * p.W;
+            const double mean = S / n;
+            double var = Q / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.gnb_eps)));
+            nmr = -static_cast<float>(mean) * rstd;
+          }
+          gnb_s[i] = rstd;
+          gnb_s[p.n_tile + i] = nmr;
+          gnb_s[2 * p.n_tile + i] = __ldg(p.gnb_gamma + ncol_base + i);
+          gnb_s[3 * p.n_tile + i] = __ldg(p.gnb_beta + ncol_base + i);
+        }
       }
       if (p.res_staged && elected) {
         // staging buffer cc&1 is free: the store that last read it was waited for before the previous chunk barrier
@@ -449,6 +483,62 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(srow + ((j ^ sw) << 4)) =
               make_float4(v[4 * j] * sc, v[4 * j + 1] * sc, v[4 * j + 2] * sc, v[4 * j + 3] * sc);
+        if (p.gnb_x && in_batch) {
+          // GroupNorm-backward pass 0 for the tensor this launch differentiates through: per 4-channel bundle of this
+          // thread's pixel, (sum dxh, sum dxh*xh); butterfly-reduced over the warp's 32 pixels (16 shuffles for the
+          // 16 values), one fp64 atomic pair per bundle per warp.
+          float part[16];
+          {
+            const long long pix = (static_cast<long long>(b) * p.H + (h0 + hl)) * p.W + (w0 + wl);
+            const float4* xp = reinterpret_cast<const float4*>(p.gnb_x + pix * p.n_total + ncol_base + c * 32);
+            const float* rs = gnb_s + c * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x4 = valid ? __ldg(xp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int cc = 4 * j + q;
+                const float xh = fmaf(xv[q], rs[cc], rs[p.n_tile + cc]);
+                const float gam = rs[2 * p.n_tile + cc];
+                float dz = v[cc] * sc;
+                if (p.gnb_silu) {
+                  const float z = fmaf(xh, gam, rs[3 * p.n_tile + cc]);
+                  const float sg = __fdividef(1.f, 1.f + __expf(-z));
+                  dz *= sg * fmaf(z, 1.f - sg, 1.f);
+                }
+                const float dxh = dz * gam;
+                s1 += dxh;
+                s2 = fmaf(dxh, xh, s2);
+              }
+              part[2 * j] = s1;
+              part[2 * j + 1] = s2;
+            }
+          }
+          // transpose-reduce: after the steps lane l holds the warp sum of value index (l >> 1) & 15
+#pragma unroll
+          for (int step = 0; step < 4; ++step) {
+            const int half = 8 >> step;              // values kept after this step
+            const int bit = 16 >> step;              // lane bit deciding which half is kept
+            const bool upper = (lane & bit) != 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i < half) {
+                const float keep = upper ? part[i + half] : part[i];
+                const float send = upper ? part[i] : part[i + half];
+                part[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+              }
+            }
+          }
+          part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
+          if ((lane & 1) == 0) {
+            const int vi = lane >> 1;                // value index 0..15 = 2 * bundle + {0: sum dxh, 1: sum dxh*xh}
+            const int ch = ncol_base + c * 32 + (vi >> 1) * 4;
+            atomicAdd(p.gnb_gsum + (static_cast<long long>(b) * p.gnb_groups + ch / p.gnb_cpg) * 2 + (vi & 1),
+                      static_cast<double>(part[0]));
+          }
+        }
         fence_proxy_async();
         if (elected) tma_store_wait_read0();   // the previous chunk's store no longer reads the other buffer
         named_bar_sync(1, kEpiThreads);
@@ -800,7 +890,15 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
                  ? 1
                  : 0;
   p.res_staged = (p.staged && d->resid) ? 1 : 0;
-  const int epi_bytes = p.staged ? 2 * kChunkBytes + 1024 : 0;
+  if (d->gnb_x) {
+    if (!p.staged || !d->gnb_stats || !d->gnb_gamma || !d->gnb_beta || !d->gnb_gsum || d->gnb_groups <= 0 ||
+        d->n_total % d->gnb_groups || (d->n_total / d->gnb_groups) % 4) {
+      set_last_error("buddy_conv_gemm: gnb_* needs the staged epilogue (dense fp32 output, n_tile %% 32 == 0) and "
+                     "channels-per-group a multiple of 4");
+      return BUDDY_ERR_UNSUPPORTED;
+    }
+  }
+  const int epi_bytes = p.staged ? 2 * kChunkBytes + 1024 + (d->gnb_x ? 4096 : 0) : 0;
   const int ring_bytes = 227 * 1024 - 1536 - epi_bytes;
   p.tpb = 1;
   if (p.halo) {
@@ -829,6 +927,15 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   p.scale = d->scale;
   p.stats = d->stats;
   p.dbg = d->debug_flags;
+  p.gnb_x = d->gnb_x;
+  p.gnb_stats = d->gnb_stats;
+  p.gnb_gamma = d->gnb_gamma;
+  p.gnb_beta = d->gnb_beta;
+  p.gnb_gsum = d->gnb_gsum;
+  p.gnb_groups = d->gnb_groups;
+  p.gnb_cpg = d->gnb_groups > 0 ? d->n_total / d->gnb_groups : 0;
+  p.gnb_silu = d->gnb_silu;
+  p.gnb_eps = d->gnb_eps;
 
   CUtensorMap tmA, tmB, tmA2, tmB2, tmA8, tmB8, tmA82, tmB82, tmOut, tmRes;
   p.kchunks8_1 = 0;

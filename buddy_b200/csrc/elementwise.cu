@@ -889,11 +889,16 @@ extern "C" int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, 
   long long gx = (P + ppb * gn_ppt() - 1) / (ppb * gn_ppt());
   if (gx > 148 * 16) gx = 148 * 16;
   if (gx < 1) gx = 1;
-  e = check_cuda(cudaMemsetAsync(g->gsum, 0, sizeof(double) * 2 * d->groups * d->batch, STREAM), "memset gsum");
-  if (e) return e;
-  gn_bwd_kernel<false><<<dim3((unsigned)gx, d->batch), threads, 0, STREAM>>>(a);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  BUDDY_CHECK_LAUNCH("gn_bwd_kernel<stats>");
+  if (!g->pass0_done) {
+    e = check_cuda(cudaMemsetAsync(g->gsum, 0, sizeof(double) * 2 * d->groups * d->batch, STREAM), "memset gsum");
+    if (e) return e;
+    gn_bwd_kernel<false><<<dim3((unsigned)gx, d->batch), threads, 0, STREAM>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    BUDDY_CHECK_LAUNCH("gn_bwd_kernel<stats>");
+  } else if (d->mode != 0 || d->xb) {
+    set_last_error("buddy_gn_bwd: pass0_done needs mode 0 and a single input tensor");
+    return BUDDY_ERR_INVALID;
+  }
   gn_bwd_kernel<true><<<dim3((unsigned)gx, d->batch), threads, 0, STREAM>>>(a);
   LAUNCH_END("gn_bwd_kernel<apply>");
 }

@@ -105,6 +105,12 @@ class Engine:
         self.c8 = precision in ("fp16c8", "mixed")
         self.mixed = precision == "mixed"
         self.x1_convs = set()   # (module index, conv index) of the single-pass convolutions (mixed mode)
+        import os
+        # BUDDY_FUSE_GNB=1 folds GroupNorm-backward's statistics pass into the producing dgrad convolution's epilogue
+        # where the geometry allows (no resample, single input tensor).  Correct (tests) but OFF by default: measured
+        # on B200 it removes 19 ms of GroupNorm time per B=32 step and adds 51 ms to the convolutions (the epilogue's
+        # exp/rcp work and x reads no longer hide behind the mainloop at the board's power cap): 398 -> 429 ms.
+        self.fuse_gnb = os.environ.get("BUDDY_FUSE_GNB", "0") == "1"
         self._graphs = {}
         self.graph_max_batch = 8    # larger batches are GPU-bound: plain launches (no pinned graph memory pool)
         self.split = 2 if self.c8 else (1 if self.np > 1 else 0)
@@ -346,14 +352,20 @@ class Engine:
         dev = self.device
         gsum = self._scratch_gsum(B)
         da1 = torch.empty(B, Ho, Wo, r.cout, device=dev)
-        self._conv(g16, r.wd1, da1, taps=9, n_total=r.cout)
+        fuse1 = self.fuse_gnb        # GroupNorm_1 sits directly under conv 1: always the same geometry
+        gsum1 = torch.zeros(B, 32, 2, device=dev, dtype=torch.float64) if fuse1 else gsum
+        self._conv(g16, r.wd1, da1, taps=9, n_total=r.cout,
+                   gnb=(h1, s1, r.g1, r.b1, gsum1, 32, 1e-6, 1) if fuse1 else None)
         dh1 = self._operand(B, Ho, Wo, r.cout, self._gscale(("h1", i)), need8=not r.x1[0])
-        ops.gn_bwd(h1, s1, r.g1, r.b1, da1, gsum, silu=True, g16a=dh1.t16, g16_scale=dh1.gs, split=self.split,
-                   g8a=dh1.t8)
+        ops.gn_bwd(h1, s1, r.g1, r.b1, da1, gsum1, silu=True, g16a=dh1.t16, g16_scale=dh1.gs, split=self.split,
+                   g8a=dh1.t8, pass0_done=fuse1)
         self._record(("h1", i), dh1)
         del da1
         da0 = torch.empty(B, Ho, Wo, r.cin, device=dev)
-        self._conv(dh1, r.wd0, da0, taps=9, n_total=r.cin)
+        fuse0 = self.fuse_gnb and mode == MODE_NONE and xb is None     # GroupNorm_0 of a plain block
+        gsum0 = torch.zeros(B, 32, 2, device=dev, dtype=torch.float64) if fuse0 else gsum
+        self._conv(dh1, r.wd0, da0, taps=9, n_total=r.cin,
+                   gnb=(xa, sa, r.g0, r.b0, gsum0, 32, 1e-6, 1) if fuse0 else None)
         del dh1
         if r.has_skip_conv:
             dsk = torch.empty(B, Ho, Wo, r.cin, device=dev)
@@ -366,9 +378,10 @@ class Engine:
         g16a = (self._operand(*xa.shape[:3], Ca, self._gscale(("x", i)), need8=not self._x1(consumer, 1))
                 if want_a16 else None)
         dxb = torch.empty_like(xb) if xb is not None else None
-        ops.gn_bwd(xa, sa, r.g0, r.b0, da0, gsum, xb=xb, sb=sb, silu=True, mode=mode, dskip=dsk, skip_scale=skip_scale,
+        ops.gn_bwd(xa, sa, r.g0, r.b0, da0, gsum0, xb=xb, sb=sb, silu=True, mode=mode, dskip=dsk, skip_scale=skip_scale,
                    extra_a=extra_a, dxa=dxa, dxb=dxb, g16a=g16a.t16 if g16a else None,
-                   g16_scale=a16_scale * (g16a.gs if g16a else 1.0), split=self.split, g8a=g16a.t8 if g16a else None)
+                   g16_scale=a16_scale * (g16a.gs if g16a else 1.0), split=self.split, g8a=g16a.t8 if g16a else None,
+                   pass0_done=fuse0)
         if g16a:
             self._record(("x", i), g16a)
         return dxa, g16a, dxb

@@ -24,7 +24,7 @@ def _pick_n_tile(n_total):
 
 def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=None, bias_b=None, resid=None,
               scale=1.0, stats=None, b_batched=False, col_off=0, ldc=None, max_ctas=0, passes=1, a8=None, w8=None,
-              a8_2=None, w8_2=None, direct_epilogue=False, no_pairs=False, debug_flags=0, one_tap_per_stage=False):
+              a8_2=None, w8_2=None, direct_epilogue=False, no_pairs=False, debug_flags=0, one_tap_per_stage=False, gnb=None):
     """out[b,h,w,n] = scale*(sum_{tap,k} a[b,h+dy,w+dx,k] w[tap,n,k] + sum_k a2[b,h,w,k] w2[n,k] + bias + bias_b + resid).
 
     a, a2 : fp16 [B,H,W,C] (channel stride 1, other strides arbitrary multiples of 8 elements)
@@ -76,6 +76,13 @@ def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=N
     d.no_cta_pairs = 1 if no_pairs else 0
     d.debug_flags = int(debug_flags)
     d.one_tap_per_stage = 1 if one_tap_per_stage else 0
+    if gnb is not None:
+        # (x, bundle stats of x, gamma, beta, gsum out, groups, eps, silu): fused GroupNorm-backward statistics
+        gx, gstats, ggam, gbet, ggsum, ggroups, geps, gsilu = gnb
+        assert gx.dtype == torch.float32 and gx.is_contiguous() and tuple(gx.shape) == (B, H, W, n_total)
+        assert ggsum.dtype == torch.float64 and tuple(ggsum.shape) == (B, ggroups, 2)
+        d.gnb_x, d.gnb_stats, d.gnb_gamma, d.gnb_beta, d.gnb_gsum = ptr(gx), ptr(gstats), ptr(ggam), ptr(gbet), ptr(ggsum)
+        d.gnb_groups, d.gnb_eps, d.gnb_silu = int(ggroups), float(geps), int(gsilu)
     if a8 is not None:
         assert a8.dtype == torch.uint8 and w8.dtype == torch.uint8 and a8.shape[:3] == a.shape[:3]
         assert w8.is_contiguous() and w8.shape[:2] == w.shape[:2] and w8.shape[2] == a8.shape[3]
@@ -140,13 +147,14 @@ def gn_apply(xa, sa, gamma, beta, out, *, xb=None, sb=None, groups=32, silu=True
 
 def gn_bwd(xa, sa, gamma, beta, da, gsum, *, xb=None, sb=None, groups=32, silu=True, mode=MODE_NONE, dskip=None,
            skip_scale=1.0, extra_a=None, extra_b=None, dxa=None, dxb=None, g16a=None, g16b=None, g16_scale=1.0,
-           eps=1e-6, split=False, g8a=None, g8b=None):
+           eps=1e-6, split=False, g8a=None, g8b=None, pass0_done=False):
     d = _gn_desc(xa, sa, xb, sb, gamma, beta, groups, silu, mode, eps, split)
     g = GnBwdDesc()
     g.da, g.dskip, g.skip_scale = ptr(da), ptr(dskip), skip_scale
     g.extra_a, g.extra_b, g.gsum = ptr(extra_a), ptr(extra_b), ptr(gsum)
     g.dxa, g.dxb, g.g16a, g.g16b, g.g16_scale = ptr(dxa), ptr(dxb), ptr(g16a), ptr(g16b), g16_scale
     g.g8a, g.g8b = ptr(g8a), ptr(g8b)
+    g.pass0_done = 1 if pass0_done else 0
     assert da.dtype == torch.float32 and gsum.dtype == torch.float64
     check(lib().buddy_gn_bwd(ctypes.byref(d), ctypes.byref(g), stream_ptr()), "buddy_gn_bwd")
 

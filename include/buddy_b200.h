@@ -112,6 +112,22 @@ typedef struct buddy_gemm_desc {
   int32_t debug_flags;
   /* 1 = one weight tile per pipeline stage even where a kernel row of three fits (testing / A-B timing only) */
   int32_t one_tap_per_stage;
+  /* Fused GroupNorm-backward statistics (staged epilogue only).  When this launch is the data-gradient convolution
+   * whose output `da` is the gradient w.r.t. act(GroupNorm(x)) of a tensor x of the SAME geometry (no resampling in
+   * between, single tensor), the epilogue also accumulates, per (image, group),
+   *     gnb_gsum[b][g][0] += sum dxh,  gnb_gsum[b][g][1] += sum dxh * xh,
+   *     xh = (x - mean_g) * rstd_g,  dxh = da * act'(xh * gamma + beta) * gamma
+   * i.e. pass 0 of buddy_gn_bwd (which is then called with pass0_done = 1): the statistics pass' 8 bytes per element
+   * of HBM reads disappear behind the tensor-core mainloop.  gnb_stats = bundle sums of x (as for buddy_gn_apply),
+   * gnb_gsum fp64 [batch][gnb_groups][2], zeroed by the caller. */
+  const float* gnb_x; /* NULL = off */
+  const double* gnb_stats;
+  const float* gnb_gamma;
+  const float* gnb_beta;
+  double* gnb_gsum;
+  int32_t gnb_groups;
+  float gnb_eps;
+  int32_t gnb_silu;
 } buddy_gemm_desc;
 
 int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream);
@@ -155,7 +171,7 @@ typedef struct buddy_gn_bwd_desc {
   float skip_scale;
   const float* extra_a; /* optional fp32 [batch][H][W][Ca] added to dxa */
   const float* extra_b; /* optional fp32 [batch][H][W][Cb] added to dxb */
-  double* gsum;         /* scratch fp64 [batch][groups][2] (zeroed by the call) */
+  double* gsum;         /* scratch fp64 [batch][groups][2] (zeroed by the call unless pass0_done) */
   float* dxa;           /* optional fp32 out [batch][H][W][Ca] */
   float* dxb;           /* optional fp32 out [batch][H][W][Cb] */
   void* g16a;           /* optional fp16 out = dxa * g16_scale (dgrad operand of the producer) */
@@ -163,6 +179,7 @@ typedef struct buddy_gn_bwd_desc {
   float g16_scale;
   void* g8a; /* e4m3 pairs of g16a / g16b when the gn desc has split == 2 */
   void* g8b;
+  int32_t pass0_done; /* 1: gsum already holds the group sums (buddy_conv_gemm's gnb_* epilogue): skip pass 0 */
 } buddy_gn_bwd_desc;
 
 int buddy_gn_stats(const float* x, int batch, int64_t pixels, int C, double* stats /* += */, void* stream);

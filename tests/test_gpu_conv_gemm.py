@@ -226,3 +226,30 @@ def test_cta_pairs_match_single_cta(B, H, W, C, N, c8):
     assert not torch.isnan(outs[1]).any()
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert rel(sts[1], sts[0]) < 1e-9 and rel(sts[2], sts[0]) < 1e-9
+
+
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 16, 24, 64, 128), (3, 19, 37, 128, 256), (1, 40, 50, 64, 384)])
+def test_fused_groupnorm_backward_statistics(B, H, W, C, N):
+    """The dgrad epilogue's fused GroupNorm-backward statistics (pass 0 of buddy_gn_bwd) give the same input gradient as
+    the two-pass kernel: conv -> da, then dx = GN/SiLU backward of x under da, with and without the fused pass."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    a = torch.randn(B, H, W, C, device="cuda", generator=g).half()
+    w = (torch.randn(9, N, C, device="cuda", generator=g) * 0.05).half()
+    x = torch.randn(B, H, W, N, device="cuda", generator=g) * 1.5 + 0.3
+    gamma = 1.0 + 0.2 * torch.randn(N, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(N, device="cuda", generator=g)
+    sx = ops.gn_stats(x)
+    outs = []
+    for fused in (False, True):
+        da = torch.empty(B, H, W, N, device="cuda")
+        gsum = torch.zeros(B, 32, 2, device="cuda", dtype=torch.float64)
+        ops.conv_gemm(a, w, da, taps=9, n_total=N, scale=0.37,
+                      gnb=(x, sx, gamma, beta, gsum, 32, 1e-6, 1) if fused else None)
+        dx = torch.empty_like(x)
+        ops.gn_bwd(x, sx, gamma, beta, da, gsum, silu=True, dxa=dx, pass0_done=fused)
+        outs.append((da, gsum.clone(), dx))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert rel(outs[1][1], outs[0][1]) < 1e-5, rel(outs[1][1], outs[0][1])
+    assert rel(outs[1][2], outs[0][2]) < 1e-6, rel(outs[1][2], outs[0][2])
