@@ -14,7 +14,7 @@ import math
 import torch
 
 from . import ops
-from .spectral import LossSTFT, _dft_mats
+from .spectral import LossSTFT, _dft_mats, _use_fft, irfft_weights
 
 EQ_FREQS = [0, 125, 250, 375, 500, 625, 750, 875, 1000, 1250, 1500, 1750, 2000, 2250, 2500, 2750, 3000, 3500, 4000,
             4500, 5000, 5500, 6000, 6500, 7000, 7500, 8000]
@@ -39,10 +39,16 @@ class BlindEngine:
         self.loss_stft = LossSTFT(dev)
         w = torch.hann_window(self.WIN, dtype=torch.float64)
         norm = math.sqrt(float((w ** 2).sum()))
-        ana, syn = _dft_mats(self.NFFT, self.F, w, self.WIN, "cpu")
-        self.cons_ana = ana.to(dev).contiguous()                               # stft, not normalised
-        self.cons_syn = syn.to(dev).contiguous()                               # istft (irfft * window)
-        self.istft_syn = (syn.double() * norm).float().to(dev).contiguous()    # apply_istft: X * sqrt(sum w^2) first
+        if _use_fft():
+            aw = irfft_weights(self.F, self.NFFT)
+            self.cons_ana = ops.FftMat(torch.ones(self.F, dtype=torch.float64), w, dev)   # stft, not normalised
+            self.cons_syn = ops.FftMat(aw, w, dev)                                         # istft (irfft * window)
+            self.istft_syn = ops.FftMat(aw * norm, w, dev)                                 # apply_istft: X * sqrt(sum w^2)
+        else:
+            ana, syn = _dft_mats(self.NFFT, self.F, w, self.WIN, "cpu")
+            self.cons_ana = ana.to(dev).contiguous()                               # stft, not normalised
+            self.cons_syn = syn.to(dev).contiguous()                               # istft (irfft * window)
+            self.istft_syn = (syn.double() * norm).float().to(dev).contiguous()    # apply_istft: X * sqrt(sum w^2) first
         # interpolation tables 27 knots -> 513 bins (torchcde stand-in: piecewise linear)
         freqs = torch.fft.rfftfreq(self.NFFT, d=1 / sample_rate)
         knots = torch.tensor(g("EQ_freqs", EQ_FREQS), dtype=torch.float32)
@@ -137,7 +143,7 @@ class BlindEngine:
         B, N, T = st["B"], self.N_BIG, self.T_MP
         ops.blind_design_fwd(st["decays"], st["weights"], st["phases"], self.tabs, bf["A"], bf["H0"])
         fr = torch.empty(B, self.NF + 2, self.WIN, device=self.device)
-        ops.dft_synthesis(bf["H0"], self.cons_syn, self.NF + 2, fr)
+        ops.stft_synthesis(bf["H0"], self.cons_syn, self.NF + 2, fr)
         ops.ola_gather(fr, self.HOP, self.NFFT // 2, self.LEN_RIR, bf["u"], tab=self._inv_env(self.NF + 2))
         ops.fft_mixed(bf["u"], True, bf["work"], bf["Hf"], self.N1, -1, self.tw512)
         ops.minphase_pw(0, B, N, T, c0=bf["Hf"], or0=bf["m"], oc=bf["c1"])
@@ -150,7 +156,7 @@ class BlindEngine:
         ops.minphase_pw(3, B, N, T, c0=bf["c2"], r0=self.direct, or0=h2)
         ops.pad_signal(h2, 384, 384 + T, 0, bf["sig"])
         H = torch.empty(B, self.F, self.NF, 2, device=self.device)
-        ops.dft_analysis(bf["sig"], self.cons_ana, self.HOP, self.NF, self.NF, H)
+        ops.stft_analysis(bf["sig"], self.cons_ana, self.HOP, self.NF, self.NF, H)
         st["H"].copy_(H)
         return H
 
@@ -160,7 +166,7 @@ class BlindEngine:
         B, N, T = st["B"], self.N_BIG, self.T_MP
         dev = self.device
         fr = torch.empty(B, self.NF, self.WIN, device=dev)
-        ops.dft_synthesis(dH, self.cons_ana, self.NF, fr)
+        ops.stft_synthesis(dH, self.cons_ana, self.NF, fr)
         dh2 = torch.empty(B, T, device=dev)
         ops.ola_gather(fr, self.HOP, 384, T, dh2)
         gz = bf["r1"]
@@ -181,7 +187,7 @@ class BlindEngine:
         dpad = torch.empty(B, total, device=dev)
         ops.pad_signal(dh[:, :self.LEN_RIR], self.NFFT // 2, total, 0, dpad, tab=self._inv_env(frames))
         dH0 = torch.empty(B, self.F, frames, 2, device=dev)
-        ops.dft_analysis(dpad, self.cons_syn, self.HOP, frames, frames, dH0)
+        ops.stft_analysis(dpad, self.cons_syn, self.HOP, frames, frames, dH0)
         dph = torch.empty_like(st["phases"])
         dd, dw = torch.empty_like(st["decays"]), torch.empty_like(st["weights"])
         ops.blind_design_bwd(st["decays"], st["weights"], st["phases"], bf["A"], self.tabs, dH0, dph, dd, dw)
@@ -191,7 +197,7 @@ class BlindEngine:
     def apply_istft(self, Ys, n):
         B, _, frames, _ = Ys.shape
         fr = torch.empty(B, frames, self.WIN, device=self.device)
-        ops.dft_synthesis(Ys, self.istft_syn, frames, fr)
+        ops.stft_synthesis(Ys, self.istft_syn, frames, fr)
         out = torch.empty(B, n, device=self.device)
         return ops.ola_gather(fr, self.HOP, self.NFFT // 2 + self.WIN // 2, n, out, tab=self._inv_env(frames))
 
@@ -202,7 +208,7 @@ class BlindEngine:
         gp = torch.empty(B, total, device=self.device)
         ops.pad_signal(g, self.NFFT // 2 + self.WIN // 2, total, 0, gp, tab=self._inv_env(frames))
         out = torch.empty(B, self.F, frames, 2, device=self.device)
-        return ops.dft_analysis(gp, self.istft_syn, self.HOP, frames, frames, out)
+        return ops.stft_analysis(gp, self.istft_syn, self.HOP, frames, frames, out)
 
     def degradation_from_stft(self, X, H, n):
         Ys = ops.subband_fir(X, H, torch.empty_like(X), Nf=self.NF, pre=1, mode=0)

@@ -256,6 +256,50 @@ def dft_synthesis(S, mat, frames, fr):
     return fr
 
 
+class FftMat:
+    """The 1024-point STFT matrix mat[2f+c][n] = a[f] * w[n] * (cos, -sin)(2 pi f n / 1024) in factored form."""
+    __slots__ = ("a", "w", "tw")
+
+    def __init__(self, a, w, device):
+        import math
+        self.a = torch.as_tensor(a, dtype=torch.float64).float().to(device).contiguous()
+        self.w = torch.as_tensor(w, dtype=torch.float64).float().to(device).contiguous()
+        k = torch.arange(512, dtype=torch.float64)
+        self.tw = torch.stack([torch.cos(2 * math.pi * k / 1024), -torch.sin(2 * math.pi * k / 1024)], -1).float().to(
+            device).contiguous()
+
+
+def stft_analysis(sig, m, hop, frames, Tout, out):
+    """dft_analysis or fft_analysis depending on the matrix representation (`FftMat` = factored 1024-point form)."""
+    if isinstance(m, FftMat):
+        return fft_analysis(sig, m, hop, frames, Tout, out)
+    return dft_analysis(sig, m, hop, frames, Tout, out)
+
+
+def stft_synthesis(S, m, frames, fr):
+    if isinstance(m, FftMat):
+        return fft_synthesis(S, m, frames, fr)
+    return dft_synthesis(S, m, frames, fr)
+
+
+def fft_analysis(sig, fm, hop, frames, Tout, out):
+    """sig fp32 [B, L]; out fp32 [B, bins, Tout, 2] = a[f] * FFT_1024(w * frame)[f]."""
+    B = sig.shape[0]
+    check(lib().buddy_fft_analysis(ptr(sig), c_i64(sig.stride(0)), c_int(B), ptr(fm.w), ptr(fm.a), ptr(fm.tw),
+                                   c_int(fm.a.numel()), c_int(fm.w.numel()), c_int(hop), c_int(frames), c_int(Tout),
+                                   ptr(out), stream_ptr()), "buddy_fft_analysis")
+    return out
+
+
+def fft_synthesis(S, fm, frames, fr):
+    """S fp32 [B, bins, Tin, 2]; fr fp32 [B, frames, K] = w[n] * Re(sum_f a[f] S[f] e^{+2 pi i f n / 1024})."""
+    B, _, Tin, _ = S.shape
+    check(lib().buddy_fft_synthesis(ptr(S), c_int(B), c_int(Tin), ptr(fm.w), ptr(fm.a), ptr(fm.tw),
+                                    c_int(fm.a.numel()), c_int(fm.w.numel()), c_int(frames), ptr(fr), stream_ptr()),
+          "buddy_fft_synthesis")
+    return fr
+
+
 def ola_gather(fr, hop, off, n_out, out, tab=None, scale_b=None):
     B, frames, K = fr.shape
     check(lib().buddy_ola_gather(ptr(fr), c_int(B), c_int(frames), c_int(K), c_int(hop), c_int(off), c_int(n_out),
@@ -427,7 +471,7 @@ def _timed(fn, work_fn=None, tag_fn=_shape_tag):
 
 conv_gemm = _timed(conv_gemm, _conv_flops, _conv_tag)
 for _n in ("gn_stats", "gn_apply", "gn_bwd", "im2col_c2", "col2im_c2", "resample_c2", "combine_fwd", "combine_bwd",
-           "affine_c2", "softmax_fwd", "softmax_bwd", "transpose_h", "cast_scale_h", "dft_analysis", "dft_synthesis",
+           "affine_c2", "softmax_fwd", "softmax_bwd", "transpose_h", "cast_scale_h", "dft_analysis", "dft_synthesis", "fft_analysis", "fft_synthesis",
            "ola_gather", "pad_signal", "reflect_fold", "comp_loss", "row_stats", "fftconv", "fourier_features",
            "dense", "philox_normal", "lincomb3"):
     globals()[_n] = _timed(globals()[_n])

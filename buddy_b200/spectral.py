@@ -14,6 +14,22 @@ import torch
 from . import ops
 
 
+def _use_fft():
+    """1024-point transforms (likelihood STFT, blind operator) as shared-memory FFTs (default) or as DFT-matrix
+    products (BUDDY_STFT=dft: the round-1 first implementation, kept for A/B tests).  Same linear maps."""
+    import os
+    return os.environ.get("BUDDY_STFT", "fft") != "dft"
+
+
+def irfft_weights(bins, n_fft):
+    """onesided -> real synthesis weights: 1 for DC (and Nyquist), 2 elsewhere, / n_fft."""
+    a = torch.full((bins,), 2.0, dtype=torch.float64)
+    a[0] = 1.0
+    if n_fft % 2 == 0 and bins == n_fft // 2 + 1:
+        a[-1] = 1.0
+    return a / n_fft
+
+
 def _dft_mats(n_fft, bins, window, k_len, device):
     """analysis [2*bins, k_len]: (w cos, -w sin); synthesis [2*bins, k_len]: irfft weights * window."""
     n = torch.arange(k_len, dtype=torch.float64)
@@ -108,8 +124,11 @@ class LossSTFT:
         self.device = device
         w = torch.hann_window(self.WIN, dtype=torch.float64)
         norm = math.sqrt(float((w ** 2).sum()))
-        ana, _ = _dft_mats(self.N_FFT, self.BINS, w, self.WIN, "cpu")
-        self.ana = (ana.double() / norm).float().to(device).contiguous()
+        if _use_fft():
+            self.ana = ops.FftMat(torch.full((self.BINS,), 1.0 / norm, dtype=torch.float64), w, device)
+        else:
+            ana, _ = _dft_mats(self.N_FFT, self.BINS, w, self.WIN, "cpu")
+            self.ana = (ana.double() / norm).float().to(device).contiguous()
 
     def frames(self, n):
         return 1 + (n + self.WIN) // self.HOP
@@ -122,13 +141,13 @@ class LossSTFT:
         xp = torch.empty(B, total, device=x.device)
         ops.pad_signal(x, self.N_FFT // 2, total, 0, xp)
         out = torch.empty(B, self.BINS, F, 2, device=x.device)
-        return ops.dft_analysis(xp, self.ana, self.HOP, F, F, out)
+        return ops.stft_analysis(xp, self.ana, self.HOP, F, F, out)
 
     def adjoint(self, G, n, scale_b=None):
         """adjoint of `forward`: [B, 513, frames, 2] -> fp32 [B, n]."""
         B, _, F, _ = G.shape
         fr = torch.empty(B, F, self.WIN, device=G.device)
-        ops.dft_synthesis(G, self.ana, F, fr)
+        ops.stft_synthesis(G, self.ana, F, fr)
         out = torch.empty(B, n, device=G.device)
         return ops.ola_gather(fr, self.HOP, self.N_FFT // 2, n, out, scale_b=scale_b)
 

@@ -230,6 +230,13 @@ int buddy_dft_analysis(const float* sig, int64_t sig_ld, int batch, const float*
                        int frames, int Tout, float* out, void* stream);
 int buddy_dft_synthesis(const float* S, int batch, int Tin, const float* mat, int M, int K, int frames, float* fr,
                         void* stream);
+/* The same two maps for the 1024-point transforms (likelihood STFT, blind operator: subband_filtering.py:41-65) as
+ * shared-memory FFTs: mat[2f+c][n] == av[f] * wv[n] * (cos, -sin)(2 pi f n / 1024); tw1024 = exp(-2 pi i k / 1024),
+ * k < 512, as float2.  ~20x fewer FLOPs than the DFT-matrix form and lower rounding error. */
+int buddy_fft_analysis(const float* sig, int64_t sig_ld, int batch, const float* wv, const float* av,
+                       const float* tw1024, int bins, int K, int hop, int frames, int Tout, float* out, void* stream);
+int buddy_fft_synthesis(const float* S, int batch, int Tin, const float* wv, const float* av, const float* tw1024,
+                        int bins, int K, int frames, float* fr, void* stream);
 int buddy_ola_gather(const float* fr, int batch, int frames, int K, int hop, int off, int n_out, const float* tab,
                      const float* scale_b, float* out, int64_t out_ld, void* stream);
 int buddy_pad_signal(const float* x, int64_t x_ld, int batch, int N, int left, int total, int mode, const float* tab,

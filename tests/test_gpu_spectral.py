@@ -128,3 +128,34 @@ def test_temb_philox_lincomb_rowstats():
     assert rel(o, ca[:, None] * x + cb[:, None] * y_) < 1e-6
     st = ops.row_stats(x)
     assert rel(st[:, 0], x.double().sum(1)) < 1e-9 and rel(st[:, 1], (x.double() ** 2).sum(1)) < 1e-9
+
+
+@pytest.mark.parametrize("frames,K", [(517, 512), (113, 512), (7, 512), (33, 1024)])
+def test_fft_stft_kernels_match_dft_matrix_form(frames, K):
+    """1024-point FFT analysis / synthesis == the DFT-matrix kernels with mat = a[f] * w[n] * (cos, -sin) (and both ==
+    fp64 torch): arbitrary per-bin weights a, window w of length K, ragged frame counts (16 frames per CTA)."""
+    import math
+    from buddy_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, bins, hop = 3, 513, 128
+    a = torch.rand(bins, device="cuda", generator=g).double() + 0.5
+    w = torch.rand(K, device="cuda", generator=g).double()
+    n = torch.arange(K, device="cuda", dtype=torch.float64)
+    f = torch.arange(bins, device="cuda", dtype=torch.float64)
+    ang = 2 * math.pi * torch.outer(f, n) / 1024
+    mat = torch.empty(2 * bins, K, device="cuda", dtype=torch.float64)
+    mat[0::2] = a[:, None] * torch.cos(ang) * w
+    mat[1::2] = -a[:, None] * torch.sin(ang) * w
+    fm = ops.FftMat(a.cpu(), w.cpu(), "cuda")
+    L = (frames - 1) * hop + K
+    sig = torch.randn(B, L, device="cuda", generator=g)
+    out_f = ops.fft_analysis(sig, fm, hop, frames, frames, torch.empty(B, bins, frames, 2, device="cuda"))
+    out_d = ops.dft_analysis(sig, mat.float().contiguous(), hop, frames, frames, torch.empty(B, bins, frames, 2, device="cuda"))
+    fr64 = sig.double().unfold(1, K, hop)                                # [B, frames, K]
+    ref = torch.einsum("mk,btk->bmt", mat, fr64).reshape(B, bins, 2, frames).permute(0, 1, 3, 2)
+    assert rel(out_f, ref) < 2e-6 and rel(out_d, ref) < 1e-5, (rel(out_f, ref), rel(out_d, ref))
+    S = torch.randn(B, bins, frames, 2, device="cuda", generator=g)
+    fr_f = ops.fft_synthesis(S, fm, frames, torch.empty(B, frames, K, device="cuda"))
+    fr_d = ops.dft_synthesis(S, mat.float().contiguous(), frames, torch.empty(B, frames, K, device="cuda"))
+    ref_s = torch.einsum("bmt,mk->btk", S.double().permute(0, 1, 3, 2).reshape(B, 2 * bins, frames), mat)
+    assert rel(fr_f, ref_s) < 2e-6 and rel(fr_d, ref_s) < 1e-5, (rel(fr_f, ref_s), rel(fr_d, ref_s))
