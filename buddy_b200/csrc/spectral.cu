@@ -433,7 +433,7 @@ static int grid1(long long items, int threads, int cap = 148 * 8) {
 //   synthesis: fr[b][t][n]  = w[n] * Re( sum_f a[f] S[b][f][t] e^{+2 pi i f n / 1024} )
 // ------------------------------------------------------------------------------------------------
 constexpr int kFftN = 1024;
-constexpr int kFftFrames = 16;
+constexpr int kFftFrames = 8;   // 68 KB of shared memory per CTA: three CTAs per SM hide the stage barriers
 __device__ __forceinline__ int bitrev10(int k) { return static_cast<int>(__brev(static_cast<unsigned>(k)) >> 22); }
 // in-place radix-2 decimation-in-frequency over `kFftFrames` frames [frame][1024] (natural order in, bit-reversed
 // out); tw[k] = exp(-2 pi i k / 1024), k < 512; conj_tw: inverse transform (unnormalised)
@@ -475,7 +475,7 @@ fft_analysis_kernel(const float* __restrict__ sig, long long sig_ld, const float
   fft1024_dif(s, tw, false);
   float2* ob = out + static_cast<long long>(b) * bins * Tout;
   for (int i = threadIdx.x; i < bins * kFftFrames; i += blockDim.x) {
-    const int f = i >> 4, fr = i & 15;
+    const int f = i / kFftFrames, fr = i % kFftFrames;
     const int t = t0 + fr;
     if (t >= Tout) continue;
     float2 v = make_float2(0.f, 0.f);
@@ -499,7 +499,7 @@ fft_synthesis_kernel(const float2* __restrict__ S, int Tin, const float* __restr
   for (int i = threadIdx.x; i < 512; i += blockDim.x) tw[i] = tw_g[i];
   const float2* Sb = S + static_cast<long long>(b) * bins * Tin;
   for (int i = threadIdx.x; i < kFftFrames * kFftN; i += blockDim.x) {
-    const int f = i >> 4, fr = i & 15;     // frames fastest: 128-byte global segments per bin
+    const int f = i / kFftFrames, fr = i % kFftFrames;     // frames fastest: contiguous global segments per bin
     const int t = t0 + fr;
     float2 v = make_float2(0.f, 0.f);
     if (f < bins && t < frames) {
