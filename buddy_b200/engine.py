@@ -39,14 +39,6 @@ def _split_k(w, passes):
     return torch.cat([hi, hi, lo], dim=-1).contiguous()
 
 
-def _pack3x3(w, passes):
-    """[Cout, Cin, 3, 3] -> fwd B operand [9, Cout, p*Cin] and dgrad B operand [9, Cin, p*Cout] (taps flipped)."""
-    co, ci = w.shape[:2]
-    fwd = w.permute(2, 3, 0, 1).reshape(9, co, ci)
-    dgr = w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, ci, co)
-    return _split_k(fwd, passes), _split_k(dgr, passes)
-
-
 def _pad_rows(w, rows):
     if w.shape[-2] >= rows:
         return w
@@ -113,6 +105,7 @@ class Engine:
         self.fuse_gnb = os.environ.get("BUDDY_FUSE_GNB", "0") == "1"
         self._graphs = {}
         self.graph_max_batch = 8    # larger batches are GPU-bound: plain launches (no pinned graph memory pool)
+        self.graph_cache_size = 4   # captured shapes kept (oldest evicted)
         self.split = 2 if self.c8 else (1 if self.np > 1 else 0)
         self.am = 2 if self.split == 1 else 1
         self.gs = {}            # per-call-site power-of-two scales of the gradient operands (fp16c8)
@@ -510,6 +503,8 @@ class Engine:
             ent["bwd"] = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ent["bwd"], pool=pool):
                 ent["dx"] = self._vjp_impl(ent["ctx"], ent["dout"])
+        while len(self._graphs) >= self.graph_cache_size:        # each entry pins its activations: keep a few shapes
+            self._graphs.pop(next(iter(self._graphs)))
         self._graphs[key] = ent
         return ent
 
