@@ -229,6 +229,7 @@ def run_ours(args):
     smp.utterance_offset = rank * B
     smp.micro_batch = args.micro_batch
     smp.n_streams = args.streams
+    smp.use_graphs = not args.no_graphs
     if blind:
         # reference initialisation (tester.py:149-151): T60 = 0.1 s, weight 2, phases of coherent noise, per utterance
         from buddy_b200.blind import BlindEngine
@@ -415,6 +416,7 @@ def main():
     ap.add_argument("--streams", type=int, default=1, help="micro-batches in flight on separate CUDA streams")
     ap.add_argument("--precision", default=os.environ.get("BUDDY_PRECISION", "mixed"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="plain launches even for batches <= 8 (profiling)")
     ap.add_argument("--mode", default="informed", choices=["informed", "blind", "long"],
                     help="informed = BASELINE configs[1] (default, the bench line); blind = configs[2] (order 1, T=60, "
                          "10 operator-Adam iterations per step); long = configs[4] (30 s utterances, batch 16)")
