@@ -111,12 +111,12 @@ class _FShim:
         return patched_conv2d if k == "conv2d" else getattr(F, k)
 
 
-def run(frames=80):
-    torch.manual_seed(0)
-    sd = make_state_dict(0)
-    g = torch.Generator().manual_seed(1)
+def run(frames=80, seed=0, sigma=0.1):
+    torch.manual_seed(seed)
+    sd = make_state_dict(seed)
+    g = torch.Generator().manual_seed(1 + seed)
     spec = torch.complex(torch.randn(1, 1, 256, frames, generator=g), torch.randn(1, 1, 256, frames, generator=g)) * 3.0
-    tc = torch.tensor([0.25 * math.log(0.1)])
+    tc = torch.tensor([0.25 * math.log(sigma)])
     cot = torch.randn(1, 2, 256, frames, generator=g)
 
     def evaluate():
@@ -147,6 +147,8 @@ def run(frames=80):
         "C: top5 x1 fwd / a8 bwd, rest c8": lambda H, d: (x1 if d == "fwd" else a8) if big(H) else c8,
         "D: top5+mid x1, rest c8": lambda H, d: x1 if (big(H) or mid(H)) else c8,
     }
+    if seed != 0:
+        policies = {"all x1": lambda H, d: x1, "all c8": lambda H, d: c8, "A: top5 x1, rest c8": policies["A: top5 x1, rest c8"]}
     for name, pol in policies.items():
         SCHEME["policy"] = pol
         COST["flops"] = COST["passes"] = 0.0
@@ -157,4 +159,5 @@ def run(frames=80):
 
 
 if __name__ == "__main__":
-    run(int(sys.argv[1]) if len(sys.argv) > 1 else 80)
+    run(int(sys.argv[1]) if len(sys.argv) > 1 else 80, int(sys.argv[2]) if len(sys.argv) > 2 else 0,
+        float(sys.argv[3]) if len(sys.argv) > 3 else 0.1)
