@@ -1,16 +1,23 @@
 // Implicit-GEMM 3x3 / 1x1 convolution and batched GEMM for sm_100a.
 //
-//   * operands: fp16, channels-last; fp32 accumulation in TMEM (tcgen05.mma kind::f16, M=128, N<=256, K=16)
-//   * A tile  : TMA 4-D tiled load of a (bh x bw) pixel patch x 64 channels, shifted by the filter tap;
-//               out-of-image coordinates are zero-filled by TMA == the conv's "same" padding, so no im2col
-//               buffer and no halo logic exist anywhere.
-//   * B tile  : TMA 3-D load of [n_tile rows][64 k] of the packed weights for (tap, k-chunk)
+//   * operands: fp16 (+ optional e4m3 correction pair), channels-last; fp32 accumulation in TMEM
+//     (tcgen05.mma kind::f16 K=16 / kind::f8f6f4 K=32, N <= 256)
+//   * CTA pairs: two CTAs of a 2-CTA cluster share a 256-row tile pair (cta_group::2, M = 256): each loads its own
+//     128-pixel activation patch and HALF of the weight tile; the leader CTA issues the MMAs
+//   * A ring : per 64-channel chunk, three column-shifted (bh+2) x 8-pixel patches (TMA 4-D tiled loads; out-of-image
+//              coordinates are zero-filled by TMA == the conv's "same" padding, no im2col buffer, no halo code);
+//              a patch row is one 1024-byte swizzle atom, so the nine taps are aligned descriptor offsets into the
+//              stage: the chunk is read 3.4x instead of 9x
+//   * B ring : TMA 3-D loads of the packed weights per (chunk, tap) — a whole kernel row of three taps per stage where
+//              it fits (N <= 128)
 //   * both land in SWIZZLE_128B K-major layout, exactly what the UMMA shared-memory descriptors expect
-//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue
+//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue; producer and
+//     issuer loops are warp-uniform (descriptor math on the uniform datapath), one elected lane issues
 //   * persistent CTAs (one per SM), double-buffered TMEM accumulator so the epilogue of tile i overlaps
 //     the mainloop of tile i+1
-//   * epilogue: TMEM -> registers -> (+bias, +per-image bias, +residual) * scale -> fp32/fp16 global,
-//               optional fused GroupNorm partial statistics (fp64 atomics per 4-channel bundle)
+//   * epilogue: TMEM -> registers -> (+bias row, +TMA-loaded residual) * scale -> swizzled smem chunk -> TMA store;
+//               fused GroupNorm bundle statistics (column sums of the staged chunk, fp64 atomics); a direct
+//               register -> global epilogue serves fp16 / strided / narrow outputs
 //
 // Replaces nn.Conv2d / NIN / attention einsums of the reference network
 // (networks/ncsnpp_utils/layers.py:100-126,548-557; layerspp.py:75-91) and their data-gradients.
