@@ -128,3 +128,31 @@ def test_length_buckets():
     assert b == [[0, 2], [3, 6], [1, 5], [4]]
     assert sorted(i for g in b for i in g) == list(range(len(lengths)))
     assert length_buckets([], 4) == [] and length_buckets([5], 4) == [[0]]
+
+
+def test_factored_stft_matrices_equal_the_dft_matrices():
+    """Host side of the FFT-based 1024-point STFT kernels: every matrix the likelihood / blind operator uses is
+    mat[2f+c][n] = a[f] * w[n] * (cos, -sin)(2 pi f n / 1024) with the (a, w) the code passes to `ops.FftMat`
+    (spectral.LossSTFT, blind.BlindEngine) — checked against the explicit DFT matrices in fp64."""
+    import math
+    from buddy_b200.spectral import _dft_mats, irfft_weights
+    n_fft, bins, win = 1024, 513, 512
+    w = torch.hann_window(win, dtype=torch.float64)
+    norm = math.sqrt(float((w ** 2).sum()))
+    ana, syn = _dft_mats(n_fft, bins, w, win, "cpu")
+    n = torch.arange(win, dtype=torch.float64)
+    f = torch.arange(bins, dtype=torch.float64)
+    ang = 2 * math.pi * torch.outer(f, n) / n_fft
+
+    def factored(a):
+        m = torch.empty(2 * bins, win, dtype=torch.float64)
+        m[0::2] = a[:, None] * torch.cos(ang) * w
+        m[1::2] = -a[:, None] * torch.sin(ang) * w
+        return m
+
+    ones = torch.ones(bins, dtype=torch.float64)
+    aw = irfft_weights(bins, n_fft)
+    assert aw[0] == 1 / n_fft and aw[-1] == 1 / n_fft and aw[1] == 2 / n_fft
+    for got, want in ((factored(ones), ana.double()), (factored(ones / norm), ana.double() / norm),
+                      (factored(aw), syn.double()), (factored(aw * norm), syn.double() * norm)):
+        assert (got - want).abs().max().item() < 1e-7 * want.abs().max().item()
