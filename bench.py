@@ -226,6 +226,7 @@ def run_ours(args):
     T_run = 60 if blind else T_STEPS
     smp = EulerHeunSamplerDPS(net, EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10)),
                               blind_args(T_run) if blind else informed_args(T_STEPS))
+    smp.seed_base = 3000          # noise stream of utterance b = 3000 + global index
     smp.utterance_offset = rank * B
     smp.micro_batch = args.micro_batch
     smp.n_streams = args.streams

@@ -363,8 +363,12 @@ __global__ void adam_project_kernel(float* __restrict__ p, const float* __restri
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     float pi = p[i] - step_size * (mi / denom);
     const int j = static_cast<int>(i % n_per);
-    if (j < 25) pi = fminf(fmaxf(pi, dmin), dmax);
-    else if (j < 50) pi = fminf(fmaxf(pi, wmin), wmax);
+    // project_params (subband_filtering.py:298-331).  fminf/fmaxf would map a NaN parameter onto the bound; the
+    // reference asserts on NaN (:330-331), so NaN must survive the projection and reach the sampler's finiteness check.
+    if (pi == pi) {
+      if (j < 25) pi = fminf(fmaxf(pi, dmin), dmax);
+      else if (j < 50) pi = fminf(fmaxf(pi, wmin), wmax);
+    }
     p[i] = pi;
   }
 }

@@ -292,12 +292,15 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1" format):
-// rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused (=1) inside a swizzle atom.
-__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+// rows of 128 bytes, 8-row groups `sbo` bytes apart (1024 = dense), LBO unused (=1) inside a swizzle atom.
+// The start address may be any 128-byte line and `sbo` any multiple of 128 bytes: with the base-offset field left 0
+// the hardware derives the swizzle XOR from the absolute shared-memory address, exactly like a TMA SWIZZLE_128B
+// write into a 1024-byte aligned buffer (measured on B200: scripts/probes/umma_sw128_shift_probe.cu).
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr, uint32_t sbo = 1024u) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);   // start address [0,14)
   d |= static_cast<uint64_t>(1) << 16;                        // leading byte offset (ignored) [16,30)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;                // stride byte offset [32,46)
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32;     // stride byte offset [32,46)
   d |= static_cast<uint64_t>(1) << 46;                        // descriptor version = 1 (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;                        // layout type: SWIZZLE_128B
   return d;

@@ -4,10 +4,12 @@
 //     (tcgen05.mma kind::f16 K=16 / kind::f8f6f4 K=32, N <= 256)
 //   * CTA pairs: two CTAs of a 2-CTA cluster share a 256-row tile pair (cta_group::2, M = 256): each loads its own
 //     128-pixel activation patch and HALF of the weight tile; the leader CTA issues the MMAs
-//   * A ring : per 64-channel chunk, three column-shifted (bh+2) x 8-pixel patches (TMA 4-D tiled loads; out-of-image
-//              coordinates are zero-filled by TMA == the conv's "same" padding, no im2col buffer, no halo code);
-//              a patch row is one 1024-byte swizzle atom, so the nine taps are aligned descriptor offsets into the
-//              stage: the chunk is read 3.4x instead of 9x
+//   * A ring : per 64-channel chunk ONE halo patch of (bh+2) x (bw+2) pixels (one TMA 4-D tiled load; out-of-image
+//              coordinates are zero-filled by TMA == the conv's "same" padding, no im2col buffer, no halo code).
+//              The SWIZZLE_128B XOR is a function of the absolute shared-memory address (verified on B200,
+//              scripts/probes/umma_sw128_shift_probe.cu: any 128-byte line shift, 8-row groups 1280 bytes apart), so
+//              tap (dy, dx) is the descriptor start offset (dy * (bw+2) + dx) * 128 B with SBO = (bw+2) * 128 B:
+//              the chunk is read from L2 1.41x instead of 9x (round 1: three column-shifted patches, 3.4x)
 //   * B ring : TMA 3-D loads of the packed weights per (chunk, tap) — a whole kernel row of three taps per stage where
 //              it fits (N <= 128)
 //   * both land in SWIZZLE_128B K-major layout, exactly what the UMMA shared-memory descriptors expect
@@ -34,8 +36,8 @@ namespace buddy {
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;            // fp16 elements per k-block = 128 bytes = one swizzle row
 constexpr int kMaxStagesA = 4;         // A ring (activation patches)
-constexpr int kMaxStagesB = 8;         // B ring (weight tiles)
-constexpr int kAccStride = 256;        // TMEM columns per accumulator stage
+constexpr int kMaxStagesB = 12;        // B ring (weight tiles)
+constexpr int kMaxAcc = 4;             // TMEM accumulator stages: 2 x 256 columns, or 4 x 128 when n_tile <= 128
 constexpr int kThreads = 192;
 
 struct GemmParams {
@@ -45,11 +47,12 @@ struct GemmParams {
   int taps, kchunks1, kchunks2, b_batched;
   int a_wrap1, a_wrap2;  // A-side channel chunk = k-chunk % a_wrap (split-precision operands re-read the hi half)
   int kchunks8_1, kchunks8_2;  // fp8 correction phases (128-byte chunks per tap / for the skip conv); 0 = none
-  // A ring: one stage = the activation patch(es) of ONE 64-channel chunk.  3x3 convs (halo = 1): three column-
-  // shifted patches of (bh + 2) rows x bw = 8 pixels; the nine taps are MMA-descriptor offsets into them (row shift
-  // = whole 1024-byte swizzle atoms), so a chunk is read from L2 3.4x instead of 9x.  B ring: one weight tile per
+  // A ring: one stage = the activation patch of ONE 64-channel chunk.  3x3 phases (halo = 1): one patch of
+  // (bh + 2) x (bw + 2) pixels (patch_bytes; 128-byte lines, a_pitch bytes between patch rows); the nine taps are
+  // MMA-descriptor start offsets into it.  1x1 phases: bh x bw pixels (patch1_bytes).  B ring: weight tiles per
   // (chunk, tap).
-  int halo, patch_bytes, stages_a, stages_b;
+  int halo, patch_bytes, patch1_bytes, a_pitch, a_stage_bytes, stages_a, stages_b;
+  int acc_stages, acc_stride;   // TMEM accumulator ring
   int tpb;  // taps per B-ring stage (3x3 phases): 3 = one kernel row of weights per stage (one TMA load, one wait, one
             // commit per 12 MMAs — the issue loop, not the tensor pipe, bounds layers with N <= 128), else 1
   float* out32;
@@ -89,14 +92,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmA82, const __grid_constant__ CUtensorMap tmB82,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const GemmParams p) {
-  // SWIZZLE_128B atoms need a 1024-byte aligned base.  The kernel has no static shared memory, so the dynamic
-  // window starts right after the 1 KB the system reserves per CTA and the declared alignment holds; no slack is
-  // allocated for a run-time round-up (every spare KB is left to co-resident GroupNorm CTAs of another stream).
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  // SWIZZLE_128B atoms need a 1024-byte aligned base: the window is rounded up at run time (the host allocates 1 KB
+  // of slack), so nothing depends on how much shared memory the driver reserves in front of the dynamic window.
+  // Both CTAs of a pair see the same window offset, so the rounded offsets agree (cta_group::2 descriptors and the
+  // multicast commits address the peer's shared memory by offset).
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader CTA of the pair
   const int b_rows = kPair ? (p.n_tile >> 1) : p.n_tile;   // weight-tile rows this CTA loads
-  const int a_stage_bytes = (p.halo ? 3 : 1) * p.patch_bytes;
+  const int a_stage_bytes = p.a_stage_bytes;
   const int b_tile_bytes = b_rows * 128;              // one weight tile (one tap, one 64-wide chunk)
   const int b_stage_bytes = p.tpb * b_tile_bytes;     // one B-ring stage
   // [A ring][B ring][2 staged epilogue chunks (if staged)][bias row 1 KB (if staged)][barriers]
@@ -110,9 +114,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* a_empty = a_full + kMaxStagesA;      // [kMaxStagesA]
   uint64_t* b_full = a_empty + kMaxStagesA;      // [kMaxStagesB]
   uint64_t* b_empty = b_full + kMaxStagesB;      // [kMaxStagesB]
-  uint64_t* tmem_full = b_empty + kMaxStagesB;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;          // [2]
-  uint64_t* res_bar = tmem_empty + 2;            // [2]
+  uint64_t* tmem_full = b_empty + kMaxStagesB;   // [kMaxAcc]
+  uint64_t* tmem_empty = tmem_full + kMaxAcc;    // [kMaxAcc]
+  uint64_t* res_bar = tmem_empty + kMaxAcc;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -133,11 +137,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&b_full[s], kPair ? 2 : 1);
       mbar_init(&b_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxAcc; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kPair ? 8 : 4);  // one arrival per epilogue warp (of both CTAs, on the leader's)
-      mbar_init(&res_bar[s], 1);
     }
+    for (int s = 0; s < 2; ++s) mbar_init(&res_bar[s], 1);
     if (p.staged) {
       tma_prefetch_desc(&tmOut);
       if (p.res_staged) tma_prefetch_desc(&tmRes);
@@ -192,23 +196,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int ptaps = (ph & 1) ? 1 : p.taps;
           const int unit = ph < 2 ? 128 : kBlockK;                       // coordinate units per chunk (128 B)
           const int wrap = ph == 2 ? p.a_wrap1 : (ph == 3 ? p.a_wrap2 : 0x7fffffff);
-          // A stage = 3 patches: the dx = -1/0/+1 patches of ONE chunk (3x3 phase), or the centre patches of up to
-          // THREE consecutive chunks (1x1 phase of a 3x3 launch, so the short skip-conv phase keeps the ring busy)
-          const int group = (p.halo && ptaps == 1) ? 3 : 1;
-          for (int kc = 0; kc < nch; kc += group) {
-            const int g = min(group, nch - kc);
-            const int nload = ptaps == 9 ? 3 : g;
+          // A stage = the patch of ONE chunk: (bh+2) x (bw+2) pixels for a 3x3 phase (one load serves all nine taps),
+          // bh x bw pixels for a 1x1 phase (the tensor maps of the two kinds carry the two box shapes)
+          const bool tap9 = ptaps == 9;
+          const int a_bytes = tap9 ? p.patch_bytes : p.patch1_bytes;
+          const int hh = tap9 ? p.halo : 0;
+          for (int kc = 0; kc < nch; ++kc) {
             mbar_wait(&a_empty[sa], pa ^ 1);
             uint8_t* abase = smem + sa * a_stage_bytes;
             if (elect_one()) {
-              const uint32_t fb = kPair ? mapa_u32(&a_full[sa], 0) : 0u;   // pair: the leader's barrier collects both
-              if (kPair) mbar_expect_tx_cluster(fb, nload * p.patch_bytes);
-              else mbar_expect_tx(&a_full[sa], nload * p.patch_bytes);
-              for (int j = 0; j < nload; ++j) {
-                const int ac = ((ptaps == 9 ? kc : kc + j) % wrap) * unit;
-                const int wx = w0 + (ptaps == 9 ? j - 1 : 0);
-                if (kPair) tma_load_4d_2sm(ma, abase + j * p.patch_bytes, fb, ac, wx, h0 - p.halo, b);
-                else tma_load_4d(ma, abase + j * p.patch_bytes, &a_full[sa], ac, wx, h0 - p.halo, b);
+              const int ac = (kc % wrap) * unit;
+              if (kPair) {
+                const uint32_t fb = mapa_u32(&a_full[sa], 0);   // pair: the leader's barrier collects both CTAs' bytes
+                mbar_expect_tx_cluster(fb, a_bytes);
+                tma_load_4d_2sm(ma, abase, fb, ac, w0 - hh, h0 - hh, b);
+              } else {
+                mbar_expect_tx(&a_full[sa], a_bytes);
+                tma_load_4d(ma, abase, &a_full[sa], ac, w0 - hh, h0 - hh, b);
               }
             }
             __syncwarp();
@@ -216,11 +220,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               sa = 0;
               pa ^= 1;
             }
-            const int nsteps = ptaps == 9 ? 9 : g;
-            const int tstep = ptaps == 9 ? p.tpb : 1;   // taps covered by one B stage (one TMA box over the tap dim)
+            const int nsteps = tap9 ? 9 : 1;
+            const int tstep = tap9 ? p.tpb : 1;   // taps covered by one B stage (one TMA box over the tap dim)
             for (int st = 0; st < nsteps; st += tstep) {
-              const int tap = ptaps == 9 ? st : 0;
-              const int kcb = ptaps == 9 ? kc : kc + st;
+              const int tap = tap9 ? st : 0;
+              const int kcb = kc;
               mbar_wait(&b_empty[sb], pb ^ 1);
               uint8_t* bbase = smem_b + sb * b_stage_bytes;
               const int b3 = (ph & 1) ? 0 : (p.b_batched ? b : tap);
@@ -253,7 +257,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (rank == 0) {
       const uint32_t idesc = make_idesc_f16(kPair ? 2 * kTileM : kTileM, p.n_tile);
       const uint32_t idesc8 = make_idesc_e4m3(kPair ? 2 * kTileM : kTileM, p.n_tile);
-      const int row_pitch = p.bw * 128;   // bytes between patch rows (halo launches: bw = 8 -> one swizzle atom)
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int acc = 0;
@@ -261,7 +264,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int t = t_first; t < total_tiles; t += t_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
         bool fresh = true;       // no MMA issued into this accumulator yet
         bool unscaled8 = false;  // fp8 corrections accumulated (x 2^14) and not yet folded
         for (int ph = 0; ph < 4; ++ph) {
@@ -269,9 +272,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (nch == 0) continue;
           const int ptaps = (ph & 1) ? 1 : p.taps;
           const bool f8 = ph < 2;
-          const int group = (p.halo && ptaps == 1) ? 3 : 1;
-          for (int kc = 0; kc < nch; kc += group) {
-            const int nsteps = ptaps == 9 ? 9 : min(group, nch - kc);
+          // 8-row groups of the A tile: a patch row apart in a halo patch, dense (1024 B) otherwise
+          const uint32_t a_sbo = ptaps == 9 ? static_cast<uint32_t>(p.a_pitch) : 1024u;
+          for (int kc = 0; kc < nch; ++kc) {
+            const int nsteps = ptaps == 9 ? 9 : 1;
             if (!(p.dbg & 4)) mbar_wait(&a_full[sa], pa);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + sa * a_stage_bytes);
@@ -284,11 +288,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (elect_one()) {
                 for (int tt = 0; tt < tstep; ++tt) {
                   const int s1 = st + tt;
-                  // 3x3 phase, tap (dy, dx): patch dx+1 shifted down dy+1 rows; 1x1 phase of a 3x3 launch: patch
-                  // `s1` (one per chunk of the group), centre rows; plain 1x1 / GEMM launch: the only patch, no halo
-                  const int a_off = ptaps == 9 ? (s1 % 3) * p.patch_bytes + (s1 / 3) * row_pitch
-                                               : s1 * p.patch_bytes + (p.halo ? row_pitch : 0);
-                  const uint64_t da = make_sw128_kmajor_desc(a_addr + a_off);
+                  // 3x3 phase, tap s1 = 3 * ky + kx: the halo patch shifted by ky rows and kx pixels (whole 128-byte
+                  // lines: the swizzle XOR follows the absolute address); 1x1 phase: the patch as loaded
+                  const int a_off = ptaps == 9 ? (s1 / 3) * p.a_pitch + (s1 % 3) * 128 : 0;
+                  const uint64_t da = make_sw128_kmajor_desc(a_addr + a_off, a_sbo);
                   const uint64_t db = make_sw128_kmajor_desc(b_addr + tt * b_tile_bytes);
                   const bool first = fresh && tt == 0;
                   // each MMA consumes 32 bytes of K per row (16 fp16 or 32 e4m3): +2 in (addr >> 4) units
@@ -346,7 +349,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           else umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
-        if (++acc == 2) {
+        if (++acc == p.acc_stages) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -371,6 +374,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t res_phase = 0;          // bit s = parity to wait for on res_bar[s]
     const int sw = (m & 7);          // swizzle phase of this thread's staging row
     const uint32_t tmem_empty_leader = kPair ? mapa_u32(tmem_empty, 0) : 0u;
+    // GroupNorm bundle statistics: every thread keeps partial sums (bundle et & 7 of each 32-column chunk, its 8
+    // rows of every tile) across the consecutive tiles this CTA works on and hands them to the global fp64
+    // accumulators only when the (image, column block) changes — a persistent CTA stays inside one image for many
+    // tiles, so the same-address fp64 atomics (all CTAs work on the same image at the same time) drop by that factor.
+    // Round 1 issued them per chunk per warp: they serialised in L2 and cost 15 % of the 256->256 layer.  The
+    // running sums are fp64 (of fp32 partials over a fixed 8-row x 4-channel footprint), so the result does not
+    // depend on which tiles a CTA happens to get, i.e. not on the batch size or the grid.
+    double st_s[8], st_q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.0;
+    int st_b = -1, st_col = 0;       // (image, first column) the partial sums belong to; -1: none
+    auto flush_stats = [&]() {
+      if (st_b >= 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c < nchunks) {
+            double s = st_s[c], q = st_q[c];
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            q += __shfl_xor_sync(0xffffffffu, q, 8);
+            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            q += __shfl_xor_sync(0xffffffffu, q, 16);
+            if (lane < 8) {
+              double* sp = p.stats + (static_cast<long long>(st_b) * (p.n_total >> 2) + ((st_col + c * 32) >> 2) + lane) * 2;
+              atomicAdd(sp, s);
+              atomicAdd(sp + 1, q);
+            }
+            st_s[c] = st_q[c] = 0.0;
+          }
+        }
+      }
+    };
     for (int t = t_first; t < total_tiles; t += t_step) {
       const int nt = t % p.n_tiles;
       const int pt = kPair ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
@@ -381,6 +415,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool in_batch = b < p.batch;   // false only for the padding tile of an odd pair count
       const bool valid = in_batch && (h0 + hl < p.H) && (w0 + wl < p.W);
       const int ncol_base = nt * p.n_tile;
+      if (p.stats && in_batch && (b != st_b || ncol_base != st_col)) {
+        flush_stats();
+        st_b = b;
+        st_col = ncol_base;
+      }
       // bias row of this tile (bias + per-image bias): every reader of the previous tile's row is past its last
       // chunk barrier, so it can be overwritten; the chunk-0 barrier below publishes it
       for (int i = et; i < p.n_tile; i += kEpiThreads) {
@@ -422,7 +461,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * kAccStride;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * p.acc_stride;
       if (p.dbg & 3) {   // profiling experiment: no stores / statistics; dbg 2 still reads the accumulator
         if (p.dbg & 2) {
           uint32_t dd[32];
@@ -438,7 +477,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (kPair) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
           else mbar_arrive(&tmem_empty[acc]);
         }
-        if (++acc == 2) {
+        if (++acc == p.acc_stages) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -569,23 +608,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             s += (x.x + x.y) + (x.z + x.w);
             q = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, q))));
           }
-          s += __shfl_xor_sync(0xffffffffu, s, 8);
-          q += __shfl_xor_sync(0xffffffffu, q, 8);
-          s += __shfl_xor_sync(0xffffffffu, s, 16);
-          q += __shfl_xor_sync(0xffffffffu, q, 16);
-          if (lane < 8) {
-            double* sp = p.stats + (static_cast<long long>(b) * (p.n_total >> 2) + ((ncol_base + c * 32) >> 2) + bun) * 2;
-            atomicAdd(sp, static_cast<double>(s));
-            atomicAdd(sp + 1, static_cast<double>(q));
-          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i == c) {
+              st_s[i] += static_cast<double>(s);
+              st_q[i] += static_cast<double>(q);
+            }
         }
         if (c + 1 < nchunks) tmem_ld_wait_dep(rr);
       }
-      if (++acc == 2) {
+      if (++acc == p.acc_stages) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    if (p.stats) flush_stats();
     if (elected) tma_store_wait_all();
   } else {
     // ================================================================ epilogue, direct (4 warps, 128 threads)
@@ -608,7 +645,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * kAccStride;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * p.acc_stride;
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         uint32_t rr[32];
         tmem_ld_32x32(taddr + c0, rr);
@@ -715,7 +752,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (kPair) mbar_arrive_cluster(tmem_empty_leader + acc * 8);
         else mbar_arrive(&tmem_empty[acc]);
       }
-      if (++acc == 2) {
+      if (++acc == p.acc_stages) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -857,8 +894,8 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   p.batch = d->batch;
   p.H = d->H;
   p.W = d->W;
-  // 3x3: fixed 16 x 8 pixel tiles — patch rows of 8 pixels are whole 1024-byte swizzle atoms, so a tap's row shift is
-  // an aligned descriptor offset into the (bh + 2)-row patch; 1x1 / GEMM: the patch shape that wastes least
+  // 3x3: fixed 16 x 8 pixel tiles with a one-pixel halo: ONE (16+2) x (8+2)-pixel patch per 64-channel chunk, 128-byte
+  // lines, the nine taps are descriptor start offsets; 1x1 / GEMM: the patch shape that wastes least
   p.halo = d->taps == 9 ? 1 : 0;
   if (p.halo) {
     p.bh = 16;
@@ -867,7 +904,11 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     choose_patch(d->H, d->W, &p.bh, &p.bw);
   }
   const int patch_rows = p.bh + 2 * p.halo;
-  p.patch_bytes = patch_rows * p.bw * 128;
+  const int patch_cols = p.bw + 2 * p.halo;
+  p.a_pitch = patch_cols * 128;
+  p.patch_bytes = patch_rows * patch_cols * 128;
+  p.patch1_bytes = p.bh * p.bw * 128;
+  p.a_stage_bytes = (p.patch_bytes + 1023) & ~1023;
   p.tiles_h = (d->H + p.bh - 1) / p.bh;
   p.tiles_w = (d->W + p.bw - 1) / p.bw;
   p.n_tile = d->n_tile;
@@ -889,7 +930,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   const long long pix_tiles = (long long)p.batch * p.tiles_h * p.tiles_w;
   const bool pair = !d->b_batched && !d->no_cta_pairs && d->n_tile >= 32 && d->n_tile % 16 == 0 && pix_tiles >= 2;
   const int b_box_rows = pair ? d->n_tile / 2 : d->n_tile;
-  const int a_stage_bytes = (p.halo ? 3 : 1) * p.patch_bytes;
+  const int a_stage_bytes = p.a_stage_bytes;
   const int b_stage_bytes = b_box_rows * 128;
   // staged epilogue (TMA stores of 128x32 fp32 chunks): dense fp32 output whose tile columns are whole chunks
   p.staged = (!d->out_fp16 && d->ldc == d->n_total && d->col_off == 0 && d->n_tile % 32 == 0 &&
@@ -905,15 +946,20 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
       return BUDDY_ERR_UNSUPPORTED;
     }
   }
+  // TMEM: 512 columns = 2 accumulators of up to 256 columns, or 4 of up to 128 (more slack for the epilogue of the
+  // short N <= 128 mainloops)
+  p.acc_stages = d->n_tile <= 128 ? 4 : 2;
+  p.acc_stride = d->n_tile <= 128 ? 128 : 256;
   const int epi_bytes = p.staged ? 2 * kChunkBytes + 1024 + (d->gnb_x ? 4096 : 0) : 0;
-  const int ring_bytes = 227 * 1024 - 1536 - epi_bytes;
+  const int ring_bytes = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - epi_bytes;
   p.tpb = 1;
   if (p.halo) {
-    // a patch stage lasts nine weight tiles: two of them, the rest of the shared memory goes to the weight ring —
+    // a patch stage lasts nine weight tiles: three of them, the rest of the shared memory goes to the weight ring —
     // as kernel rows of three taps per stage when at least three such stages fit (N <= 128 in pair mode)
-    p.stages_a = 2;
-    if (!d->one_tap_per_stage && (ring_bytes - 2 * a_stage_bytes) / (3 * b_stage_bytes) >= 3) p.tpb = 3;
-    p.stages_b = (ring_bytes - 2 * a_stage_bytes) / (p.tpb * b_stage_bytes);
+    // (a fused 1x1 skip phase drains one patch stage per k-block: one more stage keeps the ring ahead of it)
+    p.stages_a = d->a2 ? 4 : 3;
+    if (!d->one_tap_per_stage && (ring_bytes - p.stages_a * a_stage_bytes) / (3 * b_stage_bytes) >= 3) p.tpb = 3;
+    p.stages_b = (ring_bytes - p.stages_a * a_stage_bytes) / (p.tpb * b_stage_bytes);
   } else {
     p.stages_a = p.stages_b = ring_bytes / (a_stage_bytes + b_stage_bytes);
   }
@@ -955,7 +1001,8 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     p.kchunks8_1 = d->a8_c / 128;
     uint64_t dims[4] = {(uint64_t)d->a8_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
     uint64_t str[4] = {1, (uint64_t)d->a8_stride_w, (uint64_t)d->a8_stride_h, (uint64_t)d->a8_stride_b};
-    uint32_t box[4] = {128, (uint32_t)p.bw, (uint32_t)patch_rows, 1};
+    uint32_t box[4] = {128, (uint32_t)patch_cols, (uint32_t)patch_rows, 1};
+    uint32_t box1[4] = {128, (uint32_t)p.bw, (uint32_t)p.bh, 1};
     int e = encode_map(&tmA8, d->a8, 4, dims, str, box, 1);
     if (e) return e;
     uint64_t dimsb[3] = {(uint64_t)d->a8_c, (uint64_t)d->b_rows, (uint64_t)d->b_t};
@@ -972,7 +1019,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
       p.kchunks8_2 = d->a8_2_c / 128;
       uint64_t dims2[4] = {(uint64_t)d->a8_2_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
       uint64_t str2[4] = {1, (uint64_t)d->a8_2_stride_w, (uint64_t)d->a8_2_stride_h, (uint64_t)d->a8_2_stride_b};
-      e = encode_map(&tmA82, d->a8_2, 4, dims2, str2, box, 1);
+      e = encode_map(&tmA82, d->a8_2, 4, dims2, str2, box1, 1);
       if (e) return e;
       uint64_t dimsb2[3] = {(uint64_t)d->a8_2_c, (uint64_t)d->b2_rows, 1};
       uint64_t strb2[3] = {1, (uint64_t)d->a8_2_c, (uint64_t)d->a8_2_c * (uint64_t)d->b2_rows};
@@ -983,7 +1030,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   {
     uint64_t dims[4] = {(uint64_t)d->a_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
     uint64_t str[4] = {1, (uint64_t)d->a_stride_w, (uint64_t)d->a_stride_h, (uint64_t)d->a_stride_b};
-    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bw, (uint32_t)patch_rows, 1};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)patch_cols, (uint32_t)patch_rows, 1};
     int e = encode_map(&tmA, d->a, 4, dims, str, box);
     if (e) return e;
   }
@@ -997,7 +1044,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   if (d->a2) {
     uint64_t dims[4] = {(uint64_t)d->a2_c, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->batch};
     uint64_t str[4] = {1, (uint64_t)d->a2_stride_w, (uint64_t)d->a2_stride_h, (uint64_t)d->a2_stride_b};
-    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bw, (uint32_t)patch_rows, 1};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, 1};
     int e = encode_map(&tmA2, d->a2, 4, dims, str, box);
     if (e) return e;
     uint64_t dimsb[3] = {(uint64_t)k2, (uint64_t)d->b2_rows, 1};
@@ -1034,8 +1081,8 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     tmRes = tmA;
   }
 
-  const size_t smem_bytes = (size_t)p.stages_a * a_stage_bytes + (size_t)p.stages_b * p.tpb * b_stage_bytes + epi_bytes +
-                            256 /*barriers*/;
+  const size_t smem_bytes = 1024 /*run-time alignment slack*/ + (size_t)p.stages_a * a_stage_bytes +
+                            (size_t)p.stages_b * p.tpb * b_stage_bytes + epi_bytes + 512 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
     int e = check_cuda(

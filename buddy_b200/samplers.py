@@ -39,8 +39,15 @@ class Sampler:
         self.step_counter = 0
         # extensions (all optional)
         self.noise_source = None          # iterator of pre-drawn N(0,1) tensors (parity tests)
-        self.seed_base = 3000             # Philox stream of utterance b = seed_base + utterance_offset + b
+        # Philox stream of utterance b = seed + utterance_offset + b.  seed_base = None (default): every predict*()
+        # call draws a fresh 62-bit seed from torch's global CPU generator, so `torch.manual_seed` controls the run and
+        # successive calls / successive utterances of the reference's one-at-a-time Tester loop get different noise —
+        # the behaviour of the reference's `torch.randn` (EulerHeunSampler.py:21,43).  seed_base = int: fully explicit
+        # streams (results independent of batch split and GPU count; repeated calls return identical samples).
+        self.seed_base = None
+        self._run_seed = 0
         self.utterance_offset = 0         # global index of this rank's first utterance (multi-GPU shards)
+        self.nan_guard = True             # one device->host finiteness check per predict*() call (DPS.py:90,103)
         self.utterance_ids = None         # or: explicit global index of every utterance of the batch
         self.micro_batch = 32             # utterances per network evaluation (~1.9 GB of activations each)
         self.n_streams = 1                # micro-batches in flight on separate CUDA streams (results identical).  >1
@@ -95,7 +102,7 @@ class Sampler:
 
     # ---- noise ---------------------------------------------------------------------------------------
     def _randn(self, shape, device, draw=None, first=0):
-        """N(0,1) [B, n].  Philox stream of utterance b = seed_base + utterance_offset + first + b; `draw` is the draw
+        """N(0,1) [B, n].  Philox stream of utterance b = run seed + utterance_offset + first + b; `draw` is the draw
         index inside the stream (explicit, so results do not depend on micro-batching or on the GPU count)."""
         if self.noise_source is not None:
             z = next(self.noise_source).to(device=device, dtype=torch.float32)
@@ -107,15 +114,34 @@ class Sampler:
         if self.utterance_ids is not None:      # explicit global utterance indices (batches that are not contiguous)
             ids = torch.as_tensor(self.utterance_ids, dtype=torch.int64)[first:first + B]
             assert ids.numel() == B, "utterance_ids must list one index per utterance of the batch"
-            seeds = ids.to(device) + self.seed_base
+            seeds = ids.to(device) + self._run_seed
         else:
-            seeds = torch.arange(B, dtype=torch.int64, device=device) + (self.seed_base + self.utterance_offset + first)
+            seeds = torch.arange(B, dtype=torch.int64, device=device) + (self._run_seed + self.utterance_offset + first)
         out = torch.empty(B, n, device=device)
         if draw is None:
             draw = self._draw
             self._draw += 1
         ops.philox_normal(seeds, draw, out)
         return out
+
+    def _start_run(self):
+        """Per-call noise state: draw counter back to 0 and the run seed (see `seed_base`)."""
+        self._draw = 0
+        if self.seed_base is None:
+            self._run_seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        else:
+            self._run_seed = int(self.seed_base)
+
+    def _check_finite(self, x, what):
+        """The reference asserts on NaN inside the loop (EulerHeunSamplerDPS.py:90,103; subband_filtering.py:238,
+        330-331) — a host sync per check.  Here NaN/Inf propagate through every kernel (no clamp swallows them) and
+        are checked ONCE per call on the per-utterance sums of the result."""
+        if not self.nan_guard:
+            return
+        st = ops.row_stats(x.reshape(x.shape[0], -1).contiguous())
+        bad = (~torch.isfinite(st).all(dim=1)).nonzero().flatten().tolist()
+        if bad:
+            raise FloatingPointError(f"{what} is NaN/Inf for utterance(s) {bad} of the batch")
 
 
 def _vec(v, B, device):
@@ -176,14 +202,14 @@ class EulerHeunSampler(Sampler):
         dt = t_next - t_hat
         if t_next != 0 and self.order == 2:
             x_prime = ops.lincomb3(torch.empty_like(x_hat), x_hat, _vec(1.0, B, dev), d, _vec(dt, B, dev))
-            d2, x_den = self._ode_term(x_prime, t_next)
+            d2, x_den = self._ode_term(x_prime, t_next, second=True)
             x_next = ops.lincomb3(torch.empty_like(x_hat), x_hat, _vec(1.0, B, dev), d, _vec(0.5 * dt, B, dev), d2,
                                   _vec(0.5 * dt, B, dev))
         else:
             x_next = ops.lincomb3(torch.empty_like(x_hat), x_hat, _vec(1.0, B, dev), d, _vec(dt, B, dev))
         return x_next, x_den
 
-    def _ode_term(self, x, sigma):
+    def _ode_term(self, x, sigma, second=False):
         """d = (x - D(x, sigma)) / sigma   (Tweedie2score + _ode_integrand, edm.py:83-96), micro-batched."""
         B, dev = x.shape[0], x.device
         d = torch.empty_like(x)
@@ -201,7 +227,7 @@ class EulerHeunSampler(Sampler):
 
     def predict(self, shape, device, blind=False):
         t = self.create_schedule()
-        self._draw = 0
+        self._start_run()
         x = self.initialize_x(tuple(shape), device, t)
         gamma = self.get_gamma(t)
         x_den = None
@@ -209,6 +235,7 @@ class EulerHeunSampler(Sampler):
             self.step_counter = i
             x, x_den = self.step(x, t[i], t[i + 1], gamma[i], blind)
         self._last_x_den = x_den
+        self._check_finite(x, "sample")
         return x.detach()
 
     def predict_unconditional(self, shape, device):
@@ -246,9 +273,38 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
         raise NotImplementedError(mode)
 
     # ---- operator binding -----------------------------------------------------------------------------
+    _OP_HP = dict(NFFT=1024, win_length=512, hop=128, window="hann")
+    _OP_HP_BLIND = dict(Nf=100, minimum_phase=True, fix_direct_path=True, fix_EQ_extremes=True, clamp_decay=True,
+                        strictly_decreasing_decay=False)
+
+    def _validate_operator(self, operator, B, blind):
+        """The kernels implement the shipped operator configuration (conf/tester/*.yaml op_hp); anything else must fail
+        loudly instead of silently computing a different loss / filter."""
+        hp = getattr(operator, "op_hp", None)
+        want = dict(self._OP_HP, **(self._OP_HP_BLIND if blind else {}))
+        for k, v in want.items():
+            got = _get(hp, k)
+            if got is not None and got != v:
+                raise NotImplementedError(f"operator op_hp.{k} = {got!r}: the CUDA path implements {v!r} only")
+        if not blind:
+            return
+        eq = _get(hp, "EQ_freqs")
+        if eq is not None and len(eq) != 27:
+            raise NotImplementedError(f"op_hp.EQ_freqs has {len(eq)} knots: the CUDA path implements 27 (25 bands)")
+        if int(getattr(operator, "num_exponentials", 1)) != 1:
+            raise NotImplementedError("num_exponentials > 1 is not on the hot path (shipped config: one exponential)")
+        p0 = operator.params[0]
+        if p0.shape[-1] != 25 or (p0.dim() == 2 and p0.shape[0] not in (1, B)):
+            raise NotImplementedError(f"operator.params[0] has shape {tuple(p0.shape)}: expected (1, 25) or (B, 25)")
+        if float(_get(self.args.tester.posterior_sampling.blind_hp, "weight_decay", 0) or 0) != 0:
+            raise NotImplementedError("blind_hp.weight_decay != 0 is not implemented (shipped config: 0)")
+        if str(_get(self.args.tester.posterior_sampling.blind_hp, "optimizer", "adam")).lower() != "adam":
+            raise NotImplementedError("blind_hp.optimizer: only adam is implemented")
+
     def _bind_operator(self, operator, y, blind):
         dev = y.device
         n = y.shape[1]
+        self._validate_operator(operator, y.shape[0], blind)
         self._loss_stft = LossSTFT(dev)
         ps = self.args.tester.posterior_sampling
         self._loss_w = float(ps.rec_loss.weight)
@@ -305,13 +361,15 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
         coef = (self.zeta / (normguide + 1e-8)).contiguous()
         return g, coef, loss
 
-    def _ode_term(self, x, sigma):
-        """d = (x - x_den)/sigma + lh_score   (EulerHeunSamplerDPS.py:118-134), micro-batched."""
+    def _ode_term(self, x, sigma, second=False):
+        """d = (x - x_den)/sigma + lh_score   (EulerHeunSamplerDPS.py:118-134), micro-batched.
+        second = the Heun correction evaluation (:136-150): the reference rescales x_den (magnitude constraint,
+        :128-129) only after the FIRST evaluation of a step, the second one enters Tweedie2score as is."""
         B, dev = x.shape[0], x.device
         d = torch.empty_like(x)
         x_den = torch.empty_like(x)
         ps = self.args.tester.posterior_sampling
-        rescale = bool(ps.constraint_speech_magnitude.use)
+        rescale = bool(ps.constraint_speech_magnitude.use) and not second
         def body(sl):
             xs = x[sl].contiguous()
             nb = xs.shape[0]
@@ -352,7 +410,7 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
 
     def predict(self, shape, device, blind=False):
         t = self.create_schedule()
-        self._draw = 0
+        self._start_run()
         self._eval_index = 0
         x = self.initialize_x(tuple(shape), device, t)
         gamma = self.get_gamma(t)
@@ -360,7 +418,11 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
         for i in range(self.T):
             self.step_counter = i
             x, x_den = self.step(x, t[i], t[i + 1], gamma[i], blind)
+        self._check_finite(x_den, "x_den")
         if blind:
+            st = self._blind.full
+            self._check_finite(torch.cat([st["decays"], st["weights"], st["H"].reshape(st["B"], -1)], dim=1),
+                               "blind operator (decays / weights / H)")
             self._write_back_operator()
         return x_den.detach()
 
@@ -368,15 +430,13 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
         """After a blind run the estimated filter lives in the operator object again (tester.py:161 reads it)."""
         st, op = self._blind.full, self.operator
         H = torch.view_as_complex(st["H"].contiguous())
-        try:
-            if st["B"] == 1:
-                op.params[0] = st["decays"].clone()
-                op.params[1] = st["weights"].clone()
-                op.params_phases[0] = st["phases"][0].clone()
-                op.H = H[0].clone()
-            op.H_batch, op.params_batch = H, (st["decays"], st["weights"], st["phases"])
-        except Exception:
-            pass
+        if st["B"] == 1:
+            op.params[0] = st["decays"].clone()
+            op.params[1] = st["weights"].clone()
+            op.params_phases[0] = st["phases"][0].clone()
+            op.H = H[0].clone()
+        # batches: the reference object has ONE filter; the per-utterance results travel as extra attributes
+        op.H_batch, op.params_batch = H, (st["decays"], st["weights"], st["phases"])
 
     def predict_unconditional(self, *args, **kwargs):
         raise ValueError("DPS not made for unconditional sampling")

@@ -50,6 +50,10 @@ class BatchedDereverb:
         assert len(ys) == len(rirs)
         preds = [None] * len(ys)
         first = getattr(self.sampler, "utterance_offset", 0)
+        restore = self.sampler.seed_base
+        if restore is None:
+            # one run seed for the whole call: utterance i keeps stream seed + first + i whatever bucket it lands in
+            self.sampler.seed_base = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
         for idx in length_buckets([y.shape[-1] for y in ys], self.max_batch):
             y = torch.stack([ys[i].float() for i in idx])
             m = max(rirs[i].shape[-1] for i in idx)
@@ -63,4 +67,5 @@ class BatchedDereverb:
             for r, i in enumerate(idx):
                 preds[i] = out[r]
         self.sampler.utterance_ids = None
+        self.sampler.seed_base = restore
         return preds

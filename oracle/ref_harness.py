@@ -1,7 +1,9 @@
 """Loader for the UNMODIFIED reference (sp-uhh/buddy) from /root/reference — build container only.
 
-Used by oracle/make_golden.py to generate the committed fixtures under tests/golden/ and by
-tests/test_oracle_vs_reference.py (skipped where /root/reference does not exist, e.g. on the GPU box).
+Used by oracle/make_golden.py / make_golden_r2.py to generate the committed fixtures under tests/golden/, by
+tests/test_reference_integration.py and by `bench.py --impl reference`.  The reference is looked up at
+$BUDDY_REFERENCE_ROOT, /root/reference (build container) or oracle/_ref (a verbatim, git-ignored staging copy made
+by oracle/stage_ref.py so that the UNMODIFIED reference travels to the GPU box like the built .so files).
 Nothing of the reference is copied: it is imported in place, with empty stand-in modules for the
 logging/WPE-only third-party imports it never calls on this path and the
 piecewise-linear stand-in for the absent `torchcde`.
@@ -12,7 +14,17 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("BUDDY_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_ref():
+    for cand in (os.environ.get("BUDDY_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "networks")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_ref()
 
 NCSNPP_CFG = dict(nonlinearity='swish', nf=128, ch_mult=[1, 2, 2, 2], num_res_blocks=1, attn_resolutions=[0],
                   resamp_with_conv=True, time_conditional=True, fir=False, fir_kernel=[1, 3, 3, 1], skip_rescale=True,
@@ -104,13 +116,15 @@ def _loss(weight):
               multiple_compression_factors=False)
 
 
-def make_args(mode, T, audio_len=65536, warm="reverb_scaled"):
-    """Attribute-dict equivalent of conf/tester/{informed_dereverberation_DPS,blind_dereverberation_BUDDy}.yaml."""
+def make_args(mode, T, audio_len=65536, warm="reverb_scaled", rescale=False):
+    """Attribute-dict equivalent of conf/tester/{informed_dereverberation_DPS,blind_dereverberation_BUDDy}.yaml.
+    rescale (informed only): constraint_speech_magnitude.use — off in the shipped informed config, on in the blind one."""
     sde = AD(sigma_data=0.05, sigma_min=1e-4, sigma_max=0.5, rho=10)
     if mode == "informed":
         sp = AD(same_as_training=False, sde_hp=sde, Schurn=10, Snoise=1, Stmin=0, Stmax=10, order=2, T=T, schedule="edm")
         ps = AD(zeta=2.75, rec_loss=_loss(512), normalization_type="grad_norm",
-                warm_initialization=AD(mode=warm, scaling_factor=0.05), constraint_speech_magnitude=AD(use=False))
+                warm_initialization=AD(mode=warm, scaling_factor=0.05),
+                constraint_speech_magnitude=AD(use=bool(rescale), speech_scaling=0.05))
     elif mode == "blind":
         sp = AD(same_as_training=False, sde_hp=sde, Schurn=50, Snoise=1, Stmin=0, Stmax=10, order=1, T=T, schedule="edm")
         ps = AD(zeta=0.5, rec_loss=_loss(512), rec_loss_params=_loss(512),

@@ -81,8 +81,11 @@ def _likelihood(sd, x_in, sigma, y, degrade, zeta, audio_len, rescale):
     return -sigma * score + lh, x_den, x_in.detach()
 
 
-def dps_informed(sd, y, rir, T, noise, zeta=2.75, Schurn=10, order=2, audio_len=65536, warm="reverb_scaled"):
-    """y (1,N) observation, rir (M,).  Informed DPS (conf/tester/informed_dereverberation_DPS.yaml)."""
+def dps_informed(sd, y, rir, T, noise, zeta=2.75, Schurn=10, order=2, audio_len=65536, warm="reverb_scaled",
+                 rescale=False):
+    """y (1,N) observation, rir (M,).  Informed DPS (conf/tester/informed_dereverberation_DPS.yaml).
+    rescale = constraint_speech_magnitude.use: applied after the FIRST evaluation of a step only — the reference's
+    Heun correction (EulerHeunSamplerDPS.py:136-150) has no rescale line."""
     t = create_schedule(T)
     gamma = get_gamma(t, Schurn)
     it = iter(noise)
@@ -93,7 +96,7 @@ def dps_informed(sd, y, rir, T, noise, zeta=2.75, Schurn=10, order=2, audio_len=
     x_den = None
     for i in range(T):
         x_hat, t_hat = _perturb(x, t[i], gamma[i], next(it))
-        d, x_den, x_hat = _likelihood(sd, x_hat, t_hat, y, degrade, zeta, audio_len, False)
+        d, x_den, x_hat = _likelihood(sd, x_hat, t_hat, y, degrade, zeta, audio_len, rescale)
         dt = t[i + 1] - t_hat
         if t[i + 1] != 0 and order == 2:
             x_p = x_hat + dt * d
@@ -134,9 +137,12 @@ def optimize_op(state, x_den, y, t, rir_noise_iter, n_iter=10, crop_max=0.01, cr
 
 
 def dps_blind(sd, y, state, T, noise, rir_noise, zeta=0.5, Schurn=50, audio_len=65536, warm="reverb_scaled",
-              n_iter=10):
+              n_iter=10, denoise_fn=None):
     """Blind DPS (conf/tester/blind_dereverberation_BUDDy.yaml; order 1) for ONE utterance y (1,N).
-    noise: [init, step0, step1, ...]; rir_noise: iterable of (13824,) draws, one per operator-Adam iteration."""
+    noise: [init, step0, step1, ...]; rir_noise: iterable of (13824,) draws, one per operator-Adam iteration.
+    denoise_fn (sensitivity experiments only): replaces `denoise`, e.g. to perturb the network output at the
+    tolerance the network itself is tested to."""
+    denoise = denoise_fn or globals()["denoise"]
     t = create_schedule(T)
     gamma = get_gamma(t, Schurn)
     it, rit = iter(noise), iter(rir_noise)

@@ -24,6 +24,10 @@ def e4m3(t):
     return t.clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)
 
 
+if os.environ.get("SHAPESET") == "n128":
+    SHAPES = [(256, 528, 128, 128, "c8"), (256, 528, 128, 128, "x1"), (256, 528, 128, 128, "c8", 384),
+              (256, 528, 256, 128, "x1"), (256, 528, 256, 256, "x1"), (128, 264, 256, 256, "c8")]
+
 for shp in SHAPES:
     H, W, ci, co, mode = shp[:5]
     cs = shp[5] if len(shp) > 5 else 0

@@ -172,15 +172,134 @@ def test_blind_dps_trajectory_vs_reference_fixture():
     e_w = rel(op.params[1].cpu(), g["final_weights"])
     print(f"\n[blind DPS T2] pred {e_pred:.2e}  H {e_H:.2e}  decays {e_d:.2e}  weights {e_w:.2e}")
     # 20 Adam iterations: the optimiser divides each element by its own gradient scale, so elements with noise-level
-    # gradients take +-lr steps in an implementation-dependent direction (the reference and its fp32 restatement already
-    # differ by 5e-4 / 4e-3 (pred / H) here, tests/test_oracle_golden.py::test_blind_dps_sampler).  Every deterministic
-    # stage is pinned tightly elsewhere in this file (one-iteration losses/gradients 1e-4..1e-3, update_H 1e-4) and
-    # test_blind_single_iteration_trajectory below holds 1e-3 on the trajectory itself.
-    # The reference algorithm itself is this sensitive: scripts/blind_sensitivity.py perturbs the observation of the
-    # fp32 oracle by 1e-7 / 1e-5 relative and its own output moves by 1.1e-3 / 2.1e-3 (H: 3.7e-3 / 6.1e-3) after these
-    # 20 iterations; our network evaluations differ from fp32 by ~3e-4, and the measured 4.5e-3..4.8e-3 is the same
-    # for every operand-precision mode (fp16x3 .. mixed).  The run is bitwise reproducible (no fp32 atomics).
-    assert e_pred < 8e-3 and e_H < 2e-2 and e_d < 5e-3 and e_w < 5e-3
+    # gradients take +-lr steps in an implementation-dependent direction and the trajectory amplifies rounding-level
+    # differences.  The bound is therefore MEASURED here, from the reference algorithm itself (the fp32 oracle, run on
+    # this GPU with cuDNN/cuFFT, TF32 off): (i) its distance to the CPU reference fixture = backend spread of the
+    # unmodified algorithm; (ii) its own response to a perturbation of the denoiser output at the tolerance the
+    # network is tested to (5e-4 relative, tests/test_gpu_network.py), several noise seeds.  Our trajectory must lie
+    # within twice the largest of those.  (CPU, scripts/blind_backend_spread.py: the oracle with 1 vs 2/4/8 threads
+    # differs by 1.5e-3..1.7e-3 (pred) / 3.9e-3..4.6e-3 (H); perturbations of 1e-4..5e-4 move it by 7.7e-4..5.5e-3 /
+    # 3.7e-3..1.7e-2.)  Every deterministic stage is pinned tightly elsewhere in this file (one-iteration
+    # losses/gradients, update_H 1e-4) and the single-iteration trajectory below holds 1e-3.
+    from oracle import sampler as osm
+    sdc = {k: v.cuda() for k, v in make_state_dict(0).items()}
+
+    def oracle_run(eps, seed):
+        st = osm.BlindState(i["decays"].cuda(), i["weights"].cuda(), i["phases"].cuda(), i["H"].cuda())
+        k = [0]
+
+        def dn(sdd, x, sigma):
+            d = osm.denoise(sdd, x, sigma)
+            if eps:
+                z = randn(seed + k[0], *d.shape).cuda()
+                k[0] += 1
+                d = d + eps * d.detach().norm() / z.norm() * z
+            return d
+        p = osm.dps_blind(sdc, g["y"].cuda(), st, T, [z.cuda() for z in step_noise], [z.cuda() for z in rir_noise],
+                          denoise_fn=dn)
+        return p.detach().cpu(), torch.view_as_real(st.H.detach()).cpu()
+
+    base = oracle_run(0.0, 0)
+    spread = [(rel(base[0], g["pred"]), rel(base[1], torch.view_as_real(g["final_H"])))]
+    for seed in (7, 70, 700, 7000):
+        r = oracle_run(5e-4, seed)
+        spread.append((rel(r[0], base[0]), rel(r[1], base[1])))
+    b_pred, b_H = 2 * max(v[0] for v in spread), 2 * max(v[1] for v in spread)
+    print("[blind DPS T2] reference-algorithm spread on this GPU (pred, H): " +
+          ", ".join(f"({a:.1e}, {b:.1e})" for a, b in spread) + f" -> bounds {b_pred:.1e} / {b_H:.1e}")
+    assert e_pred < max(b_pred, 1e-3) and e_H < max(b_H, 1e-3) and e_d < 5e-3 and e_w < 5e-3
+    assert e_pred < 1e-2        # whatever the measured spread: never looser than this
+
+
+def _blind_case(B, n):
+    """B synthetic blind problems with DIFFERENT operator initialisations (decays / weights / phases per utterance)."""
+    from buddy_b200.blind import BlindEngine
+    y = (randn(900, B, n) * 0.05).cuda()
+    decays = torch.stack([torch.full((25,), 0.5 - 0.05 * b) for b in range(B)]).cuda()
+    weights = torch.stack([torch.full((25,), 2.0 + 0.2 * b) for b in range(B)]).cuda()
+    phases = ((torch.rand(B, 513, 100, generator=torch.Generator().manual_seed(901)) * 2 - 1) * 3.14159).cuda()
+    eng = BlindEngine(n, "cuda")
+    eng.init_state(B, decays, weights, phases, torch.zeros(B, 513, 100, dtype=torch.complex64))
+    eng.select(slice(0, B))
+    H = torch.view_as_complex(eng.update_H().contiguous()).clone()
+    return y, decays, weights, phases, H
+
+
+class _Op:      # duck-typed stand-in for the reference BlindSubbandFiltering object (only its state is read)
+    def __init__(self, decays, weights, phases, H):
+        self.params, self.params_phases, self.H = [decays.clone(), weights.clone()], [phases.clone()], H.clone()
+
+
+def test_blind_batched_matches_single_utterance_runs():
+    """B = 4 blind DPS (T = 2, 10 operator iterations per step) in micro-batches of 2 == every utterance run alone:
+    per-utterance H / parameter / Adam-state slicing (`BlindEngine.select`), micro-batch offsets, and the per-utterance
+    Philox streams of the step noise and of the RIR-noise regulariser (samplers.optimize_op)."""
+    from buddy_b200.edm import EDM
+    from buddy_b200.ncsnpp import NCSNppTime
+    from buddy_b200.samplers import EulerHeunSamplerDPS
+    from oracle import ref_harness as rh
+    from oracle.weights import make_state_dict
+    B, n, T = 4, 8192, 2
+    y, decays, weights, phases, H = _blind_case(B, n)
+    net = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    net.load_state_dict(make_state_dict(0))
+    net = net.cuda().eval()
+    edm = EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10))
+
+    def run(rows, mb, offset):
+        smp = EulerHeunSamplerDPS(net, edm, rh.make_args("blind", T))
+        smp.seed_base, smp.utterance_offset, smp.micro_batch = 3000, offset, mb
+        op = _Op(decays[rows], weights[rows], phases[rows] if rows.stop - rows.start > 1 else phases[rows][0],
+                 H[rows] if rows.stop - rows.start > 1 else H[rows][0])
+        pred = smp.predict_conditional(y[rows], op, shape=(rows.stop - rows.start, n), blind=True)
+        return pred, op
+
+    pred, op = run(slice(0, B), 2, 0)
+    assert op.H_batch.shape == (B, 513, 100)
+    for b in range(B):
+        p1, o1 = run(slice(b, b + 1), 1, b)
+        e, eH = rel(p1, pred[b:b + 1]), rel(torch.view_as_real(o1.H), torch.view_as_real(op.H_batch[b]))
+        ed = rel(o1.params[0], op.params_batch[0][b:b + 1])
+        print(f"\n[blind batched vs alone, utt {b}] pred {e:.1e} H {eH:.1e} decays {ed:.1e}")
+        assert e < 1e-5 and eH < 1e-5 and ed < 1e-5
+
+
+def test_blind_full_size_trajectory_vs_oracle():
+    """The benchmarked blind shape (65 536 samples, BASELINE configs[2]/[3]), B = 2 with different operator
+    initialisations, T = 2 with one operator update per step (no chaotic amplification) vs per-utterance oracle runs
+    on the GPU."""
+    from buddy_b200.edm import EDM
+    from buddy_b200.ncsnpp import NCSNppTime
+    from buddy_b200.samplers import EulerHeunSamplerDPS
+    from oracle import ref_harness as rh
+    from oracle import sampler as osm
+    from oracle.weights import make_state_dict
+    B, n, T = 2, 65536, 2
+    y, decays, weights, phases, H = _blind_case(B, n)
+    sd = make_state_dict(0)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    net = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    step_noise = [randn(910 + k, B, n).cuda() for k in range(T + 1)]
+    rir_noise = [randn(920 + k, B, 13824).cuda() for k in range(T)]
+    args = rh.make_args("blind", T)
+    args.tester.posterior_sampling.blind_hp["op_updates_per_step"] = 1
+    smp = EulerHeunSamplerDPS(net, EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10)), args)
+    order = [step_noise[0]]
+    for k in range(T):
+        order += [step_noise[1 + k], rir_noise[k]]
+    smp.noise_source = iter(order)
+    op = _Op(decays, weights, phases, H)
+    pred = smp.predict_conditional(y, op, shape=(B, n), blind=True)
+    for b in range(B):
+        st = osm.BlindState(decays[b:b + 1], weights[b:b + 1], phases[b], H[b])
+        pref = osm.dps_blind(sdc, y[b:b + 1], st, T, [z[b:b + 1] for z in step_noise], [z[b] for z in rir_noise],
+                             n_iter=1)
+        e = rel(pred[b:b + 1], pref)
+        eH = rel(torch.view_as_real(op.H_batch[b]), torch.view_as_real(st.H.detach()))
+        print(f"\n[blind DPS full size, utt {b}] pred {e:.2e} H {eH:.2e}")
+        assert e < 1e-3 and eH < 5e-3
 
 
 def test_blind_single_iteration_trajectory_vs_oracle():

@@ -120,6 +120,14 @@ def test_informed_dps_sampler(sd):
     assert rel(pred, g["pred"]) < 1e-3
 
 
+def test_informed_dps_order2_with_magnitude_constraint(sd):
+    """Order 2 + constraint_speech_magnitude: the rescale follows the first evaluation of a step only."""
+    g = gold("sampler_informed_T2_rescale.pt")
+    noise = [randn(g["noise_seed0"] + i, 1, g["n"]) for i in range(g["T"] + 1)]
+    pred = osm.dps_informed(sd, g["y"], g["h"], g["T"], noise, rescale=True)
+    assert rel(pred, g["pred"]) < 1e-3
+
+
 def test_blind_dps_sampler(sd):
     """Blind path incl. the filter-design chain, Adam, projection and the RIR-noise regulariser.  The 27->513 band
     interpolation is the torchcde stand-in on BOTH sides (parity unpinned at that one call, see oracle/__init__.py)."""
