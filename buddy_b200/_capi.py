@@ -37,6 +37,7 @@ class GemmDesc(ctypes.Structure):
         ("b8", c_void_p),
         ("a8_2", c_void_p), ("a8_2_c", c_int), ("a8_2_stride_w", c_i64), ("a8_2_stride_h", c_i64),
         ("a8_2_stride_b", c_i64), ("b8_2", c_void_p), ("no_staged_epilogue", c_int), ("no_cta_pairs", c_int), ("debug_flags", c_int), ("one_tap_per_stage", c_int),
+        ("single_tile_per_cta", c_int),
         ("gnb_x", c_void_p), ("gnb_stats", c_void_p), ("gnb_gamma", c_void_p), ("gnb_beta", c_void_p),
         ("gnb_gsum", c_void_p), ("gnb_groups", c_int), ("gnb_eps", c_float), ("gnb_silu", c_int),
     ]
@@ -83,6 +84,16 @@ def reset_launch_count():
 
 
 c_double_p = ctypes.c_void_p
+
+
+class PackDesc(ctypes.Structure):
+    """Mirror of `buddy_pack_desc`."""
+    _fields_ = [
+        ("src", c_void_p), ("off0", c_i64), ("st", c_i64), ("ndiv", c_int), ("sn_outer", c_i64), ("sn_inner", c_i64),
+        ("kdiv", c_int), ("sk_outer", c_i64), ("sk_inner", c_i64),
+        ("T", c_int), ("N", c_int), ("K", c_int), ("n_valid", c_int), ("k_valid", c_int), ("passes", c_int),
+        ("w16", c_void_p), ("w8", c_void_p),
+    ]
 
 
 class GnDesc(ctypes.Structure):

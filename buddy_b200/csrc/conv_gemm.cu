@@ -53,6 +53,9 @@ struct GemmParams {
   // (chunk, tap).
   int halo, patch_bytes, patch1_bytes, a_pitch, a_stage_bytes, stages_a, stages_b;
   int acc_stages, acc_stride;   // TMEM accumulator ring
+  int mt;   // pixel tiles (of bh x bw) stacked vertically per CTA and work item: 1, or 2 for N <= 128 3x3 launches —
+            // every weight tile then feeds two accumulators (M = 256 per CTA), halving the weight stream that
+            // dominates the L2->SM traffic of those layers; the two halves share one (2*bh + 2)-row halo patch
   int tpb;  // taps per B-ring stage (3x3 phases): 3 = one kernel row of weights per stage (one TMA load, one wait, one
             // commit per 12 MMAs — the issue loop, not the tensor pipe, bounds layers with N <= 128), else 1
   float* out32;
@@ -168,8 +171,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // work items: (pixel tile | pixel-tile pair) x n-tile; a pair's second tile may lie past the end (b == batch):
   // its TMA loads are zero-filled, its stores clipped, its statistics skipped
   const int total_tiles = (kPair ? ((pix_tiles + 1) >> 1) : pix_tiles) * p.n_tiles;
-  const int t_first = kPair ? (blockIdx.x >> 1) : blockIdx.x;
-  const int t_step = kPair ? (gridDim.x >> 1) : gridDim.x;
+  // blocked assignment: CTA (pair) k works on the consecutive work items [t_begin, t_end) — it stays inside one image
+  // as long as possible, so the epilogue's running GroupNorm sums are flushed (fp64 atomics) a few times per launch
+  const int n_workers = kPair ? (gridDim.x >> 1) : gridDim.x;
+  const int worker = kPair ? (blockIdx.x >> 1) : blockIdx.x;
+  const int t_begin = static_cast<int>(static_cast<long long>(total_tiles) * worker / n_workers);
+  const int t_end = static_cast<int>(static_cast<long long>(total_tiles) * (worker + 1) / n_workers);
+  const int th = p.bh * p.mt;   // pixel rows per work item and CTA
   // contraction order: phases [fp8 conv | fp8 skip conv | fp16 conv | fp16 skip conv]; inside a phase: channel chunk
   // outer (one A stage each), tap inner (one B stage each)
 
@@ -180,12 +188,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (!(p.dbg & 4)) {   // dbg 4 (profiling): no loads at all, the MMA loop runs on stale smem
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int t = t_first; t < total_tiles; t += t_step) {
+      for (int t = t_begin; t < t_end; ++t) {
         const int nt = t % p.n_tiles;
         const int pt = kPair ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
         const int b = pt / tiles_per_img;
         const int r = pt - b * tiles_per_img;
-        const int h0 = (r / p.tiles_w) * p.bh;
+        const int h0 = (r / p.tiles_w) * th;
         const int w0 = (r % p.tiles_w) * p.bw;
         const int brow = nt * p.n_tile + static_cast<int>(rank) * b_rows;   // first weight row this CTA loads
         for (int ph = 0; ph < 4; ++ph) {
@@ -261,7 +269,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = t_first; t < total_tiles; t += t_step) {
+      for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
@@ -294,6 +302,46 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   const uint64_t da = make_sw128_kmajor_desc(a_addr + a_off, a_sbo);
                   const uint64_t db = make_sw128_kmajor_desc(b_addr + tt * b_tile_bytes);
                   const bool first = fresh && tt == 0;
+                  if (p.mt == 2) {
+                    // two stacked pixel tiles per CTA: the same weight tile feeds accumulator halves 0 / 1 (rows
+                    // 0..bh-1 / bh..2bh-1 of the shared halo patch)
+                    const uint64_t da1 = make_sw128_kmajor_desc(a_addr + a_off + p.bh * p.a_pitch, a_sbo);
+                    const uint32_t d1 = d_tmem + (p.acc_stride >> 1);
+                    if (f8) {
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) {
+                        const uint32_t accu = (first && k == 0) ? 0u : 1u;
+                        if (kPair) {
+                          umma_f8_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc8, accu);
+                          umma_f8_2sm(d1, da1 + 2 * k, db + 2 * k, idesc8, accu);
+                        } else {
+                          umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc8, accu);
+                          umma_f8(d1, da1 + 2 * k, db + 2 * k, idesc8, accu);
+                        }
+                      }
+                    } else {
+                      const bool fold = unscaled8 && tt == 0;
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) {
+                        const uint32_t accu = (first && k == 0) ? 0u : 1u;
+                        if (fold && k == 0) {
+                          if (kPair) {
+                            umma_f16_scale_d14_2sm(d_tmem, da, db, idesc);
+                            umma_f16_scale_d14_2sm(d1, da1, db, idesc);
+                          } else {
+                            umma_f16_scale_d14(d_tmem, da, db, idesc);
+                            umma_f16_scale_d14(d1, da1, db, idesc);
+                          }
+                        } else if (kPair) {
+                          umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
+                          umma_f16_2sm(d1, da1 + 2 * k, db + 2 * k, idesc, accu);
+                        } else {
+                          umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, accu);
+                          umma_f16(d1, da1 + 2 * k, db + 2 * k, idesc, accu);
+                        }
+                      }
+                    }
+                  } else
                   // each MMA consumes 32 bytes of K per row (16 fp16 or 32 e4m3): +2 in (addr >> 4) units
                   if (f8) {
 #pragma unroll
@@ -405,15 +453,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     };
-    for (int t = t_first; t < total_tiles; t += t_step) {
+    for (int t = t_begin; t < t_end; ++t) {
       const int nt = t % p.n_tiles;
       const int pt = kPair ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
       const int b = pt / tiles_per_img;
       const int r = pt - b * tiles_per_img;
-      const int h0 = (r / p.tiles_w) * p.bh;
+      const int h0 = (r / p.tiles_w) * th;
       const int w0 = (r % p.tiles_w) * p.bw;
       const bool in_batch = b < p.batch;   // false only for the padding tile of an odd pair count
-      const bool valid = in_batch && (h0 + hl < p.H) && (w0 + wl < p.W);
       const int ncol_base = nt * p.n_tile;
       if (p.stats && in_batch && (b != st_b || ncol_base != st_col)) {
         flush_stats();
@@ -462,11 +509,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * p.acc_stride;
+      const int half_cols = p.acc_stride >> 1;      // TMEM column offset of the second stacked tile (mt == 2)
+      const int nvc = nchunks * p.mt;               // virtual chunks of this work item: [half][32-column chunk]
       if (p.dbg & 3) {   // profiling experiment: no stores / statistics; dbg 2 still reads the accumulator
         if (p.dbg & 2) {
           uint32_t dd[32];
-          for (int c = 0; c < nchunks; ++c) {
-            tmem_ld_32x32(taddr + c * 32, dd);
+          for (int c = 0; c < nvc; ++c) {
+            tmem_ld_32x32(taddr + (c >= nchunks ? half_cols + (c - nchunks) * 32 : c * 32), dd);
             tmem_ld_wait_dep(dd);
             if (dd[0] == 0x7fc12345u && dd[1] == 0x12345u) bias_s[0] = 1.f;
           }
@@ -486,14 +535,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t rr[32];
       tmem_ld_32x32(taddr, rr);
       tmem_ld_wait_dep(rr);
-      for (int c = 0; c < nchunks; ++c, ++cc) {
+      for (int vc = 0; vc < nvc; ++vc, ++cc) {
+        const int hf = vc >= nchunks ? 1 : 0;        // which stacked tile
+        const int c = vc - hf * nchunks;             // 32-column chunk inside it
+        const int h0v = h0 + hf * p.bh;
+        const bool valid = in_batch && (h0v + hl < p.H) && (w0 + wl < p.W);
         const int sbuf = cc & 1;
         uint8_t* srow = stage_out + sbuf * kChunkBytes + m * 128;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
-        if (c + 1 < nchunks) {
-          tmem_ld_32x32(taddr + (c + 1) * 32, rr);   // in flight while this chunk is finished
+        if (vc + 1 < nvc) {
+          // next virtual chunk's load in flight while this one is finished
+          const int nv = vc + 1;
+          tmem_ld_32x32(taddr + (nv >= nchunks ? half_cols + (nv - nchunks) * 32 : nv * 32), rr);
         } else {
           // every TMEM read of this accumulator has landed in registers: hand it back to the MMA warp
           tc_fence_before();
@@ -535,7 +590,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // 16 values), one fp64 atomic pair per bundle per warp.
           float part[16];
           {
-            const long long pix = (static_cast<long long>(b) * p.H + (h0 + hl)) * p.W + (w0 + wl);
+            const long long pix = (static_cast<long long>(b) * p.H + (h0v + hl)) * p.W + (w0 + wl);
             const float4* xp = reinterpret_cast<const float4*>(p.gnb_x + pix * p.n_total + ncol_base + c * 32);
             const float* rs = gnb_s + c * 32;
 #pragma unroll
@@ -589,12 +644,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elected) tma_store_wait_read0();   // the previous chunk's store no longer reads the other buffer
         named_bar_sync(1, kEpiThreads);
         if (elected) {
-          tma_store_4d(&tmOut, stage_out + sbuf * kChunkBytes, ncol_base + c * 32, w0, h0, b);
-          tma_store_commit();
-          if (p.res_staged && c + 1 < nchunks) {
+          if (!(p.dbg & 8)) {   // dbg 8 (profiling): everything but the output stores
+            tma_store_4d(&tmOut, stage_out + sbuf * kChunkBytes, ncol_base + c * 32, w0, h0v, b);
+            tma_store_commit();
+          }
+          if (p.res_staged && vc + 1 < nvc) {
+            const int nv = vc + 1, nhf = nv >= nchunks ? 1 : 0;
             mbar_expect_tx(&res_bar[sbuf ^ 1], kChunkBytes);
-            tma_load_4d(&tmRes, stage_out + (sbuf ^ 1) * kChunkBytes, &res_bar[sbuf ^ 1], ncol_base + (c + 1) * 32, w0,
-                        h0, b);
+            tma_load_4d(&tmRes, stage_out + (sbuf ^ 1) * kChunkBytes, &res_bar[sbuf ^ 1],
+                        ncol_base + (nv - nhf * nchunks) * 32, w0, h0 + nhf * p.bh, b);
           }
         }
         if (p.stats && in_batch) {
@@ -615,7 +673,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               st_q[i] += static_cast<double>(q);
             }
         }
-        if (c + 1 < nchunks) tmem_ld_wait_dep(rr);
+        if (vc + 1 < nvc) tmem_ld_wait_dep(rr);
       }
       if (++acc == p.acc_stages) {
         acc = 0;
@@ -633,7 +691,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tmem_empty_leader = kPair ? mapa_u32(tmem_empty, 0) : 0u;
-    for (int t = t_first; t < total_tiles; t += t_step) {
+    for (int t = t_begin; t < t_end; ++t) {
       const int nt = t % p.n_tiles;
       const int pt = kPair ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
       const int b = pt / tiles_per_img;
@@ -903,13 +961,21 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   } else {
     choose_patch(d->H, d->W, &p.bh, &p.bw);
   }
-  const int patch_rows = p.bh + 2 * p.halo;
+  // staged epilogue (TMA stores of 128x32 fp32 chunks): dense fp32 output whose tile columns are whole chunks
+  p.staged = (!d->out_fp16 && d->ldc == d->n_total && d->col_off == 0 && d->n_tile % 32 == 0 &&
+              d->n_total % d->n_tile == 0 && (!d->resid || d->ld_res == d->n_total) && !d->no_staged_epilogue)
+                 ? 1
+                 : 0;
+  p.res_staged = (p.staged && d->resid) ? 1 : 0;
+  // two stacked pixel tiles per CTA (see GemmParams::mt): plain 3x3 launches with N <= 128 and the staged epilogue
+  p.mt = (p.halo && p.staged && d->n_tile <= 128 && !d->a2 && !d->gnb_x && !d->single_tile_per_cta && d->H > p.bh) ? 2 : 1;
+  const int patch_rows = p.bh * p.mt + 2 * p.halo;
   const int patch_cols = p.bw + 2 * p.halo;
   p.a_pitch = patch_cols * 128;
   p.patch_bytes = patch_rows * patch_cols * 128;
   p.patch1_bytes = p.bh * p.bw * 128;
   p.a_stage_bytes = (p.patch_bytes + 1023) & ~1023;
-  p.tiles_h = (d->H + p.bh - 1) / p.bh;
+  p.tiles_h = (d->H + p.bh * p.mt - 1) / (p.bh * p.mt);
   p.tiles_w = (d->W + p.bw - 1) / p.bw;
   p.n_tile = d->n_tile;
   p.n_total = d->n_total;
@@ -932,12 +998,6 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   const int b_box_rows = pair ? d->n_tile / 2 : d->n_tile;
   const int a_stage_bytes = p.a_stage_bytes;
   const int b_stage_bytes = b_box_rows * 128;
-  // staged epilogue (TMA stores of 128x32 fp32 chunks): dense fp32 output whose tile columns are whole chunks
-  p.staged = (!d->out_fp16 && d->ldc == d->n_total && d->col_off == 0 && d->n_tile % 32 == 0 &&
-              d->n_total % d->n_tile == 0 && (!d->resid || d->ld_res == d->n_total) && !d->no_staged_epilogue)
-                 ? 1
-                 : 0;
-  p.res_staged = (p.staged && d->resid) ? 1 : 0;
   if (d->gnb_x) {
     if (!p.staged || !d->gnb_stats || !d->gnb_gamma || !d->gnb_beta || !d->gnb_gsum || d->gnb_groups <= 0 ||
         d->n_total % d->gnb_groups || (d->n_total / d->gnb_groups) % 4) {
@@ -948,8 +1008,8 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   }
   // TMEM: 512 columns = 2 accumulators of up to 256 columns, or 4 of up to 128 (more slack for the epilogue of the
   // short N <= 128 mainloops)
-  p.acc_stages = d->n_tile <= 128 ? 4 : 2;
-  p.acc_stride = d->n_tile <= 128 ? 128 : 256;
+  p.acc_stages = (d->n_tile <= 128 && p.mt == 1) ? 4 : 2;
+  p.acc_stride = (d->n_tile <= 128 && p.mt == 1) ? 128 : 256;
   const int epi_bytes = p.staged ? 2 * kChunkBytes + 1024 + (d->gnb_x ? 4096 : 0) : 0;
   const int ring_bytes = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - epi_bytes;
   p.tpb = 1;
@@ -957,7 +1017,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
     // a patch stage lasts nine weight tiles: three of them, the rest of the shared memory goes to the weight ring —
     // as kernel rows of three taps per stage when at least three such stages fit (N <= 128 in pair mode)
     // (a fused 1x1 skip phase drains one patch stage per k-block: one more stage keeps the ring ahead of it)
-    p.stages_a = d->a2 ? 4 : 3;
+    p.stages_a = d->a2 ? 4 : (p.mt == 2 ? 2 : 3);
     if (!d->one_tap_per_stage && (ring_bytes - p.stages_a * a_stage_bytes) / (3 * b_stage_bytes) >= 3) p.tpb = 3;
     p.stages_b = (ring_bytes - p.stages_a * a_stage_bytes) / (p.tpb * b_stage_bytes);
   } else {

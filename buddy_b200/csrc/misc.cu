@@ -5,6 +5,8 @@
 //     torch.randn(...).to(device) of testing/EulerHeunSampler.py:21,43 — results do not depend on the GPU count)
 //   * per-utterance linear combinations used by the Euler/Heun/DPS update algebra
 //     (testing/EulerHeunSamplerDPS.py:115-157, diff_params/edm.py:83-96, diff_params/shared.py:120)
+#include <cuda_fp8.h>
+
 #include <atomic>
 
 #include "../../include/buddy_b200.h"
@@ -104,9 +106,51 @@ __global__ void lincomb3_kernel(const float* __restrict__ x, const float* __rest
     out[base + i] = v;
   }
 }
+
+// ---- one-off weight repacking (see buddy_pack_desc): thread = one (t, n, k) element of the packed operand
+__global__ void pack_weights_kernel(const buddy_pack_desc d) {
+  const long long total = static_cast<long long>(d.T) * d.N * d.K;
+  __half* w16 = static_cast<__half*>(d.w16);
+  uint8_t* w8 = static_cast<uint8_t*>(d.w8);
+  const long long ld16 = static_cast<long long>(d.passes) * d.K;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % d.K);
+    const int n = static_cast<int>((i / d.K) % d.N);
+    const int t = static_cast<int>(i / (static_cast<long long>(d.K) * d.N));
+    float w = 0.f;
+    if (n < d.n_valid && k < d.k_valid)
+      w = d.src[d.off0 + t * d.st + (n / d.ndiv) * d.sn_outer + (n % d.ndiv) * d.sn_inner +
+                (k / d.kdiv) * d.sk_outer + (k % d.kdiv) * d.sk_inner];
+    const __half hi = __float2half_rn(w);
+    const float hif = __half2float(hi);
+    __half* r16 = w16 + (static_cast<long long>(t) * d.N + n) * ld16;
+    r16[k] = hi;
+    if (d.passes >= 2) r16[d.K + k] = hi;
+    if (d.passes >= 3) r16[2 * d.K + k] = __float2half_rn(w - hif);
+    if (w8) {
+      uint8_t* r8 = w8 + (static_cast<long long>(t) * d.N + n) * (2LL * d.K);
+      r8[k] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(hif * 32.f, __NV_SATFINITE, __NV_E4M3));
+      r8[d.K + k] = static_cast<uint8_t>(__nv_cvt_float_to_fp8((w - hif) * 16384.f, __NV_SATFINITE, __NV_E4M3));
+    }
+  }
+}
 }  // namespace buddy
 
 using namespace buddy;
+
+extern "C" int buddy_pack_weights(const buddy_pack_desc* d, void* stream) {
+  if (!d || !d->src || !d->w16 || d->T <= 0 || d->N <= 0 || d->K <= 0 || d->ndiv <= 0 || d->kdiv <= 0 ||
+      d->passes < 1 || d->passes > 3 || d->n_valid > d->N || d->k_valid > d->K) {
+    set_last_error("buddy_pack_weights: invalid descriptor");
+    return BUDDY_ERR_INVALID;
+  }
+  const long long total = static_cast<long long>(d->T) * d->N * d->K;
+  long long gx = (total + 255) / 256;
+  if (gx > 148 * 8) gx = 148 * 8;
+  pack_weights_kernel<<<static_cast<unsigned>(gx), 256, 0, STREAM>>>(*d);
+  LAUNCH_END("pack_weights_kernel");
+}
 
 extern "C" int buddy_fourier_features(const float* t, const float* Wf, int B, int E, float* out, void* stream) {
   fourier_features_kernel<<<(B * E + 255) / 256, 256, 0, STREAM>>>(t, Wf, B, E, out);

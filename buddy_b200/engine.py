@@ -118,11 +118,9 @@ class Engine:
         self.lin1 = (f32(sd["all_modules.1.weight"]), f32(sd["all_modules.1.bias"]))
         self.lin2 = (f32(sd["all_modules.2.weight"]), f32(sd["all_modules.2.bias"]))
         # ---- input conv 2 -> NF as an im2col GEMM (K index = tap*2 + ci, padded to 64)
-        w3 = sd["all_modules.3.weight"]  # [NF, 2, 3, 3]
-        w3c = torch.zeros(NF, 64, device=self.device)
-        w3c[:, :18] = w3.permute(0, 2, 3, 1).reshape(NF, 18)
-        self.in_w = self._pack(w3c[None])                                      # [1, NF, p*64]
-        self.in_wd = self._pack(w3c[:, :32].t().contiguous()[None])            # [1, 32, p*NF]
+        w3 = sd["all_modules.3.weight"].contiguous()  # [NF, 2, 3, 3]; im2col column = tap*2 + ci (18 used)
+        self.in_w = self._packv(w3, 1, NF, 64, sn=(NF, 0, 18), sk=(2, 1, 9), k_valid=18)     # [1, NF, p*64]
+        self.in_wd = self._packv(w3, 1, 32, NF, sn=(2, 1, 9), sk=(NF, 0, 18), n_valid=18)    # [1, 32, p*NF]
         self.in_b = f32(sd["all_modules.3.bias"])
         # ---- walk the module list exactly as the reference builds it
         self.rb = {}
@@ -178,11 +176,18 @@ class Engine:
         w8 = torch.cat([_e4m3(hi * 32.0), _e4m3((w - hi) * 16384.0)], dim=-1).contiguous()
         return WPack(w16, w8)
 
+    def _packv(self, src, T, N, K, x1=False, **kw):
+        """One `buddy_pack_weights` launch on the checkpoint tensor itself (element strides, see ops.pack_weights)."""
+        w16, w8 = ops.pack_weights(src, T, N, K, passes=self.np, e4m3=self.c8 and not x1, **kw)
+        return WPack(w16, w8)
+
     def _pack3x3(self, w, x1=False):
+        """[Co, Ci, 3, 3] -> forward [9, Co, Ci] (tap = 3*ky + kx) and data-gradient [9, Ci, Co] (taps flipped)."""
+        w = w.contiguous()
         co, ci = w.shape[:2]
-        fwd = w.permute(2, 3, 0, 1).reshape(9, co, ci)
-        dgr = w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, ci, co)
-        return self._pack(fwd, x1), self._pack(dgr, x1)
+        fwd = self._packv(w, 9, co, ci, x1, st=1, sn=(co, 0, ci * 9), sk=(ci, 0, 9))
+        dgr = self._packv(w, 9, ci, co, x1, off0=8, st=-1, sn=(ci, 0, 9), sk=(co, 0, ci * 9))
+        return fwd, dgr
 
     def _operand(self, B, H, W, C, gs=1.0, need8=True):
         """need8 = False: every consumer of this operand runs a single fp16 pass (no e4m3 correction pair)."""
@@ -241,9 +246,9 @@ class Engine:
         r.dense = (sd[p + "Dense_0.weight"].contiguous(), sd[p + "Dense_0.bias"].contiguous())
         r.has_skip_conv = (p + "Conv_2.weight") in sd
         if r.has_skip_conv:
-            w2 = sd[p + "Conv_2.weight"].reshape(r.cout, r.cin)
-            r.w2 = self._pack(w2[None], r.x1[1])                    # [1, Cout, p*Cin] (fused into conv 1's launch)
-            r.wd2 = self._pack(w2.t().contiguous()[None], r.x1[1])  # [1, Cin, p*Cout]
+            w2 = sd[p + "Conv_2.weight"].contiguous()               # [Cout, Cin, 1, 1]
+            r.w2 = self._packv(w2, 1, r.cout, r.cin, r.x1[1], sn=(r.cout, 0, r.cin), sk=(r.cin, 0, 1))   # fused into conv 1
+            r.wd2 = self._packv(w2, 1, r.cin, r.cout, r.x1[1], sn=(r.cin, 0, 1), sk=(r.cout, 0, r.cin))
             r.bias1 = (sd[p + "Conv_1.bias"] + sd[p + "Conv_2.bias"]).contiguous()
         else:
             r.bias1 = sd[p + "Conv_1.bias"].contiguous()
@@ -267,21 +272,19 @@ class Engine:
         sd = self.sd
         h = _RB()
         h.g, h.b = sd[f"all_modules.{i}.weight"].contiguous(), sd[f"all_modules.{i}.bias"].contiguous()
-        w = sd[f"all_modules.{i + 1}.weight"]  # [2, C, 3, 3]
+        w = sd[f"all_modules.{i + 1}.weight"].contiguous()  # [2, C, 3, 3]
         c = w.shape[1]
         # forward as ONE 1x1 GEMM to 18 (-> 32) per-tap partial outputs + a 9-tap gather (col2im_c2):
         #   colh[q][t*2+co] = sum_c a[q][c] * W[co][c][8-t],  out[p][co] = sum_t colh[p - off(t)][t*2+co]
         # (a 3x3 tensor-core conv with N = 2 padded to 16 re-reads the operand patches for nothing: 1.5 ms -> 0.4 ms
         # at full resolution, B = 16).  The bias rides on the centre tap, which is always inside the image.
-        fwd = w.flip(2, 3).permute(2, 3, 0, 1).reshape(18, c)
-        h.w = self._pack(_pad_rows(fwd, 32)[None])    # [1, 32, p*C]
+        # row = t*2 + co (18 of 32 used) <- W[co][:, 8 - t]
+        h.w = self._packv(w, 1, 32, c, off0=8, sn=(2, -1, c * 9), sk=(c, 0, 9), n_valid=18)    # [1, 32, p*C]
         bias = torch.zeros(32, device=self.device)
         bias[8:10] = sd[f"all_modules.{i + 1}.bias"]
         h.bias = bias
         # dgrad as an im2col GEMM: dcol[p][tap'*2+co] = dP[p + tap' offset][co];  wd[c][tap'*2+co] = W[co][c][2-ky'][2-kx']
-        wd = torch.zeros(c, 64, device=self.device)
-        wd[:, :18] = w.flip(2, 3).permute(1, 2, 3, 0).reshape(c, 18)
-        h.wd = self._pack(wd[None])                   # [1, C, p*64]
+        h.wd = self._packv(w, 1, c, 64, off0=8, sn=(c, 0, 9), sk=(2, -1, c * 9), k_valid=18)   # [1, C, p*64]
         h.c = c
         self.heads[i] = h
 

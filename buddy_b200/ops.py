@@ -24,7 +24,8 @@ def _pick_n_tile(n_total):
 
 def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=None, bias_b=None, resid=None,
               scale=1.0, stats=None, b_batched=False, col_off=0, ldc=None, max_ctas=0, passes=1, a8=None, w8=None,
-              a8_2=None, w8_2=None, direct_epilogue=False, no_pairs=False, debug_flags=0, one_tap_per_stage=False, gnb=None):
+              a8_2=None, w8_2=None, direct_epilogue=False, no_pairs=False, debug_flags=0, one_tap_per_stage=False, gnb=None,
+              single_tile=False):
     """out[b,h,w,n] = scale*(sum_{tap,k} a[b,h+dy,w+dx,k] w[tap,n,k] + sum_k a2[b,h,w,k] w2[n,k] + bias + bias_b + resid).
 
     a, a2 : fp16 [B,H,W,C] (channel stride 1, other strides arbitrary multiples of 8 elements)
@@ -76,6 +77,7 @@ def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=N
     d.no_cta_pairs = 1 if no_pairs else 0
     d.debug_flags = int(debug_flags)
     d.one_tap_per_stage = 1 if one_tap_per_stage else 0
+    d.single_tile_per_cta = 1 if single_tile else 0
     if gnb is not None:
         # (x, bundle stats of x, gamma, beta, gsum out, groups, eps, silu): fused GroupNorm-backward statistics
         gx, gstats, ggam, gbet, ggsum, ggroups, geps, gsilu = gnb
@@ -105,7 +107,29 @@ def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=N
     return out
 
 
-from ._capi import GnBwdDesc, GnDesc, c_float, c_i64, c_int  # noqa: E402
+from ._capi import GnBwdDesc, GnDesc, PackDesc, c_float, c_i64, c_int  # noqa: E402
+
+
+def pack_weights(src, T, N, K, *, off0=0, st=0, sn=(1, 0, 0), sk=(1, 0, 0), n_valid=None, k_valid=None, passes=1,
+                 e4m3=False):
+    """One launch: fp32 weight `src` (any contiguous tensor, addressed by element strides) -> packed B operand.
+    Element (t, n, k) = src.flatten()[off0 + t*st + (n // ndiv)*sn_outer + (n % ndiv)*sn_inner + (k // kdiv)*sk_outer
+    + (k % kdiv)*sk_inner] with sn = (ndiv, sn_outer, sn_inner), sk = (kdiv, sk_outer, sk_inner).
+    Returns (w16 [T, N, passes*K] fp16, w8 [T, N, 2K] uint8 or None) — see buddy_pack_desc."""
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    w16 = torch.empty(T, N, passes * K, device=src.device, dtype=torch.float16)
+    w8 = torch.empty(T, N, 2 * K, device=src.device, dtype=torch.uint8) if e4m3 else None
+    d = PackDesc()
+    d.src, d.off0, d.st = ptr(src), off0, st
+    d.ndiv, d.sn_outer, d.sn_inner = sn
+    d.kdiv, d.sk_outer, d.sk_inner = sk
+    d.T, d.N, d.K = T, N, K
+    d.n_valid = N if n_valid is None else n_valid
+    d.k_valid = K if k_valid is None else k_valid
+    d.passes = passes
+    d.w16, d.w8 = ptr(w16), ptr(w8)
+    check(lib().buddy_pack_weights(ctypes.byref(d), stream_ptr()), "buddy_pack_weights")
+    return w16, w8
 
 MODE_NONE, MODE_UP, MODE_DOWN = 0, 1, 2
 

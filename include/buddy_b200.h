@@ -112,6 +112,9 @@ typedef struct buddy_gemm_desc {
   int32_t debug_flags;
   /* 1 = one weight tile per pipeline stage even where a kernel row of three fits (testing / A-B timing only) */
   int32_t one_tap_per_stage;
+  /* 1 = one 16x8-pixel tile per CTA and work item even where two stacked tiles share every weight tile (plain 3x3
+   * launches with n_tile <= 128); testing / A-B timing only */
+  int32_t single_tile_per_cta;
   /* Fused GroupNorm-backward statistics (staged epilogue only).  When this launch is the data-gradient convolution
    * whose output `da` is the gradient w.r.t. act(GroupNorm(x)) of a tensor x of the SAME geometry (no resampling in
    * between, single tensor), the epilogue also accumulates, per (image, group),
@@ -131,6 +134,27 @@ typedef struct buddy_gemm_desc {
 } buddy_gemm_desc;
 
 int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream);
+
+/* One-off repacking of a convolution / linear weight into buddy_conv_gemm's B operand (replaces the eager
+ * permute / cast / cat chain a PyTorch host would run; reference weights: nn.Conv2d.weight [Co][Ci][kh][kw],
+ * networks/ncsnpp_utils/layers.py:100-126).  Element (t, n, k) of the packed operand is read from
+ *     src[off0 + t*st + (n / ndiv)*sn_outer + (n % ndiv)*sn_inner + (k / kdiv)*sk_outer + (k % kdiv)*sk_inner]
+ * (element strides of the fp32 source; n >= n_valid or k >= k_valid: zero padding), which covers forward 3x3
+ * weights, their flipped / transposed data-gradient form and the im2col-ordered thin convolutions.
+ *   w16 : fp16 [T][N][passes*K] = [hi] | [hi | hi] | [hi | hi | lo],  hi = fp16(w), lo = fp16(w - hi)
+ *   w8  : optional uint8 [T][N][2K] = [e4m3(hi * 2^5) | e4m3((w - hi) * 2^14)]  (buddy_gemm_desc.b8) */
+typedef struct buddy_pack_desc {
+  const float* src;
+  int64_t off0, st;
+  int32_t ndiv;
+  int64_t sn_outer, sn_inner;
+  int32_t kdiv;
+  int64_t sk_outer, sk_inner;
+  int32_t T, N, K, n_valid, k_valid, passes;
+  void* w16;
+  void* w8; /* or NULL */
+} buddy_pack_desc;
+int buddy_pack_weights(const buddy_pack_desc* d, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------------

@@ -55,6 +55,8 @@ for shp in SHAPES:
         kw["one_tap_per_stage"] = True
     if os.environ.get("DBG"):
         kw["debug_flags"] = int(os.environ["DBG"])
+    if os.environ.get("SINGLE"):
+        kw["single_tile"] = True
     if os.environ.get("NOPAIR"):
         kw["no_pairs"] = True
     if os.environ.get("DIRECT"):

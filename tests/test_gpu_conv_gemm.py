@@ -253,3 +253,37 @@ def test_fused_groupnorm_backward_statistics(B, H, W, C, N):
     assert torch.equal(outs[0][0], outs[1][0])
     assert rel(outs[1][1], outs[0][1]) < 1e-5, rel(outs[1][1], outs[0][1])
     assert rel(outs[1][2], outs[0][2]) < 1e-6, rel(outs[1][2], outs[0][2])
+
+
+@pytest.mark.parametrize("B,H,W,C,N,c8,with_res", [(2, 32, 24, 64, 128, False, True), (3, 19, 37, 64, 128, True, True),
+                                                   (1, 33, 50, 128, 64, False, False), (2, 50, 9, 64, 32, True, True),
+                                                   (1, 256, 528, 128, 128, True, False)])
+def test_stacked_tiles_match_single_tile(B, H, W, C, N, c8, with_res):
+    """Plain 3x3 launches with N <= 128 stack two 16x8-pixel tiles per CTA (every weight tile feeds two accumulators
+    from one (32+2)-row halo patch) — same products in the same order as one tile per CTA: identical output, including
+    heights that are not a multiple of 32 (the lower half hangs over the border) and the residual / statistics path."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.randn(B, H, W, C, device="cuda", generator=g).half()
+    w = (torch.randn(9, N, C, device="cuda", generator=g) * 0.05).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    bias_b = torch.randn(B, N, device="cuda", generator=g)
+    res = torch.randn(B, H, W, N, device="cuda", generator=g) if with_res else None
+    kw = {}
+    if c8:
+        e4 = lambda t: t.clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)
+        kw = dict(a8=e4(torch.randn(B, H, W, 2 * C, device="cuda", generator=g)),
+                  w8=e4(torch.randn(9, N, 2 * C, device="cuda", generator=g)))
+    outs = []
+    for single in (True, False):
+        out = torch.full((B, H, W, N), float("nan"), device="cuda")
+        stats = torch.zeros(B, N // 4, 2, device="cuda", dtype=torch.float64)
+        ops.conv_gemm(a, w, out, taps=9, n_total=N, bias=bias, bias_b=bias_b, resid=res, scale=0.7, stats=stats,
+                      single_tile=single, **kw)
+        torch.cuda.synchronize()
+        outs.append((out, stats))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert rel(outs[1][1], outs[0][1]) < 1e-12
+    if not c8:
+        ref = (ref_conv(a, w, 9) + bias + bias_b[:, None, None, :] + (res if with_res else 0)) * 0.7
+        assert rel(outs[1][0], ref) < 1e-5
