@@ -111,21 +111,49 @@ def peaks():
 
 # --------------------------------------------------------------------------------------------------- CPU arm
 def cpu_reference_step_time(steps, warmup, threads=None):
-    """Oracle port of the reference sampler on the host cores: B = 1, one Euler-Heun DPS step per 'step'."""
-    from oracle import operators as oop
-    from oracle import sampler as osm
+    """The reference's own sampler on the host cores: B = 1, one Euler-Heun DPS step per 'step'.
+
+    kind "reference": the UNMODIFIED reference (`testing.EulerHeunSamplerDPS.step` driving `networks.ncsnpp.NCSNppTime`,
+    `testing.operators.reverb.RIROperator`, `utils.losses`) imported from oracle/_ref (staged by oracle/stage_ref.py;
+    /root/reference in the build container).  kind "port": the oracle restatement, when no reference copy travelled.
+    Must run in a process that sees no GPU (the reference's operators pick "cuda" whenever it is available)."""
+    from oracle import ref_harness as rh
     from oracle.weights import make_state_dict
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     sd = make_state_dict(0)
     s, h = synth_batch(0, 1)
+    g = torch.Generator().manual_seed(3000)
+    times = []
+    if rh.available() and not torch.cuda.is_available():
+        rh.install()
+        from testing.EulerHeunSamplerDPS import EulerHeunSamplerDPS
+        from testing.operators.reverb import RIROperator
+        from utils.losses import get_loss
+        args = rh.make_args("informed", T_STEPS)
+        net, edm = rh.build_network(sd), rh.build_edm()
+        op = RIROperator(args.tester.informed_dereverberation.op_hp, time_kernel_size=h.shape[-1], sample_rate=16000)
+        op.update_params(h[0])
+        y = op.degradation(s)
+        smp = EulerHeunSamplerDPS(net, edm, args)
+        smp.operator, smp.y = op, y
+        smp.rec_loss = get_loss(args.tester.posterior_sampling.rec_loss, operator=op)
+        t = smp.create_schedule()
+        gamma = smp.get_gamma(t)
+        x = smp.initialize_x((1, N_SAMPLES), "cpu", t)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            x, _ = smp.step(x, t[i], t[i + 1], gamma[i], blind=False)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        return sum(times) / len(times), threads, "reference"
+    from oracle import operators as oop
+    from oracle import sampler as osm
     y = oop.fast_apply_rir(s, h[0])
     t = osm.create_schedule(T_STEPS)
     gamma = osm.get_gamma(t, 10)
-    g = torch.Generator().manual_seed(3000)
     x = 0.05 * y / y.std() + t[0] * torch.randn(1, N_SAMPLES, generator=g)
     degrade = lambda v: oop.fast_apply_rir(v, h[0])
-    times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         x_hat, t_hat = osm._perturb(x, t[i], gamma[i], torch.randn(1, N_SAMPLES, generator=g))
@@ -136,14 +164,21 @@ def cpu_reference_step_time(steps, warmup, threads=None):
         x = x_hat + dt * 0.5 * (d + d2)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return sum(times) / len(times), threads
+    return sum(times) / len(times), threads, "port"
+
+
+_SAMPLE = {"reference": "B=1, one Euler-Heun DPS step (2 network fwd+VJP evaluations) per step, fp32: the UNMODIFIED "
+                        "reference (testing.EulerHeunSamplerDPS.step, networks.ncsnpp.NCSNppTime, RIROperator; staged "
+                        "copy oracle/_ref) on all host cores",
+           "port": "B=1, one Euler-Heun DPS step (2 network fwd+VJP evaluations) per step, fp32, oracle port of the "
+                   "reference run on all host cores (no reference copy on this box)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sec, threads = cpu_reference_step_time(args.steps, args.warmup)
+    sec, threads, kind = cpu_reference_step_time(args.steps, args.warmup)
     val = 1.0 / sec
     line = {
         "impl": "reference", "metric": "sampler_steps_per_sec", "value": val, "unit": "utterance-steps/s",
@@ -151,12 +186,25 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(1, "cpu"),
         "utterances_per_sec": val * 2 / EVALS_PER_UTT,
-        "cpu_baseline": {"value": val, "unit": "utterance-steps/s", "cores": threads, "kind": "port",
-                         "sample": "B=1, one Euler-Heun DPS step (2 network fwd+VJP evaluations) per step, fp32, "
-                                   "oracle port of the reference run on all host cores"},
+        "cpu_baseline": {"value": val, "unit": "utterance-steps/s", "cores": threads, "kind": kind,
+                         "sample": _SAMPLE[kind]},
         "e2e": {"value": val, "unit": "utterance-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(steps=1, warmup=0):
+    """The cpu_baseline leg of the GPU arm: the reference arm in a child process that sees no GPU."""
+    import subprocess
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps),
+                          "--warmup", str(warmup)], env=env, capture_output=True, text=True, timeout=900)
+    for ln in reversed(out.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError("cpu baseline subprocess failed: " + out.stderr[-500:])
 
 
 def blind_args(T):
@@ -323,6 +371,8 @@ def run_ours(args):
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
     if rank != 0:
+        if not blind and not long_form and not args.no_extras:
+            extras(args, net, smp, op, y_host, h_host, dev, world, rank, B)     # collective-free, but keeps ranks in step
         if world > 1:
             dist.destroy_process_group()
         return
@@ -338,26 +388,22 @@ def run_ours(args):
         dtype_s = "f16 products + 2 e4m3 correction passes (2 fp16-pass equivalents) / f32 accumulate+activations"
     else:
         dtype_s = f"f16 operands x{eng.np} passes / f32 accumulate+activations"
+    # roofline.traffic: DRAM bytes of the dominant launch cannot be measured outside a profiler; the number reported
+    # is the `ncu --set full` capture of THIS kernel revision committed under profiles/ (file and revision named), per
+    # launch, scaled to this run's utterances per launch; null when no capture of the current revision is present.
     traffic, traffic_note = None, None
-    tp = os.path.join(ROOT, "profiles", "conv_gemm_r01_final_ncu_full.txt")
-    if os.path.exists(tp) and B >= 16 and args.micro_batch >= 16 and not blind and not long_form:
-        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (256->256 3x3 @256x528, 16 utterances,
-        # single pass) from the committed `ncu --set full` capture of this kernel
+    tp = os.path.join(ROOT, "profiles", "conv_gemm_r02_ncu_full.json")
+    if os.path.exists(tp) and not blind and not long_form:
         try:
-            rd = wr = None
-            for ln in open(tp):
-                if ln.startswith("dram__bytes_read.sum"):
-                    rd = float(ln.split(":")[1].split("|")[0])
-                if ln.startswith("dram__bytes_write.sum"):
-                    wr = float(ln.split(":")[1].split("|")[0])
-            mbs = min(B, args.micro_batch) / 16.0       # the capture is at 16 utterances per launch; bytes scale with it
-            traffic = (rd + wr) * 1e9 * mbs
-            traffic_note = ("DRAM bytes per launch of the dominant shape (conv 256->256 3x3 @256x528): ncu capture at 16 "
-                            "utterances per launch in profiles/conv_gemm_r01_final_ncu_full.txt (3.342e9 B vs "
-                            "algorithmic 3.323e9 B = fp16 input 1.107e9 + fp32 output 2.215e9 + weights 1.2e6), scaled "
-                            "to this run's utterances per launch")
-        except Exception:
-            traffic = None
+            cap = json.load(open(tp))
+            mbs = min(B, args.micro_batch) / float(cap["utterances_per_launch"])
+            traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) * mbs
+            traffic_note = (f"ncu --set full capture {cap['file']} (kernel revision {cap['kernel_rev']}): dominant launch "
+                            f"{cap['shape']} at {cap['utterances_per_launch']} utterances per launch, dram read "
+                            f"{cap['dram_bytes_read']:.4g} B + write {cap['dram_bytes_write']:.4g} B vs algorithmic "
+                            f"{cap['algorithmic_bytes']:.4g} B; scaled x{mbs:g} to this run (not measured in this run)")
+        except Exception as e:
+            traffic_note = f"profiles/conv_gemm_r02_ncu_full.json unreadable: {e}"
     total_ms_ops = sum(v[1] for v in summ.values())
     line = {
         "metric": "sampler_steps_per_sec", "value": value, "unit": "utterance-steps/s", "n_gpus": world,
@@ -382,7 +428,16 @@ def run_ours(args):
                      "share_of_step": conv_ms / total_ms_ops if total_ms_ops else None},
         "kernel_time_share": {k: round(v[1] / total_ms_ops, 4) for k, v in
                               sorted(summ.items(), key=lambda kv: -kv[1][1])[:6]},
+        "roofline_secondary": [
+            {"kernel": k, "bound": "hbm", "achieved": summ[k][2] / (summ[k][1] * 1e-3) / 1e9, "peak": peak_gbs,
+             "unit": "GB/s", "frac": summ[k][2] / (summ[k][1] * 1e-3) / 1e9 / peak_gbs, "launches": summ[k][0],
+             "share_of_step": summ[k][1] / total_ms_ops,
+             "achieved_definition": "algorithmic bytes (every input / output tensor of the launch once) / summed "
+                                    "CUDA-event duration; gn_bwd is a two-pass kernel and really moves x and da twice"}
+            for k in ("gn_bwd", "gn_apply") if k in summ and summ[k][1] > 0],
     }
+    if not blind and not long_form and not args.no_extras:
+        line["extra"] = extras(args, net, smp, op, y_host, h_host, dev, world, rank, B)
     if long_form:
         line["config"]["workload"] = ("LONG-FORM informed EulerHeunSamplerDPS T=35 order 2, synthetic 30 s @ 16 kHz "
                                       "(480000 samples -> 256 x 3760 spectrogram, attention over 15040 tokens, "
@@ -397,13 +452,115 @@ def run_ours(args):
         line["config"]["step_definition"] = "one Euler sampler step over the batch = 1 network fwd+VJP + 10 operator updates"
         line["config"]["T"], line["config"]["order"], line["config"]["evals_per_utterance"] = 60, 1, 60
     if world == 1 and not args.no_cpu_baseline and not blind and not long_form:
-        sec, threads = cpu_reference_step_time(1, 0)
-        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "utterance-steps/s", "cores": threads, "kind": "port",
-                                "sample": "B=1, ONE Euler-Heun DPS step (2 fwd+VJP evaluations) of the same config, "
-                                          "oracle port of the reference on all host cores, no warm-up"}
+        line["cpu_baseline"] = cpu_baseline_subprocess(1, 0)
+        line["cpu_baseline"]["sample"] += "; ONE step, no warm-up"
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def extras(args, net, smp, op, y_host, h_host, dev, world, rank, B):
+    """Extra legs of the default bench line, each on this rank's shard and timed with CUDA events:
+       e2e_full   : ONE complete `predict_conditional` (T = 35, order 2: 69 evaluations per utterance) through the
+                    public API with host buffers (H2D of y inside, D2H of the result inside);
+       b1_latency : the reference's own usage, one utterance at a time (CUDA-graph replay), ms per sampler step;
+       blind      : BASELINE configs[2] (batch 128 per GPU, order 1 + 10 operator-Adam iterations per step), 3 steps."""
+    from buddy_b200.edm import EDM
+    from buddy_b200.operators import RIROperator
+    from buddy_b200.samplers import EulerHeunSamplerDPS
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    edm = EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10))
+    # ---- full trajectory
+    res_host = torch.empty(B, N_SAMPLES).pin_memory()
+    torch.cuda.synchronize()
+    e0.record()
+    yd = y_host.to(dev, non_blocking=True)
+    pred = smp.predict_conditional(yd, op, shape=(B, N_SAMPLES))
+    res_host.copy_(pred, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    out["e2e_full"] = {"seconds": sec, "utterances": B, "T": T_STEPS, "evals_per_utterance": EVALS_PER_UTT,
+                       "utterances_per_sec": B / sec, "utterance_steps_per_sec": B * T_STEPS / sec,
+                       "h2d_bytes": B * N_SAMPLES * 4, "d2h_bytes": B * N_SAMPLES * 4,
+                       "what": "one complete predict_conditional(y, RIROperator) per GPU, host buffers in / out"}
+    del pred, yd
+    # ---- B = 1 latency
+    s1 = EulerHeunSamplerDPS(net, edm, informed_args(T_STEPS))
+    s1.seed_base = 3000
+    op1 = RIROperator()
+    op1.update_params(h_host[0].to(dev))
+    y1 = y_host[:1].to(dev)
+    s1.operator, s1.y = op1, y1
+    s1._bind_operator(op1, y1, False)
+    t = s1.create_schedule()
+    gamma = s1.get_gamma(t)
+    s1._start_run()
+    x = s1.initialize_x((1, N_SAMPLES), dev, t)
+    for i in range(3):
+        x, _ = s1.step(x, t[i], t[i + 1], gamma[i])
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(3, 9):
+        x, _ = s1.step(x, t[i], t[i + 1], gamma[i])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 6
+    out["b1_latency"] = {"ms_per_step": ms, "ms_per_evaluation": ms / 2, "utterance_steps_per_sec": 1e3 / ms,
+                         "what": "B = 1 (the reference's own usage, tester.py:153), CUDA-graph replay of forward / VJP"}
+    del s1, x
+    # ---- blind leg (configs[2])
+    torch.cuda.empty_cache()
+    Bb, steps = 128, 3
+    from buddy_b200.blind import BlindEngine
+    sb, hb = synth_batch(rank * Bb, Bb)
+    opb = RIROperator()
+    opb.update_params(hb.to(dev))
+    yb = opb.degradation(sb.to(dev))
+    smb = EulerHeunSamplerDPS(net, edm, blind_args(60))
+    smb.seed_base, smb.utterance_offset, smb.micro_batch = 3000, rank * Bb, args.micro_batch
+    be = BlindEngine(N_SAMPLES, dev)
+    g = torch.Generator().manual_seed(4000 + rank)
+    ph0 = torch.angle(torch.view_as_complex(be.loss_stft.forward(
+        torch.randn(Bb, be.LEN_RIR, generator=g).to(dev))[:, :, 1:101].contiguous()))
+    be.init_state(Bb, torch.full((1, 25), 6.908 / (0.1 * 125)), torch.full((1, 25), 2.0), ph0,
+                  torch.zeros(Bb, 513, 100, dtype=torch.complex64))
+    be.select(slice(0, Bb))
+    H0 = torch.view_as_complex(be.update_H())
+
+    class _Op:
+        pass
+    bop = _Op()
+    bop.params = [be.full["decays"].clone(), be.full["weights"].clone()]
+    bop.params_phases = [torch.angle(H0)]
+    bop.H = H0
+    del be
+    smb.operator, smb.y = bop, yb
+    smb._bind_operator(bop, yb, True)
+    tb = smb.create_schedule()
+    gb = smb.get_gamma(tb)
+    smb._start_run()
+    x = smb.initialize_x((Bb, N_SAMPLES), dev, tb)
+    x, _ = smb.step(x, tb[0], tb[1], gb[0], True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(1, 1 + steps):
+        x, _ = smb.step(x, tb[i], tb[i + 1], gb[i], True)
+    e1.record()
+    torch.cuda.synchronize()
+    msb = e0.elapsed_time(e1)
+    if world > 1:
+        import torch.distributed as dist
+        tms = torch.tensor([msb], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        msb = tms.item()
+    out["blind"] = {"value": world * Bb * steps / (msb * 1e-3), "unit": "utterance-steps/s", "batch_per_gpu": Bb,
+                    "steps": steps, "warmup": 1, "ms_per_step": msb / steps,
+                    "utterances_per_sec": world * Bb * steps / (msb * 1e-3) / 60,
+                    "workload": "BASELINE configs[2]/[3]: blind EulerHeunSamplerDPS T=60 order 1 + 10 operator-Adam "
+                                "iterations per step, 128 utterances per GPU, 4.096 s @ 16 kHz"}
+    return out
 
 
 def main():
@@ -417,6 +574,7 @@ def main():
     ap.add_argument("--streams", type=int, default=1, help="micro-batches in flight on separate CUDA streams")
     ap.add_argument("--precision", default=os.environ.get("BUDDY_PRECISION", "mixed"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (full trajectory, B=1 latency, blind)")
     ap.add_argument("--no-graphs", action="store_true", help="plain launches even for batches <= 8 (profiling)")
     ap.add_argument("--mode", default="informed", choices=["informed", "blind", "long"],
                     help="informed = BASELINE configs[1] (default, the bench line); blind = configs[2] (order 1, T=60, "
@@ -430,6 +588,7 @@ def main():
         if args.micro_batch == 32:
             args.micro_batch = 4
     if args.impl == "reference":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""       # the reference's operators take "cuda" whenever it is available
         run_reference(args)
     else:
         if not torch.cuda.is_available():

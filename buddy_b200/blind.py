@@ -142,6 +142,21 @@ class BlindEngine:
         st, bf = self.state, self.buf
         B, N, T = st["B"], self.N_BIG, self.T_MP
         ops.blind_design_fwd(st["decays"], st["weights"], st["phases"], self.tabs, bf["A"], bf["H0"])
+        H = self._cons_tail()
+        st["H"].copy_(H)
+        return H
+
+    def cons(self, Hin):
+        """`BlindSubbandFiltering.cons` (subband_filtering.py:333-351) of an arbitrary filter [B,513,100,2]:
+        pad one frame each side -> istft(12 800) -> pad 128 -> minimum phase -> h[0] = 2 -> stft, drop first/last frame."""
+        bf = self.buf
+        bf["H0"].zero_()
+        bf["H0"][:, :, 1:-1].copy_(Hin)
+        return self._cons_tail()
+
+    def _cons_tail(self):
+        st, bf = self.state, self.buf
+        B, N, T = st["B"], self.N_BIG, self.T_MP
         fr = torch.empty(B, self.NF + 2, self.WIN, device=self.device)
         ops.stft_synthesis(bf["H0"], self.cons_syn, self.NF + 2, fr)
         ops.ola_gather(fr, self.HOP, self.NFFT // 2, self.LEN_RIR, bf["u"], tab=self._inv_env(self.NF + 2))
@@ -157,7 +172,6 @@ class BlindEngine:
         ops.pad_signal(h2, 384, 384 + T, 0, bf["sig"])
         H = torch.empty(B, self.F, self.NF, 2, device=self.device)
         ops.stft_analysis(bf["sig"], self.cons_ana, self.HOP, self.NF, self.NF, H)
-        st["H"].copy_(H)
         return H
 
     def update_H_backward(self, dH):

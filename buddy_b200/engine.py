@@ -387,6 +387,39 @@ class Engine:
         return dxa, g16a, dxb
 
     # ------------------------------------------------------------------ attention
+    # Attention over N = H*W tokens (AttnBlockpp, layerspp.py:75-91).  Up to ATTN_DENSE_BYTES of logits + probabilities
+    # (4 s utterances: N = 2112, 27 MB per utterance, 0.86 GB for a micro-batch of 32) the N x N matrices are materialised once and P is kept for the
+    # backward pass.  Beyond (30 s: N = 15 040, 1.36 GB per utterance) the block runs over query blocks of ATTN_QBLOCK
+    # rows with exact row-wise softmax — at most ATTN_QBLOCK x N logits exist at a time, nothing N x N is stored, and
+    # the backward pass recomputes each block's probabilities from q, k (flash-attention style recomputation).
+    ATTN_DENSE_BYTES = 1 << 30
+    ATTN_QBLOCK = 2048
+
+    def _attn_blocked(self, B, N):
+        return B * N * N * 6 > self.ATTN_DENSE_BYTES
+
+    def _attn_probs(self, q, k, r0, nq, C):
+        """softmax(q[r0:r0+nq] k^T / sqrt(C)) for one query block: fp16 [B, nq, N] (logits live in fp32 scratch)."""
+        B, N = q.shape[0], q.shape[2]
+        S = torch.empty(B, 1, nq, N, device=self.device)
+        ops.conv_gemm(q[:, :, r0:r0 + nq], k[:, 0], S, taps=1, n_total=N, b_batched=True, scale=float(C) ** -0.5)
+        P = torch.empty(B, nq, N, device=self.device, dtype=torch.float16)
+        return ops.softmax_fwd(S, P)
+
+    def _attn_fwd_blocked(self, q, k, v, C):
+        B, N = q.shape[0], q.shape[2]
+        dev = self.device
+        vT = torch.empty(B, C, N, device=dev, dtype=torch.float16)
+        ops.transpose_h(v[:, 0], vT)
+        o = torch.empty(B, 1, N, C, device=dev, dtype=torch.float16)
+        for r0 in range(0, N, self.ATTN_QBLOCK):
+            nq = min(self.ATTN_QBLOCK, N - r0)
+            P = self._attn_probs(q, k, r0, nq, C)
+            ob = torch.empty(B, 1, nq, C, device=dev, dtype=torch.float16)
+            ops.conv_gemm(P.view(B, 1, nq, N), vT, ob, taps=1, n_total=C, b_batched=True)
+            o[:, :, r0:r0 + nq].copy_(ob)
+        return o
+
     def _attn_fwd(self, x, sx, save):
         a = self.attn
         B, H, W, C = x.shape
@@ -398,6 +431,15 @@ class Engine:
         ops.conv_gemm(hn.view(B, 1, N, C), a.wqkv, qkv, taps=1, n_total=3 * C, bias=a.bqkv)
         del hn
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        if self._attn_blocked(B, N):
+            o = self._attn_fwd_blocked(q, k, v, C)
+            out = torch.empty(B, H, W, C, device=dev)
+            so = self._zeros_stats(B, C)
+            ops.conv_gemm(o.view(B, H, W, C), a.w3, out, taps=1, n_total=C, bias=a.b3, resid=x, scale=INV_SQRT2,
+                          stats=so)
+            if save is not None:
+                save["attn"] = (x, sx, qkv, None)
+            return out, so
         S = torch.empty(B, 1, N, N, device=dev)
         ops.conv_gemm(q, k[:, 0], S, taps=1, n_total=N, b_batched=True, scale=float(C) ** -0.5)
         P = torch.empty(B, N, N, device=dev, dtype=torch.float16)
@@ -423,6 +465,15 @@ class Engine:
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         do = torch.empty(B, 1, N, C, device=dev, dtype=torch.float16)
         ops.conv_gemm(g16.t16.view(B, 1, N, C * self.am)[..., :C], a.w3_d, do, taps=1, n_total=C, scale=1.0 / g16.gs)
+        if P is None:
+            dqkv = self._attn_bwd_blocked(q, k, v, do, C)
+            dhn = torch.empty(B, H, W, C, device=dev)
+            ops.conv_gemm(dqkv.view(B, H, W, 3 * C), a.wqkv_d, dhn, taps=1, n_total=C)
+            dx = torch.empty_like(x)
+            g16x = self._operand(B, H, W, C, self._gscale(("attn",)), need8=not self._x1(consumer, 1))
+            ops.gn_bwd(x, sx, a.g, a.b, dhn, self._scratch_gsum(B), silu=False, dskip=dout32, skip_scale=INV_SQRT2,
+                       dxa=dx, g16a=g16x.t16, g16_scale=INV_SQRT2 * g16x.gs, split=self.split, g8a=g16x.t8)
+            return dx, g16x
         doT = torch.empty(B, C, N, device=dev, dtype=torch.float16)
         ops.transpose_h(do[:, 0], doT)
         PT = torch.empty(B, N, N, device=dev, dtype=torch.float16)
@@ -452,6 +503,41 @@ class Engine:
                    g16a=g16x.t16, g16_scale=INV_SQRT2 * g16x.gs, split=self.split, g8a=g16x.t8)
         self._record(("attn",), g16x)
         return dx, g16x
+
+    def _attn_bwd_blocked(self, q, k, v, do, C):
+        """d(q, k, v) for the query-blocked attention: per block, recompute P, then
+        dP = dO V^T, dS = P * (dP - rowsum(P * dP)) / sqrt(C), dQ = dS K, dK += dS^T Q, dV += P^T dO
+        (dK, dV accumulate over the blocks in fp32)."""
+        B, N = q.shape[0], q.shape[2]
+        dev = self.device
+        h16 = dict(device=dev, dtype=torch.float16)
+        kT = torch.empty(B, C, N, **h16)
+        ops.transpose_h(k[:, 0], kT)
+        dk32 = torch.zeros(B, 1, N, C, device=dev)
+        dv32 = torch.zeros(B, 1, N, C, device=dev)
+        dqkv = torch.empty(B, 1, N, 3 * C, **h16)
+        for r0 in range(0, N, self.ATTN_QBLOCK):
+            nq = min(self.ATTN_QBLOCK, N - r0)
+            P = self._attn_probs(q, k, r0, nq, C)
+            dP = torch.empty(B, 1, nq, N, device=dev)
+            ops.conv_gemm(do[:, :, r0:r0 + nq], v[:, 0], dP, taps=1, n_total=N, b_batched=True)
+            dS = torch.empty(B, nq, N, **h16)
+            ops.softmax_bwd(P, dP, float(C) ** -0.5, dS)
+            del dP
+            dqb = torch.empty(B, 1, nq, C, **h16)
+            ops.conv_gemm(dS.view(B, 1, nq, N), kT, dqb, taps=1, n_total=C, b_batched=True)
+            dqkv[:, :, r0:r0 + nq, :C].copy_(dqb)
+            T = torch.empty(B, N, nq, **h16)               # dS^T, then P^T
+            bT = torch.empty(B, C, nq, **h16)              # q_block^T, then dO_block^T
+            ops.transpose_h(dS, T)
+            ops.transpose_h(q[:, 0, r0:r0 + nq], bT)
+            ops.conv_gemm(T.view(B, 1, N, nq), bT, dk32, taps=1, n_total=C, b_batched=True, resid=dk32)
+            ops.transpose_h(P, T)
+            ops.transpose_h(do[:, 0, r0:r0 + nq], bT)
+            ops.conv_gemm(T.view(B, 1, N, nq), bT, dv32, taps=1, n_total=C, b_batched=True, resid=dv32)
+        dqkv[..., C:2 * C].copy_(dk32)
+        dqkv[..., 2 * C:].copy_(dv32)
+        return dqkv
 
     # ------------------------------------------------------------------ pyramid heads
     def _head_fwd(self, i, h, sh, save):
@@ -520,7 +606,9 @@ class Engine:
 
         graph=True (used by the samplers for batches <= `graph_max_batch`): replay a captured CUDA graph.  The returned
         tensors are the graph's static buffers — valid until the next graphed call of the same shape."""
-        if graph and spec.shape[0] <= self.graph_max_batch and ops._timer is None:
+        # (graphs pin their activations in a private pool: only for launch-bound sizes, up to graph_max_batch 4 s
+        # utterances' worth of frames)
+        if graph and spec.shape[0] * spec.shape[2] <= self.graph_max_batch * 528 and ops._timer is None:
             ent = self._graph_entry(spec, save)
             ent["spec"].copy_(spec)
             ent["tc"].copy_(time_cond)

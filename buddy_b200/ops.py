@@ -493,8 +493,25 @@ def _timed(fn, work_fn=None, tag_fn=_shape_tag):
     return wrapper
 
 
+def _nbytes(*ts):
+    return float(sum(t.numel() * t.element_size() for t in ts if isinstance(t, torch.Tensor)))
+
+
+def _gn_apply_bytes(args, kw):
+    """algorithmic HBM bytes: every input / output tensor exactly once (statistics and affine vectors are noise)"""
+    return _nbytes(args[0], args[4], kw.get("xb"), kw.get("out_raw"), kw.get("out8"), kw.get("out_raw8"))
+
+
+def _gn_bwd_bytes(args, kw):
+    """algorithmic HBM bytes: x, da, dskip, extra and every output once (the two-pass kernel reads x and da twice)"""
+    return _nbytes(args[0], args[4], kw.get("xb"), kw.get("dskip"), kw.get("extra_a"), kw.get("extra_b"),
+                   kw.get("dxa"), kw.get("dxb"), kw.get("g16a"), kw.get("g16b"), kw.get("g8a"), kw.get("g8b"))
+
+
 conv_gemm = _timed(conv_gemm, _conv_flops, _conv_tag)
-for _n in ("gn_stats", "gn_apply", "gn_bwd", "im2col_c2", "col2im_c2", "resample_c2", "combine_fwd", "combine_bwd",
+gn_apply = _timed(gn_apply, _gn_apply_bytes)
+gn_bwd = _timed(gn_bwd, _gn_bwd_bytes)
+for _n in ("gn_stats", "im2col_c2", "col2im_c2", "resample_c2", "combine_fwd", "combine_bwd",
            "affine_c2", "softmax_fwd", "softmax_bwd", "transpose_h", "cast_scale_h", "dft_analysis", "dft_synthesis", "fft_analysis", "fft_synthesis",
            "ola_gather", "pad_signal", "reflect_fold", "comp_loss", "row_stats", "fftconv", "fourier_features",
            "dense", "philox_normal", "lincomb3"):
@@ -552,3 +569,13 @@ def adam_project(p, g, m, v, step, lr, beta1, beta2, eps, dmin, dmax, wmin, wmax
 
 for _n in ("subband_fir", "blind_design_fwd", "blind_design_bwd", "fft_mixed", "minphase_pw", "adam_project"):
     globals()[_n] = _timed(globals()[_n])
+
+
+def wpe(Y, taps, delay, iterations, Z=None):
+    """Y fp32 [B, F, T, 2] -> WPE-filtered spectra, same layout (see buddy_wpe)."""
+    assert Y.dtype == torch.float32 and Y.is_contiguous() and Y.dim() == 4 and Y.shape[3] == 2
+    B, F, T, _ = Y.shape
+    Z = torch.empty_like(Y) if Z is None else Z
+    check(lib().buddy_wpe(ptr(Y), c_int(B), c_int(F), c_int(T), c_int(int(taps)), c_int(int(delay)),
+                          c_int(int(iterations)), ptr(Z), stream_ptr()), "buddy_wpe")
+    return Z

@@ -268,8 +268,16 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
             coef = (float(ps.warm_initialization.scaling_factor) / std).contiguous()
             return ops.lincomb3(torch.empty_like(z), self.y, coef, z, _vec(float(schedule[0]), B, device))
         if mode == "wpe_scaled":
-            raise NotImplementedError("wpe_scaled warm initialisation depends on nara_wpe (third-party, CPU): "
-                                      "out of scope, use reverb_scaled / none (SURVEY.md §8f-2)")
+            # EulerHeunSamplerDPS.py:32-54 — the reference goes to the CPU (nara_wpe, numpy); here STFT -> WPE -> iSTFT
+            # stay on the device, one one-channel problem per utterance (buddy_b200/wpe.py, csrc/wpe.cu)
+            from .wpe import WpeDereverb
+            w = ps.warm_initialization.wpe
+            x_pred = WpeDereverb(device, taps=w.taps, delay=w.delay, iterations=w.iterations)(self.y)
+            st = ops.row_stats(x_pred)
+            n = x_pred.shape[1]
+            std = torch.sqrt((st[:, 1] - st[:, 0] ** 2 / n) / (n - 1)).float()     # unbiased, per utterance
+            coef = (float(ps.warm_initialization.scaling_factor) / std).contiguous()
+            return ops.lincomb3(torch.empty_like(z), x_pred, coef, z, _vec(float(schedule[0]), B, device))
         raise NotImplementedError(mode)
 
     # ---- operator binding -----------------------------------------------------------------------------

@@ -132,7 +132,7 @@ def make_args(mode, T, audio_len=65536, warm="reverb_scaled", rescale=False):
                 project_parameters=True, normalization_type="grad_norm",
                 blind_hp=AD(optimizer="adam", lr_op=0.1, beta1=0.9, beta2=0.99, noise=0.1, lr_op_phase=1,
                             weight_decay=0, op_updates_per_step=10, grad_clip=1),
-                warm_initialization=AD(mode=warm, scaling_factor=0.05),
+                warm_initialization=AD(mode=warm, scaling_factor=0.05, wpe=AD(delay=2, taps=50, iterations=5)),
                 constraint_speech_magnitude=AD(use=True, speech_scaling=0.05))
     elif mode == "unconditional":
         sp = AD(same_as_training=False, sde_hp=sde, Schurn=10, Snoise=1, Stmin=0, Stmax=10, order=2, T=T, schedule="edm")

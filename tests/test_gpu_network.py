@@ -120,3 +120,53 @@ def test_other_lengths_forward_and_vjp_vs_oracle(sd):
         e_out, e_vjp = rel(out.detach(), ref.detach()), rel(gout, gref)
         print(f"\n[net n={n}] fwd rel-L2 {e_out:.2e}  vjp rel-L2 {e_vjp:.2e}")
         assert e_out < TOL and e_vjp < TOL
+
+
+def test_query_blocked_attention_matches_dense(sd):
+    """Long utterances run the bottleneck attention over query blocks with recomputation in the backward pass (no
+    N x N tensor is ever stored): forced here on a 0.5 s utterance (N = 320 tokens, blocks of 128 / 128 / 64) and
+    compared with the dense path — the same softmax rows, so forward and data-gradient agree to fp16 rounding of P."""
+    from buddy_b200.engine import Engine
+    from buddy_b200.spectral import NetSTFT
+    st = NetSTFT("cuda")
+    x = (randn(20, 2, 8192) * 0.2).cuda()
+    tc = torch.full((2,), -0.6, device="cuda")
+    cot = randn(21, 2, 256, 80, 2).cuda()
+    outs = []
+    for blocked in (False, True):
+        eng = Engine(sd, "cuda")
+        if blocked:
+            eng.ATTN_DENSE_BYTES, eng.ATTN_QBLOCK = 0, 128
+        out, ctx = eng.forward(st.forward(x), tc, save=True)
+        assert (ctx["attn"][3] is None) == blocked
+        outs.append((out.clone(), eng.vjp(ctx, cot).clone()))
+    e_f, e_b = rel(outs[1][0], outs[0][0]), rel(outs[1][1], outs[0][1])
+    print(f"\n[blocked attention vs dense] fwd {e_f:.2e} vjp {e_b:.2e}")
+    assert e_f < 1e-4 and e_b < 2e-4
+
+
+def test_long_form_30s_forward_and_vjp_vs_oracle(sd):
+    """BASELINE configs[4]: one 30 s utterance (480 000 samples -> 256 x 3760 spectrogram, attention over 15 040 tokens
+    in query blocks, GroupNorm statistics over 7x the pixels) against the oracle on the GPU, default precision."""
+    from buddy_b200.ncsnpp import NCSNppTime
+    from oracle import net as onet
+    net = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    n = 480000
+    x = (randn(30, 1, 1, n) * 0.2).cuda()
+    tc = torch.tensor([0.25 * torch.log(torch.tensor(0.07))]).cuda()
+    cot = randn(31, 1, 1, n).cuda() * 1e-3
+    xr = x.clone().requires_grad_(True)
+    ref = onet.ncsnpp_time_forward(sdc, xr, tc)
+    (gref,) = torch.autograd.grad((ref * cot).sum(), xr)
+    ref = ref.detach()
+    torch.cuda.empty_cache()
+    xg = x.clone().requires_grad_(True)
+    out = net(xg, tc)
+    assert net.engine()._attn_blocked(1, 15040)
+    (gout,) = torch.autograd.grad((out * cot).sum(), xg)
+    e_out, e_vjp = rel(out.detach(), ref), rel(gout, gref)
+    print(f"\n[net 30 s] fwd rel-L2 {e_out:.2e}  vjp rel-L2 {e_vjp:.2e}")
+    assert e_out < TOL and e_vjp < TOL

@@ -159,3 +159,61 @@ def test_fft_stft_kernels_match_dft_matrix_form(frames, K):
     fr_d = ops.dft_synthesis(S, mat.float().contiguous(), frames, torch.empty(B, frames, K, device="cuda"))
     ref_s = torch.einsum("bmt,mk->btk", S.double().permute(0, 1, 3, 2).reshape(B, 2 * bins, frames), mat)
     assert rel(fr_f, ref_s) < 2e-6 and rel(fr_d, ref_s) < 1e-5, (rel(fr_f, ref_s), rel(fr_d, ref_s))
+
+
+def test_wpe_warm_start_vs_oracle():
+    """`wpe_scaled` warm start (EulerHeunSamplerDPS.py:32-54): STFT(512/128, Blackman, fading) -> WPE (50 taps, delay 2,
+    5 iterations, per bin, fp64) -> iSTFT on the GPU vs the numpy restatement of nara_wpe (oracle/wpe.py — parity
+    unpinned: the package is absent, the algorithm is restated from its publication).  Ragged length, B = 2."""
+    import numpy as np
+    from buddy_b200 import ops
+    from buddy_b200.wpe import WpeDereverb
+    from oracle import wpe as ow
+    n = 20517
+    rng = np.random.default_rng(3)
+    ys = []
+    for b in range(2):
+        s = np.convolve(rng.standard_normal(n), np.ones(6) / 6)[:n]
+        h = rng.standard_normal(4000) * np.exp(-np.arange(4000) / (400.0 + 300 * b))
+        h[0] = 1.0
+        ys.append(0.05 * np.convolve(s, h)[:n])
+    y = torch.tensor(np.stack(ys), dtype=torch.float32).cuda()
+    wd = WpeDereverb("cuda")
+    Y = wd.stft(y)
+    Yo = np.stack([ow.stft(y[b].cpu().double().numpy()).T for b in range(2)])        # (B, 257, T)
+    assert Y.shape[1:3] == Yo.shape[1:3]
+    assert rel(Y.cpu(), torch.view_as_real(torch.from_numpy(Yo))) < 1e-5
+    # the kernel alone on the oracle's own spectra (fp32 in / out, fp64 inside)
+    Yin = torch.view_as_real(torch.from_numpy(Yo)).float().cuda().contiguous()
+    Z = ops.wpe(Yin, 50, 2, 5)
+    Zo = np.stack([ow.wpe(Yin[b].cpu().double().numpy().view(np.complex128)[..., 0], 50, 2, 5) for b in range(2)])
+    e_k = rel(Z.cpu(), torch.view_as_real(torch.from_numpy(Zo)))
+    x = wd(y)
+    xo = torch.tensor(np.stack([ow.wpe_dereverb(y[b].cpu().double().numpy()) for b in range(2)]))
+    e = rel(x.cpu(), xo)
+    print(f"\n[WPE] kernel vs numpy on identical spectra {e_k:.2e}; end to end (fp32 STFT) {e:.2e}")
+    assert e_k < 1e-5 and e < 1e-4 and x.shape == (2, n)
+    # a silent bin / utterance must come back as zeros (singular system -> minimum-norm solution), not NaN
+    Zz = ops.wpe(torch.zeros(1, 3, 64, 2, device="cuda"), 50, 2, 5)
+    assert torch.equal(Zz, torch.zeros_like(Zz))
+
+
+def test_wpe_scaled_initialisation():
+    """initialize_x(mode = wpe_scaled) = scaling_factor * wpe(y) / std + sigma_max * noise, per utterance."""
+    from buddy_b200.samplers import EulerHeunSamplerDPS
+    from buddy_b200.wpe import WpeDereverb
+    from oracle import ref_harness as rh
+
+    class _Net(torch.nn.Module):
+        pass
+    args = rh.make_args("blind", 2, warm="wpe_scaled")
+    from buddy_b200.edm import EDM
+    smp = EulerHeunSamplerDPS(_Net(), EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10)), args)
+    y = (torch.randn(2, 8192, generator=torch.Generator().manual_seed(5)) * 0.05).cuda()
+    z = torch.randn(2, 8192, generator=torch.Generator().manual_seed(6)).cuda()
+    smp.y, smp.noise_source = y, iter([z])
+    t = smp.create_schedule()
+    x = smp.initialize_x((2, 8192), "cuda", t)
+    xp = WpeDereverb("cuda")(y)
+    want = 0.05 * xp / xp.std(dim=1, keepdim=True) + float(t[0]) * z
+    assert rel(x, want) < 1e-5

@@ -1,0 +1,156 @@
+"""Drop-in check against the UNMODIFIED reference (sp-uhh/buddy) on the GPU box.
+
+The reference travels as oracle/_ref (a verbatim, git-ignored staging copy made by oracle/stage_ref.py; in the build
+container /root/reference is used directly).  These tests do what testing/tester.py:32,143-161 does: build the
+reference's own `EDM`, `RIROperator` / `BlindSubbandFiltering` objects, hand them to the buddy_b200 samplers, and — for
+the blind path — call `sampler.operator.get_time_RIR()` on the reference object afterwards.  The expected values come
+from the reference's own sampler + network run on the same GPU (fp32, TF32 off) with identical injected noise.
+"""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+NS = 8192
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def randn(seed, *shape):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.fixture(scope="module")
+def rh():
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("unmodified reference not staged (run `python -m oracle.stage_ref` in the build container)")
+    ref_harness.install()
+    return ref_harness
+
+
+@pytest.fixture(scope="module")
+def nets(rh):
+    from buddy_b200.ncsnpp import NCSNppTime
+    from oracle.weights import make_state_dict
+    sd = make_state_dict(0)
+    ref_net = rh.build_network(sd).cuda()
+    ours = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    ours.load_state_dict(ref_net.state_dict())          # the reference module's own state_dict loads as is
+    return ref_net, ours.cuda().eval()
+
+
+def _observation(rh, seed):
+    from testing.operators.reverb import RIROperator
+    h = (randn(seed, 2000) * torch.exp(-6.908 * torch.arange(2000) / (0.5 * 16000)))
+    h[0] = 1.0
+    s = (randn(seed + 1, NS) * 0.05)
+    op = RIROperator(rh.op_hp(), time_kernel_size=h.shape[-1], sample_rate=16000)
+    op.update_params(h.cuda())
+    return op, op.degradation(s.cuda()[None])
+
+
+def test_informed_with_reference_operator_and_edm(rh, nets):
+    from buddy_b200.samplers import EulerHeunSamplerDPS as Ours
+    from testing.EulerHeunSamplerDPS import EulerHeunSamplerDPS as Ref
+    ref_net, our_net = nets
+    T = 2
+    op, y = _observation(rh, 100)
+    noise = [randn(110 + i, 1, NS) for i in range(T + 1)]
+    edm = rh.build_edm()
+    with rh.injected_noise(noise):
+        want = Ref(ref_net, edm, rh.make_args("informed", T)).predict_conditional(y, op, shape=(1, NS), blind=False)
+    smp = Ours(our_net, edm, rh.make_args("informed", T))          # the reference's EDM and RIROperator objects
+    smp.noise_source = iter(noise)
+    got = smp.predict_conditional(y, op, shape=(1, NS), blind=False)
+    e = rel(got, want)
+    print(f"\n[reference objects, informed T2] rel-L2 vs the reference sampler on this GPU {e:.2e}")
+    assert e < TOL
+
+
+def test_blind_with_reference_operator_object(rh, nets):
+    """tester.py:147-161: BlindSubbandFiltering object in, estimated filter written back, `get_time_RIR()` afterwards."""
+    from buddy_b200.samplers import EulerHeunSamplerDPS as Ours
+    from testing.EulerHeunSamplerDPS import EulerHeunSamplerDPS as Ref
+    from testing.operators.subband_filtering import BlindSubbandFiltering
+    ref_net, our_net = nets
+    T = 2
+    _, y = _observation(rh, 200)
+    torch.manual_seed(11)
+    bop = BlindSubbandFiltering(rh.op_hp(), sample_rate=16000)
+    with torch.no_grad():
+        bop.update_H(use_noise=True)
+    bop2 = copy.deepcopy(bop)
+    step_noise = [randn(210 + i, 1, NS) for i in range(T + 1)]
+    rir_noise = [randn(220 + i, 13824) for i in range(T)]
+    order = [step_noise[0]]
+    for i in range(T):
+        order += [step_noise[1 + i], rir_noise[i]]
+    args = rh.make_args("blind", T)
+    args.tester.posterior_sampling.blind_hp["op_updates_per_step"] = 1     # no chaotic amplification (see test_gpu_blind)
+    edm = rh.build_edm()
+    ref = Ref(ref_net, edm, args)
+    with rh.injected_noise(order):
+        want = ref.predict_conditional(y, bop, shape=(1, NS), blind=True)
+    want_rir = ref.operator.get_time_RIR().detach()
+    smp = Ours(our_net, edm, args)
+    smp.noise_source = iter(order)
+    got = smp.predict_conditional(y, bop2, shape=(1, NS), blind=True)
+    got_rir = smp.operator.get_time_RIR().detach()          # the REFERENCE object's method on the written-back filter
+    e, er = rel(got, want), rel(got_rir, want_rir)
+    eH = rel(torch.view_as_real(bop2.H), torch.view_as_real(bop.H.detach()))
+    print(f"\n[reference objects, blind T2] pred {e:.2e}  time RIR {er:.2e}  H {eH:.2e}")
+    assert e < TOL and er < 5e-3 and eH < 5e-3
+
+
+def test_api_operator_classes_match_reference(rh):
+    """buddy_b200.operators.{RIROperator, BlindSubbandFiltering} against the reference classes, method by method."""
+    from buddy_b200 import operators as ours
+    from testing.operators.subband_filtering import BlindSubbandFiltering
+    hp = rh.op_hp()
+    torch.manual_seed(5)
+    rop = BlindSubbandFiltering(hp, sample_rate=16000)
+    torch.manual_seed(5)
+    bop = ours.BlindSubbandFiltering(hp, sample_rate=16000)
+    assert bop.H.shape == rop.H.shape == (513, 100) and bop.params[0].shape == rop.params[0].shape == (1, 25)
+    noise = randn(300, 12800).cuda()
+    with torch.no_grad():
+        rop.update_H(use_noise=True, noise=noise)
+    bop.update_H(use_noise=True, noise=noise)
+    assert rel(torch.view_as_real(bop.H), torch.view_as_real(rop.H.detach())) < 1e-4
+    unit = lambda ph: torch.view_as_real(torch.polar(torch.ones_like(ph), ph))      # phases live on the circle
+    assert rel(unit(bop.params_phases[0]), unit(rop.params_phases[0])) < 1e-3
+    x = (randn(301, 2, NS) * 0.05).cuda()
+    with torch.no_grad():
+        assert rel(bop.degradation(x), rop.degradation(x)) < 1e-4
+        assert rel(torch.view_as_real(bop.degradation(x, mode="STFT")),
+                   torch.view_as_real(rop.degradation(x, mode="STFT"))) < 1e-4
+        assert rel(torch.view_as_real(bop.apply_stft(x[0])), torch.view_as_real(rop.apply_stft(x[0]))) < 1e-5
+        assert rel(bop.get_time_RIR(), rop.get_time_RIR()) < 1e-4
+        assert rel(bop.design_filter(), rop.design_filter()) < 1e-5
+        Hc = rop.H.detach().clone()
+        assert rel(torch.view_as_real(bop.cons(Hc)), torch.view_as_real(rop.cons(Hc.clone(), length=12800))) < 1e-4
+        # informed sub-band operator from a time-domain RIR
+        h = (randn(302, 3000) * torch.exp(-torch.arange(3000) / 400.0)).cuda()
+        rop.update_H(rir=h)
+        bop.update_H(rir=h)
+        assert rel(torch.view_as_real(bop.H), torch.view_as_real(rop.H)) < 1e-5
+    # projection (clamps) and the NaN guard
+    for o in (rop, bop):
+        o.params[0] = torch.full((1, 25), 0.9, device="cuda")
+        o.params[1] = torch.full((1, 25), 0.5, device="cuda")
+        o.project_params()
+    assert torch.allclose(bop.params[0], rop.params[0]) and torch.allclose(bop.params[1], rop.params[1])
+    bop.params[0] = torch.full((1, 25), float("nan"), device="cuda")
+    with pytest.raises(AssertionError):
+        bop.project_params()
