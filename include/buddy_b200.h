@@ -162,6 +162,16 @@ int buddy_pack_weights(const buddy_pack_desc* d, void* stream);
  * Y, Z: fp32 [batch][F][T][2] (re, im); arithmetic in fp64.  taps <= 64, T <= 2048. */
 int buddy_wpe(const float* Y, int batch, int F, int T, int taps, int delay, int iterations, float* Z, void* stream);
 
+/* upfirdn2d: zero-insertion upsample -> pad / crop -> 2-D FIR -> downsample, fp32 — the reference's only native
+ * operator (pybind11 `upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)`,
+ * networks/ncsnpp_utils/op/upfirdn2d.cpp:12-23, op/upfirdn2d_kernel.cu:107-207), same contract:
+ * in [major][in_h][in_w][minor], kernel [kh][kw] (<= 32 x 32),
+ * out [major][(in_h*up_y + pad_y0 + pad_y1 - kh)/down_y + 1][(in_w*up_x + pad_x0 + pad_x1 - kw)/down_x + 1][minor].
+ * Negative pads crop.  The data-gradient is the same operator with the flipped kernel and up / down exchanged. */
+int buddy_upfirdn2d(const float* in, const float* kernel, int major, int in_h, int in_w, int minor, int kh, int kw,
+                    int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                    float* out, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU) (+nearest-x2 / 2x2-mean resample) (+virtual channel concat) and its data-gradient.

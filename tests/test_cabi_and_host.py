@@ -156,3 +156,20 @@ def test_factored_stft_matrices_equal_the_dft_matrices():
     for got, want in ((factored(ones), ana.double()), (factored(ones / norm), ana.double() / norm),
                       (factored(aw), syn.double()), (factored(aw * norm), syn.double() * norm)):
         assert (got - want).abs().max().item() < 1e-7 * want.abs().max().item()
+
+
+def test_async_wav_writer_roundtrip(tmp_path):
+    """I/O half of the tester front-end (reference utils/log.py:90-110): 16-bit PCM mono files, written off-thread."""
+    import wave
+
+    import torch
+    from buddy_b200.tester import AsyncWavWriter
+    w = AsyncWavWriter(workers=2)
+    xs = [torch.sin(torch.arange(4000 + 100 * i) * 0.03) * 0.5 for i in range(5)]
+    paths = [w.write(x, 16000, f"utt{i}", str(tmp_path)) for i, x in enumerate(xs)]
+    assert w.close() == paths
+    for p, x in zip(paths, xs):
+        with wave.open(p) as f:
+            assert (f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()) == (1, 2, 16000, x.numel())
+            got = torch.frombuffer(bytearray(f.readframes(x.numel())), dtype=torch.int16).float() / 32767.0
+        assert (got - x).abs().max() < 1e-4

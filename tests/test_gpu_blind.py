@@ -343,3 +343,43 @@ def test_blind_single_iteration_trajectory_vs_oracle():
     # dependent direction — 229 of 51300 differ between our own FFT and DFT-matrix STFT forms (scripts/debug_blind_fft.py),
     # which moves H by 2e-3 and the sampler output by 6e-5.  The output is what the 1e-3 tolerance is about.
     assert e < 1e-3 and eH < 5e-3
+
+
+def test_blind_front_end_matches_single_utterance_runs():
+    """tester front-end, blind half (tester.py:147-161): utterances of two lengths, bucketed and batched, with the
+    operator initialised per utterance == each utterance run alone from the same initial operator state; the
+    estimated time-domain RIRs come back per utterance."""
+    from buddy_b200.edm import EDM
+    from buddy_b200.ncsnpp import NCSNppTime
+    from buddy_b200.samplers import EulerHeunSamplerDPS
+    from buddy_b200.tester import BatchedDereverb
+    from oracle import ref_harness as rh
+    from oracle.weights import make_state_dict
+    T = 2
+    lens = [8192, 6000, 8192]
+    ys = [(randn(950 + i, n) * 0.05).cuda() for i, n in enumerate(lens)]
+    net = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    net.load_state_dict(make_state_dict(0))
+    net = net.cuda().eval()
+    edm = EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10))
+    smp = EulerHeunSamplerDPS(net, edm, rh.make_args("blind", T))
+    smp.seed_base = 3000
+    fe = BatchedDereverb(smp, max_batch=8)
+    inits = []
+    orig = fe.init_blind_operator
+
+    def recording(B, device, generator=None):
+        op = orig(B, device, generator)
+        inits.append((op.params[0].clone(), op.params[1].clone(), op.params_phases[0].clone(), op.H.clone()))
+        return op
+    fe.init_blind_operator = recording
+    preds, rirs = fe.blind(ys, generator=torch.Generator().manual_seed(77))
+    assert [p.shape[0] for p in preds] == lens and all(r.shape == (13824,) for r in rirs)
+    buckets = [[0, 2], [1]]                                     # first-seen order of the two lengths
+    for bk, (d0, w0, ph0, H0) in zip(buckets, inits):
+        for r, i in enumerate(bk):
+            s1 = EulerHeunSamplerDPS(net, edm, rh.make_args("blind", T))
+            s1.seed_base, s1.utterance_offset = 3000, i
+            op = _Op(d0[r:r + 1], w0[r:r + 1], ph0[r], H0[r])
+            alone = s1.predict_conditional(ys[i][None], op, shape=(1, lens[i]), blind=True)[0]
+            assert rel(preds[i], alone) < 1e-5, (i, rel(preds[i], alone))

@@ -161,3 +161,37 @@ def test_softmax_transpose_cast():
     yh = torch.empty(1024, device="cuda", dtype=torch.float16)
     ops.cast_scale_h(xf, 0.5, yh)
     assert rel(yh.float(), xf * 0.5) < 1e-3
+
+
+def test_upfirdn2d_vs_reference_fixture_and_oracle():
+    """sm_100a upfirdn2d (the reference's only native operator, op/upfirdn2d_kernel.cu:107-207) against outputs of the
+    reference's own CPU branch (tests/golden/upfirdn2d.pt), its data-gradient against autograd through the oracle, the
+    channels-last ([major][h][w][minor > 1]) form of the C entry point, and the FIR resampling helpers."""
+    import os
+    from buddy_b200 import upfirdn2d as bu
+    from oracle import upfirdn as ou
+    rn = lambda seed, *s: torch.randn(*s, generator=torch.Generator().manual_seed(seed))
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "upfirdn2d.pt"), weights_only=False)
+    for c in gold:
+        x, k = rn(c["x_seed"], *c["shape"]).cuda(), rn(c["k_seed"], c["taps"], c["taps"]).cuda()
+        xr = x.clone().requires_grad_(True)
+        y = bu.UpFirDn2d.apply(xr, k, c["up"], c["down"], c["pad"])
+        assert y.shape == c["out"].shape and rel(y.detach().cpu(), c["out"]) < 1e-6
+        cot = torch.randn_like(y)
+        (gx,) = torch.autograd.grad((y * cot).sum(), xr)
+        xo = x.detach().cpu().double().requires_grad_(True)         # oracle in fp64 on the CPU (no TF32 convolutions)
+        (go,) = torch.autograd.grad((ou.upfirdn2d(xo, k.cpu().double(), c["up"], c["down"], c["pad"])
+                                     * cot.cpu().double()).sum(), xo)
+        assert rel(gx.cpu(), go) < 1e-6
+    # channels-last data, the layout of the engine's activations: [major = B][H][W][minor = C]
+    x4 = rn(1, 2, 12, 10, 16).cuda()
+    k = rn(2, 4, 4).cuda()
+    y4 = bu._launch(x4.contiguous(), k, (2, 2), (1, 1), (2, 1, 2, 1))
+    ref = ou.upfirdn2d(x4.cpu().double().permute(0, 3, 1, 2), k.cpu().double(), (2, 2), (1, 1),
+                       (2, 1, 2, 1)).permute(0, 2, 3, 1)
+    assert rel(y4.cpu(), ref) < 1e-6
+    # StyleGAN2 resampling helpers (up_or_down_sampling.py:195-256) with the reference's FIR [1, 3, 3, 1]
+    x = torch.ones(1, 4, 16, 20, device="cuda")
+    up, dn = bu.upsample_2d(x, [1, 3, 3, 1]), bu.downsample_2d(x, [1, 3, 3, 1])
+    assert up.shape == (1, 4, 32, 40) and dn.shape == (1, 4, 8, 10)
+    assert (up[..., 2:-2, 2:-2] - 1).abs().max() < 1e-6 and (dn[..., 1:-1, 1:-1] - 1).abs().max() < 1e-6   # unit DC gain

@@ -157,3 +157,11 @@ def test_blind_dps_sampler(sd):
     assert rel(st.weights.detach(), g["final_weights"]) < 5e-3
     assert rel(torch.view_as_real(st.H.detach()), torch.view_as_real(g["final_H"])) < 2e-2
     assert rel(pred, g["pred"]) < 1e-3
+
+
+def test_upfirdn2d_oracle_vs_reference_native():
+    """oracle/upfirdn.py against outputs of the reference's own `upfirdn2d_native` (op/upfirdn2d.py:157-200)."""
+    from oracle import upfirdn as ou
+    for c in gold("upfirdn2d.pt"):
+        x, k = randn(c["x_seed"], *c["shape"]), randn(c["k_seed"], c["taps"], c["taps"])
+        assert torch.equal(ou.upfirdn2d(x, k, c["up"], c["down"], c["pad"]), c["out"])
