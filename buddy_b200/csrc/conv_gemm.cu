@@ -26,6 +26,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/buddy_b200.h"
@@ -196,9 +197,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int h0 = (r / p.tiles_w) * th;
         const int w0 = (r % p.tiles_w) * p.bw;
         const int brow = nt * p.n_tile + static_cast<int>(rank) * b_rows;   // first weight row this CTA loads
-        for (int ph = 0; ph < 4; ++ph) {
-          const int nch = ph == 0 ? p.kchunks8_1 : (ph == 1 ? p.kchunks8_2 : (ph == 2 ? p.kchunks1 : p.kchunks2));
-          if (nch == 0) continue;
+        // one k-chunk of phase ph (0 fp8 conv, 1 fp8 skip conv, 2 fp16 conv, 3 fp16 skip conv): its A patch, then its
+        // weight stages
+        auto load_chunk = [&](int ph, int kc) {
           const CUtensorMap* ma = ph == 0 ? &tmA8 : (ph == 1 ? &tmA82 : (ph == 2 ? &tmA : &tmA2));
           const CUtensorMap* mb = ph == 0 ? &tmB8 : (ph == 1 ? &tmB82 : (ph == 2 ? &tmB : &tmB2));
           const int ptaps = (ph & 1) ? 1 : p.taps;
@@ -209,49 +210,58 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const bool tap9 = ptaps == 9;
           const int a_bytes = tap9 ? p.patch_bytes : p.patch1_bytes;
           const int hh = tap9 ? p.halo : 0;
-          for (int kc = 0; kc < nch; ++kc) {
-            mbar_wait(&a_empty[sa], pa ^ 1);
-            uint8_t* abase = smem + sa * a_stage_bytes;
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          uint8_t* abase = smem + sa * a_stage_bytes;
+          if (elect_one()) {
+            const int ac = (kc % wrap) * unit;
+            if (kPair) {
+              const uint32_t fb = mapa_u32(&a_full[sa], 0);   // pair: the leader's barrier collects both CTAs' bytes
+              mbar_expect_tx_cluster(fb, a_bytes);
+              tma_load_4d_2sm(ma, abase, fb, ac, w0 - hh, h0 - hh, b);
+            } else {
+              mbar_expect_tx(&a_full[sa], a_bytes);
+              tma_load_4d(ma, abase, &a_full[sa], ac, w0 - hh, h0 - hh, b);
+            }
+          }
+          __syncwarp();
+          if (++sa == p.stages_a) {
+            sa = 0;
+            pa ^= 1;
+          }
+          const int nsteps = tap9 ? 9 : 1;
+          const int tstep = tap9 ? p.tpb : 1;   // taps covered by one B stage (one TMA box over the tap dim)
+          for (int st = 0; st < nsteps; st += tstep) {
+            const int tap = tap9 ? st : 0;
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            uint8_t* bbase = smem_b + sb * b_stage_bytes;
+            const int b3 = (ph & 1) ? 0 : (p.b_batched ? b : tap);
             if (elect_one()) {
-              const int ac = (kc % wrap) * unit;
               if (kPair) {
-                const uint32_t fb = mapa_u32(&a_full[sa], 0);   // pair: the leader's barrier collects both CTAs' bytes
-                mbar_expect_tx_cluster(fb, a_bytes);
-                tma_load_4d_2sm(ma, abase, fb, ac, w0 - hh, h0 - hh, b);
+                const uint32_t fb = mapa_u32(&b_full[sb], 0);
+                mbar_expect_tx_cluster(fb, tstep * b_tile_bytes);
+                tma_load_3d_2sm(mb, bbase, fb, kc * unit, brow, b3);
               } else {
-                mbar_expect_tx(&a_full[sa], a_bytes);
-                tma_load_4d(ma, abase, &a_full[sa], ac, w0 - hh, h0 - hh, b);
+                mbar_expect_tx(&b_full[sb], tstep * b_tile_bytes);
+                tma_load_3d(mb, bbase, &b_full[sb], kc * unit, brow, b3);
               }
             }
             __syncwarp();
-            if (++sa == p.stages_a) {
-              sa = 0;
-              pa ^= 1;
+            if (++sb == p.stages_b) {
+              sb = 0;
+              pb ^= 1;
             }
-            const int nsteps = tap9 ? 9 : 1;
-            const int tstep = tap9 ? p.tpb : 1;   // taps covered by one B stage (one TMA box over the tap dim)
-            for (int st = 0; st < nsteps; st += tstep) {
-              const int tap = tap9 ? st : 0;
-              const int kcb = kc;
-              mbar_wait(&b_empty[sb], pb ^ 1);
-              uint8_t* bbase = smem_b + sb * b_stage_bytes;
-              const int b3 = (ph & 1) ? 0 : (p.b_batched ? b : tap);
-              if (elect_one()) {
-                if (kPair) {
-                  const uint32_t fb = mapa_u32(&b_full[sb], 0);
-                  mbar_expect_tx_cluster(fb, tstep * b_tile_bytes);
-                  tma_load_3d_2sm(mb, bbase, fb, kcb * unit, brow, b3);
-                } else {
-                  mbar_expect_tx(&b_full[sb], tstep * b_tile_bytes);
-                  tma_load_3d(mb, bbase, &b_full[sb], kcb * unit, brow, b3);
-                }
-              }
-              __syncwarp();
-              if (++sb == p.stages_b) {
-                sb = 0;
-                pb ^= 1;
-              }
-            }
+          }
+        };
+        // contraction schedule (the MMA warp walks the same one): the e4m3 group, then the fp16 group; inside a group
+        // the short k-chunks of a fused 1x1 skip conv (one MMA group each) are spread evenly between the long 3x3
+        // chunks (nine taps each), so the patch ring is never asked for several short stages in a row
+        for (int g = 0; g < 2; ++g) {
+          const int nm = g == 0 ? p.kchunks8_1 : p.kchunks1;
+          const int ns = g == 0 ? p.kchunks8_2 : p.kchunks2;
+          int js = 0;
+          for (int i = 0; i < nm; ++i) {
+            load_chunk(2 * g, i);
+            for (const int je = (i + 1) * ns / nm; js < je; ++js) load_chunk(2 * g + 1, js);
           }
         }
       }
@@ -275,14 +285,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
         bool fresh = true;       // no MMA issued into this accumulator yet
         bool unscaled8 = false;  // fp8 corrections accumulated (x 2^14) and not yet folded
-        for (int ph = 0; ph < 4; ++ph) {
-          const int nch = ph == 0 ? p.kchunks8_1 : (ph == 1 ? p.kchunks8_2 : (ph == 2 ? p.kchunks1 : p.kchunks2));
-          if (nch == 0) continue;
-          const int ptaps = (ph & 1) ? 1 : p.taps;
-          const bool f8 = ph < 2;
-          // 8-row groups of the A tile: a patch row apart in a halo patch, dense (1024 B) otherwise
-          const uint32_t a_sbo = ptaps == 9 ? static_cast<uint32_t>(p.a_pitch) : 1024u;
-          for (int kc = 0; kc < nch; ++kc) {
+        auto mma_chunk = [&](int ph) {
+          {
+            const int ptaps = (ph & 1) ? 1 : p.taps;
+            const bool f8 = ph < 2;
+            // 8-row groups of the A tile: a patch row apart in a halo patch, dense (1024 B) otherwise
+            const uint32_t a_sbo = ptaps == 9 ? static_cast<uint32_t>(p.a_pitch) : 1024u;
             const int nsteps = ptaps == 9 ? 9 : 1;
             if (!(p.dbg & 4)) mbar_wait(&a_full[sa], pa);
             tc_fence_after();
@@ -389,6 +397,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               sa = 0;
               pa ^= 1;
             }
+          }
+        };
+        // same contraction schedule as the producer warp: e4m3 group, then fp16 group; skip-conv chunks interleaved
+        for (int g = 0; g < 2; ++g) {
+          const int nm = g == 0 ? p.kchunks8_1 : p.kchunks1;
+          const int ns = g == 0 ? p.kchunks8_2 : p.kchunks2;
+          int js = 0;
+          for (int i = 0; i < nm; ++i) {
+            mma_chunk(2 * g);
+            for (const int je = (i + 1) * ns / nm; js < je; ++js) mma_chunk(2 * g + 1);
           }
         }
         // accumulator complete -> epilogue (of both CTAs of a pair)
@@ -900,6 +918,20 @@ static void choose_patch(int H, int W, int* bh, int* bw) {
 
 std::atomic<long long> g_launches{0};
 
+// Shared-memory budget of one conv CTA (bytes).  Default: everything (227 KB).  BUDDY_CONV_SMEM_KB = n leaves
+// 227 - n KB of every SM to co-resident CTAs of HBM-bound kernels launched on another stream (GroupNorm of another
+// micro-batch: sampler.n_streams = 2), at the price of shallower pipeline rings.
+static int conv_smem_budget() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("BUDDY_CONV_SMEM_KB");
+    int kb = e ? atoi(e) : 227;
+    if (kb < 128 || kb > 227) kb = 227;
+    v = kb * 1024;
+  }
+  return v;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -1011,7 +1043,7 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
   p.acc_stages = (d->n_tile <= 128 && p.mt == 1) ? 4 : 2;
   p.acc_stride = (d->n_tile <= 128 && p.mt == 1) ? 128 : 256;
   const int epi_bytes = p.staged ? 2 * kChunkBytes + 1024 + (d->gnb_x ? 4096 : 0) : 0;
-  const int ring_bytes = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/ - epi_bytes;
+  const int ring_bytes = conv_smem_budget() - 1024 /*alignment slack*/ - 512 /*barriers*/ - epi_bytes;
   p.tpb = 1;
   if (p.halo) {
     // a patch stage lasts nine weight tiles: three of them, the rest of the shared memory goes to the weight ring —
