@@ -382,8 +382,9 @@ def run_ours(args):
     eng = net.engine()
     np_ = (kt.issued_flops / conv_flops) if conv_flops else 1.0   # fp16-pass equivalents issued per algorithmic product
     if eng.mixed:
-        dtype_s = (f"f16 tensor-core operands, f32 accumulate: {len(eng.x1_convs)} largest convolutions single-pass, "
-                   "the rest + 2 e4m3 correction passes; f32 activations / statistics / sampler")
+        dtype_s = (f"f16 tensor-core operands, f32 accumulate: the {len(eng.x1_fwd)} largest forward and {len(eng.x1_convs)} "
+                   "largest data-gradient convolutions single-pass, the rest + 2 e4m3 correction passes; f32 "
+                   "activations / statistics / sampler")
     elif eng.c8:
         dtype_s = "f16 products + 2 e4m3 correction passes (2 fp16-pass equivalents) / f32 accumulate+activations"
     else:

@@ -81,6 +81,12 @@ class Engine:
     # (forward / VJP, CPU emulation scripts/precision_study.py; measured on B200 in tests/test_gpu_network.py) of
     # the 1e-3 budget and removes a quarter of the tensor-core work.
     MIXED_X1_THRESHOLD = 32768
+    # Data-gradient convolutions with Cin*Cout/4^level >= 16384 also run single-pass ("E"; "" / "F" / "G" = none / only
+    # the full-resolution / only the half-resolution ones, for A-B measurements via BUDDY_X1_BWD).  Measured on B200 at
+    # full size (tests/test_gpu_network.py, tests/test_gpu_sampler.py): forward error unchanged (3.6e-4), data-gradient
+    # 5.4e-4 -> 7.7e-4, sampler trajectories 4.9e-4 -> 5.7e-4 worst case (they are dominated by the forward error), for
+    # 1.52 -> 1.34 fp16-pass equivalents per product.
+    BWD_X1_POLICY = "E"
 
     def __init__(self, state_dict, device, precision="mixed"):
         """precision: operand scheme of the conv GEMMs (all accumulate in fp32 on tcgen05):
@@ -96,7 +102,8 @@ class Engine:
         self.np = self.PRECISIONS[precision]
         self.c8 = precision in ("fp16c8", "mixed")
         self.mixed = precision == "mixed"
-        self.x1_convs = set()   # (module index, conv index) of the single-pass convolutions (mixed mode)
+        self.x1_convs = set()   # (module index, conv index) whose DATA-GRADIENT launch runs single-pass (mixed mode)
+        self.x1_fwd = set()     # ... whose forward launch does
         import os
         # BUDDY_FUSE_GNB=1 folds GroupNorm-backward's statistics pass into the producing dgrad convolution's epilogue
         # where the geometry allows (no resample, single input tensor).  Correct (tests) but OFF by default: measured
@@ -181,13 +188,26 @@ class Engine:
         w16, w8 = ops.pack_weights(src, T, N, K, passes=self.np, e4m3=self.c8 and not x1, **kw)
         return WPack(w16, w8)
 
-    def _pack3x3(self, w, x1=False):
+    def _pack3x3(self, w, x1=False, x1_bwd=None):
         """[Co, Ci, 3, 3] -> forward [9, Co, Ci] (tap = 3*ky + kx) and data-gradient [9, Ci, Co] (taps flipped)."""
         w = w.contiguous()
         co, ci = w.shape[:2]
         fwd = self._packv(w, 9, co, ci, x1, st=1, sn=(co, 0, ci * 9), sk=(ci, 0, 9))
-        dgr = self._packv(w, 9, ci, co, x1, off0=8, st=-1, sn=(ci, 0, 9), sk=(co, 0, ci * 9))
+        dgr = self._packv(w, 9, ci, co, x1 if x1_bwd is None else x1_bwd, off0=8, st=-1, sn=(ci, 0, 9),
+                          sk=(co, 0, ci * 9))
         return fwd, dgr
+
+    def _bwd_extra_x1(self, level, cin, cout):
+        import os
+        pol = os.environ.get("BUDDY_X1_BWD", self.BWD_X1_POLICY)
+        m = cin * cout / 4 ** level
+        if pol == "E":
+            return m >= 16384
+        if pol == "F":
+            return m >= 16384 and level == 0
+        if pol == "G":
+            return m >= 16384 and level == 1
+        return False
 
     def _operand(self, B, H, W, C, gs=1.0, need8=True):
         """need8 = False: every consumer of this operand runs a single fp16 pass (no e4m3 correction pair)."""
@@ -237,18 +257,24 @@ class Engine:
         r.cin, r.cout = sd[p + "Conv_0.weight"].shape[1], sd[p + "Conv_0.weight"].shape[0]
         # relative cost of the two 3x3 convolutions: Cin*Cout / 4^level (level 0 = full resolution)
         r.x1 = [self.mixed and (ci * r.cout) / 4 ** level >= self.MIXED_X1_THRESHOLD for ci in (r.cin, r.cout)]
+        # data-gradient launches may run single-pass where the forward conv keeps its corrections: a rounding error in
+        # a dgrad conv only reaches the likelihood gradient, a forward one reaches both outputs (emulation:
+        # scripts/precision_study.py, policies E-H)
+        r.x1b = [r.x1[k] or (self.mixed and self._bwd_extra_x1(level, ci, r.cout)) for k, ci in enumerate((r.cin, r.cout))]
         for k in (0, 1):
-            if r.x1[k]:
+            if r.x1b[k]:
                 self.x1_convs.add((i, k))
-        r.w0, r.wd0 = self._pack3x3(sd[p + "Conv_0.weight"], r.x1[0])
-        r.w1, r.wd1 = self._pack3x3(sd[p + "Conv_1.weight"], r.x1[1])
+            if r.x1[k]:
+                self.x1_fwd.add((i, k))
+        r.w0, r.wd0 = self._pack3x3(sd[p + "Conv_0.weight"], r.x1[0], r.x1b[0])
+        r.w1, r.wd1 = self._pack3x3(sd[p + "Conv_1.weight"], r.x1[1], r.x1b[1])
         r.bias0 = sd[p + "Conv_0.bias"].contiguous()
         r.dense = (sd[p + "Dense_0.weight"].contiguous(), sd[p + "Dense_0.bias"].contiguous())
         r.has_skip_conv = (p + "Conv_2.weight") in sd
         if r.has_skip_conv:
             w2 = sd[p + "Conv_2.weight"].contiguous()               # [Cout, Cin, 1, 1]
             r.w2 = self._packv(w2, 1, r.cout, r.cin, r.x1[1], sn=(r.cout, 0, r.cin), sk=(r.cin, 0, 1))   # fused into conv 1
-            r.wd2 = self._packv(w2, 1, r.cin, r.cout, r.x1[1], sn=(r.cin, 0, 1), sk=(r.cout, 0, r.cin))
+            r.wd2 = self._packv(w2, 1, r.cin, r.cout, r.x1b[1], sn=(r.cin, 0, 1), sk=(r.cout, 0, r.cin))
             r.bias1 = (sd[p + "Conv_1.bias"] + sd[p + "Conv_2.bias"]).contiguous()
         else:
             r.bias1 = sd[p + "Conv_1.bias"].contiguous()
@@ -356,7 +382,7 @@ class Engine:
         gsum1 = torch.zeros(B, 32, 2, device=dev, dtype=torch.float64) if fuse1 else gsum
         self._conv(g16, r.wd1, da1, taps=9, n_total=r.cout,
                    gnb=(h1, s1, r.g1, r.b1, gsum1, 32, 1e-6, 1) if fuse1 else None)
-        dh1 = self._operand(B, Ho, Wo, r.cout, self._gscale(("h1", i)), need8=not r.x1[0])
+        dh1 = self._operand(B, Ho, Wo, r.cout, self._gscale(("h1", i)), need8=not r.x1b[0])
         ops.gn_bwd(h1, s1, r.g1, r.b1, da1, gsum1, silu=True, g16a=dh1.t16, g16_scale=dh1.gs, split=self.split,
                    g8a=dh1.t8, pass0_done=fuse1)
         self._record(("h1", i), dh1)

@@ -146,7 +146,14 @@ def run(frames=80, seed=0, sigma=0.1):
         "B: top5 x1, mid a8, rest c8": lambda H, d: x1 if big(H) else (a8 if mid(H) else c8),
         "C: top5 x1 fwd / a8 bwd, rest c8": lambda H, d: (x1 if d == "fwd" else a8) if big(H) else c8,
         "D: top5+mid x1, rest c8": lambda H, d: x1 if (big(H) or mid(H)) else c8,
+        "E: fwd top5 x1 / bwd top5+mid x1": lambda H, d: x1 if (big(H) or (d == "bwd" and mid(H))) else c8,
+        "F: fwd top5 / bwd top5+(256,128,128)": lambda H, d: x1 if (big(H) or (d == "bwd" and (H,) + SCHEME["w_shape"] == (256, 128, 128))) else c8,
+        "G: fwd top5 / bwd top5+(128,256,256)": lambda H, d: x1 if (big(H) or (d == "bwd" and (H,) + SCHEME["w_shape"] == (128, 256, 256))) else c8,
+        "H: fwd top5 / bwd ALL x1": lambda H, d: x1 if (big(H) or d == "bwd") else c8,
     }
+    import os
+    if os.environ.get("ONLY"):
+        policies = {k: v for k, v in policies.items() if k[0] in os.environ["ONLY"]}
     if seed != 0:
         policies = {"all x1": lambda H, d: x1, "all c8": lambda H, d: c8, "A: top5 x1, rest c8": policies["A: top5 x1, rest c8"]}
     for name, pol in policies.items():
