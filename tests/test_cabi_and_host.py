@@ -30,7 +30,7 @@ def test_ctypes_struct_layout_matches_header():
     src = r'''
     #include <stdio.h>
     #include "buddy_b200.h"
-    int main(void){ printf("%zu %zu %zu\n", sizeof(buddy_gemm_desc), sizeof(buddy_gn_desc), sizeof(buddy_gn_bwd_desc)); return 0; }
+    int main(void){ printf("%zu %zu %zu %zu\n", sizeof(buddy_gemm_desc), sizeof(buddy_gn_desc), sizeof(buddy_gn_bwd_desc), sizeof(buddy_pack_desc)); return 0; }
     '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
@@ -40,7 +40,7 @@ def test_ctypes_struct_layout_matches_header():
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
     assert [int(v) for v in out] == [ctypes.sizeof(_capi.GemmDesc), ctypes.sizeof(_capi.GnDesc),
-                                     ctypes.sizeof(_capi.GnBwdDesc)]
+                                     ctypes.sizeof(_capi.GnBwdDesc), ctypes.sizeof(_capi.PackDesc)]
 
 
 def test_no_cpu_fallback():
