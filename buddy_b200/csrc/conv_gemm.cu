@@ -1000,7 +1000,15 @@ extern "C" int buddy_conv_gemm(const buddy_gemm_desc* d, void* stream_v) {
                  : 0;
   p.res_staged = (p.staged && d->resid) ? 1 : 0;
   // two stacked pixel tiles per CTA (see GemmParams::mt): plain 3x3 launches with N <= 128 and the staged epilogue
-  p.mt = (p.halo && p.staged && d->n_tile <= 128 && !d->a2 && !d->gnb_x && !d->single_tile_per_cta && d->H > p.bh) ? 2 : 1;
+  // ... when there is enough work: stacking halves the number of work items (small launches keep one tile per CTA)
+  {
+    const long long tiles1 = (long long)d->batch * ((d->H + 15) / 16) * ((d->W + 7) / 8);
+    const long long items2 = ((tiles1 / 2 + 1) / 2) * ((d->n_total + d->n_tile - 1) / d->n_tile);
+    p.mt = (p.halo && p.staged && d->n_tile <= 128 && !d->a2 && !d->gnb_x && d->single_tile_per_cta != 1 && d->H > 16 &&
+            (items2 >= 2 * (num_sms() / 2) || d->single_tile_per_cta == 2))
+               ? 2
+               : 1;
+  }
   const int patch_rows = p.bh * p.mt + 2 * p.halo;
   const int patch_cols = p.bw + 2 * p.halo;
   p.a_pitch = patch_cols * 128;

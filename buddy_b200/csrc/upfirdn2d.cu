@@ -31,6 +31,8 @@ struct UpfirArgs {
   int out_h, out_w;
 };
 
+// kVec = 4: four consecutive minor elements (channels of a channels-last tensor) per thread, 128-bit loads / stores
+template <int kVec>
 __global__ void __launch_bounds__(256) upfirdn2d_kernel(const UpfirArgs a) {
   __shared__ float kflip[kUpfirMaxTaps * kUpfirMaxTaps];
   for (int i = threadIdx.x; i < a.kh * a.kw; i += blockDim.x) {
@@ -38,32 +40,48 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(const UpfirArgs a) {
     kflip[i] = a.kernel[(a.kh - 1 - ky) * a.kw + (a.kw - 1 - kx)];
   }
   __syncthreads();
-  const long long total = static_cast<long long>(a.major) * a.out_h * a.out_w * a.minor;
+  const uint32_t mv = static_cast<uint32_t>(a.minor / kVec);          // vectors per pixel
+  const uint32_t per_img = static_cast<uint32_t>(a.out_h) * a.out_w * mv;   // host guarantees < 2^31
+  const long long total = static_cast<long long>(a.major) * per_img;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(idx % a.minor);
-    long long r = idx / a.minor;
+    const long long m = idx / per_img;
+    uint32_t r = static_cast<uint32_t>(idx - m * per_img);
+    const uint32_t c = (r % mv) * kVec;
+    r /= mv;
     const int ox = static_cast<int>(r % a.out_w);
-    r /= a.out_w;
-    const int oy = static_cast<int>(r % a.out_h);
-    const long long m = r / a.out_h;
+    const int oy = static_cast<int>(r / a.out_w);
     // window origin in zero-inserted input coordinates (may be negative: padding)
     const int y0 = oy * a.down_y - a.pad_y0, x0 = ox * a.down_x - a.pad_x0;
     // first tap row / column that lands on a real sample: y0 + i >= 0 and (y0 + i) % up_y == 0
     const int i0 = y0 < 0 ? -y0 : (a.up_y - (y0 % a.up_y)) % a.up_y;
     const int j0 = x0 < 0 ? -x0 : (a.up_x - (x0 % a.up_x)) % a.up_x;
     const float* base = a.in + m * a.in_h * a.in_w * a.minor + c;
-    float acc = 0.f;
+    float acc[kVec];
+#pragma unroll
+    for (int v = 0; v < kVec; ++v) acc[v] = 0.f;
     for (int i = i0; i < a.kh; i += a.up_y) {
       const int iy = (y0 + i) / a.up_y;
       if (iy >= a.in_h) break;
       for (int j = j0; j < a.kw; j += a.up_x) {
         const int ix = (x0 + j) / a.up_x;
         if (ix >= a.in_w) break;
-        acc = fmaf(kflip[i * a.kw + j], __ldg(base + (static_cast<long long>(iy) * a.in_w + ix) * a.minor), acc);
+        const float kv = kflip[i * a.kw + j];
+        const float* src = base + (static_cast<long long>(iy) * a.in_w + ix) * a.minor;
+        if (kVec == 4) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+          acc[0] = fmaf(kv, q.x, acc[0]);
+          acc[1] = fmaf(kv, q.y, acc[1]);
+          acc[2] = fmaf(kv, q.z, acc[2]);
+          acc[kVec - 1] = fmaf(kv, q.w, acc[kVec - 1]);
+        } else {
+          acc[0] = fmaf(kv, __ldg(src), acc[0]);
+        }
       }
     }
-    a.out[idx] = acc;
+    float* dst = a.out + ((m * a.out_h + oy) * a.out_w + ox) * a.minor + c;
+    if (kVec == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[kVec - 1]);
+    else dst[0] = acc[0];
   }
 }
 }  // namespace buddy
@@ -101,10 +119,16 @@ extern "C" int buddy_upfirdn2d(const float* in, const float* kernel, int major, 
   }
   a.out_h = ph / down_y + 1;
   a.out_w = pw / down_x + 1;
-  const long long total = static_cast<long long>(major) * a.out_h * a.out_w * minor;
+  if (static_cast<long long>(a.out_h) * a.out_w * minor >= (1LL << 31)) {
+    set_last_error("buddy_upfirdn2d: one image of the output must have fewer than 2^31 elements");
+    return BUDDY_ERR_UNSUPPORTED;
+  }
+  const bool vec = minor % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const long long total = static_cast<long long>(major) * a.out_h * a.out_w * (vec ? minor / 4 : minor);
   long long grid = (total + 255) / 256;
   if (grid > 148LL * 32) grid = 148LL * 32;
-  upfirdn2d_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  if (vec) upfirdn2d_kernel<4><<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  else upfirdn2d_kernel<1><<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   BUDDY_CHECK_LAUNCH("upfirdn2d_kernel");
   return 0;

@@ -11,21 +11,27 @@ from . import _capi
 from ._capi import GemmDesc, check, lib, ptr, stream_ptr
 
 
-def _pick_n_tile(n_total):
+def _pick_n_tile(n_total, work_pairs=None):
+    """MMA N per tile.  Large problems: the widest tile (fewest re-reads of the activation patches).  Small problems
+    (one utterance at the low-resolution levels: 9-34 pixel-tile pairs for 74 CTA pairs): narrower tiles, so that
+    pairs x n-tiles covers the machine — B = 1 is the reference's own usage (tester.py:153)."""
     if n_total <= 16:
         return 16
     if n_total <= 256:
-        return (n_total + 15) // 16 * 16
-    for cand in (256, 192, 128):
-        if n_total % cand == 0:
-            return cand
-    return 256
+        nt = (n_total + 15) // 16 * 16
+    else:
+        nt = next((cand for cand in (256, 192, 128) if n_total % cand == 0), 256)
+    if work_pairs is not None and n_total % 64 == 0:
+        while nt > 64 and nt % 2 == 0 and n_total % (nt // 2) == 0 and (nt // 2) % 32 == 0 \
+                and work_pairs * ((n_total + nt - 1) // nt) < 74:
+            nt //= 2
+    return nt
 
 
 def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=None, bias_b=None, resid=None,
               scale=1.0, stats=None, b_batched=False, col_off=0, ldc=None, max_ctas=0, passes=1, a8=None, w8=None,
               a8_2=None, w8_2=None, direct_epilogue=False, no_pairs=False, debug_flags=0, one_tap_per_stage=False, gnb=None,
-              single_tile=False):
+              single_tile=None):
     """out[b,h,w,n] = scale*(sum_{tap,k} a[b,h+dy,w+dx,k] w[tap,n,k] + sum_k a2[b,h,w,k] w2[n,k] + bias + bias_b + resid).
 
     a, a2 : fp16 [B,H,W,C] (channel stride 1, other strides arbitrary multiples of 8 elements)
@@ -60,7 +66,10 @@ def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=N
     d.taps = taps
     d.b_batched = 1 if b_batched else 0
     d.n_total = n_total
-    d.n_tile = n_tile or _pick_n_tile(n_total)
+    if n_tile is None:
+        tiles = B * ((H + 15) // 16) * ((W + 7) // 8) if taps == 9 else (B * H * W + 127) // 128
+        n_tile = _pick_n_tile(n_total, None if b_batched else (tiles + 1) // 2)
+    d.n_tile = n_tile
     d.out = ptr(out)
     d.out_fp16 = 1 if out.dtype == torch.float16 else 0
     assert out.dtype in (torch.float16, torch.float32)
@@ -77,7 +86,7 @@ def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=N
     d.no_cta_pairs = 1 if no_pairs else 0
     d.debug_flags = int(debug_flags)
     d.one_tap_per_stage = 1 if one_tap_per_stage else 0
-    d.single_tile_per_cta = 1 if single_tile else 0
+    d.single_tile_per_cta = {None: 0, True: 1, False: 2}[single_tile]
     if gnb is not None:
         # (x, bundle stats of x, gamma, beta, gsum out, groups, eps, silu): fused GroupNorm-backward statistics
         gx, gstats, ggam, gbet, ggsum, ggroups, geps, gsilu = gnb

@@ -112,8 +112,9 @@ typedef struct buddy_gemm_desc {
   int32_t debug_flags;
   /* 1 = one weight tile per pipeline stage even where a kernel row of three fits (testing / A-B timing only) */
   int32_t one_tap_per_stage;
-  /* 1 = one 16x8-pixel tile per CTA and work item even where two stacked tiles share every weight tile (plain 3x3
-   * launches with n_tile <= 128); testing / A-B timing only */
+  /* Stacked tiles (two 16x8-pixel tiles per CTA and work item share every weight tile; plain 3x3 launches with
+   * n_tile <= 128): 0 = automatic (when the launch has enough work items), 1 = never, 2 = whenever legal
+   * (testing / A-B timing) */
   int32_t single_tile_per_cta;
   /* Fused GroupNorm-backward statistics (staged epilogue only).  When this launch is the data-gradient convolution
    * whose output `da` is the gradient w.r.t. act(GroupNorm(x)) of a tensor x of the SAME geometry (no resampling in

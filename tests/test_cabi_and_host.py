@@ -173,3 +173,61 @@ def test_async_wav_writer_roundtrip(tmp_path):
             assert (f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()) == (1, 2, 16000, x.numel())
             got = torch.frombuffer(bytearray(f.readframes(x.numel())), dtype=torch.int16).float() / 32767.0
         assert (got - x).abs().max() < 1e-4
+
+
+def test_error_behaviour_without_gpu():
+    """Same error classes as the reference for the same mistakes (SURVEY.md §8b "Errors"), and loud failures instead of
+    a CPU fallback."""
+    import pytest
+    import torch
+    from buddy_b200.edm import EDM
+    from buddy_b200.ncsnpp import NCSNppTime
+    from buddy_b200.samplers import EulerHeunSampler, EulerHeunSamplerDPS
+    from oracle import ref_harness as rh
+    edm = EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10))
+
+    class _Net(torch.nn.Module):
+        pass
+    s = EulerHeunSamplerDPS(_Net(), edm, rh.make_args("informed", 3))
+    with pytest.raises(ValueError):                       # EulerHeunSamplerDPS.py:181
+        s.predict_unconditional((1, 8192), "cpu")
+    with pytest.raises(RuntimeError):                     # CPU observation: no fallback
+        s.predict_conditional(torch.zeros(1, 8192), object(), shape=(1, 8192))
+    args = rh.make_args("informed", 3)
+    args.tester.sampling_params["schedule"] = "song"
+    with pytest.raises(NotImplementedError):              # Sampler.py:58-65
+        EulerHeunSampler(_Net(), edm, args).create_schedule()
+    for bad in (dict(fir=True), dict(resblock_type="ddpm"), dict(progressive="residual")):
+        with pytest.raises(NotImplementedError):
+            NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2], **bad)
+    with pytest.raises(NotImplementedError):              # other STFT sizes
+        NCSNppTime(stft=dict(n_fft=512, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    net = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    with pytest.raises(RuntimeError):                     # module still on the CPU
+        net(torch.zeros(1, 1, 8192), torch.zeros(1))
+    # operator hyper-parameters the kernels do not implement are refused when the operator is bound
+    class _Op:
+        op_hp = dict(NFFT=2048, win_length=512, hop=128, window="hann")
+        params = torch.zeros(100)
+    with pytest.raises(NotImplementedError):
+        s._validate_operator(_Op(), 1, False)
+
+
+def test_wpe_oracle_conventions():
+    """oracle/wpe.py (restated nara_wpe conventions, parity unpinned): the Blackman/fading STFT pair reconstructs
+    perfectly, the frame count is the one the reference's call produces for a 4 s utterance, and WPE removes late
+    reverberation from a synthetic exponentially decaying room."""
+    import numpy as np
+    from oracle import wpe as ow
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(65536)
+    X = ow.stft(x)
+    assert X.shape == (515, 257)
+    assert np.abs(ow.istft(X)[:65536] - x).max() < 1e-12
+    n = 8192
+    s = np.convolve(np.convolve(rng.standard_normal(n), np.ones(8) / 8)[:n], [1, -0.5])[:n]
+    h = rng.standard_normal(3000) * np.exp(-np.arange(3000) / 500.0)
+    h[0] = 1
+    y = np.convolve(s, h)[:n]
+    d = ow.wpe_dereverb(y)
+    assert d.shape == (n,) and np.linalg.norm(d - s) < 0.7 * np.linalg.norm(y - s)

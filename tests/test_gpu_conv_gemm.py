@@ -279,7 +279,7 @@ def test_stacked_tiles_match_single_tile(B, H, W, C, N, c8, with_res):
         out = torch.full((B, H, W, N), float("nan"), device="cuda")
         stats = torch.zeros(B, N // 4, 2, device="cuda", dtype=torch.float64)
         ops.conv_gemm(a, w, out, taps=9, n_total=N, bias=bias, bias_b=bias_b, resid=res, scale=0.7, stats=stats,
-                      single_tile=single, **kw)
+                      single_tile=single, **kw)       # True: never stacked, False: stacked whenever legal
         torch.cuda.synchronize()
         outs.append((out, stats))
     assert torch.equal(outs[0][0], outs[1][0])
