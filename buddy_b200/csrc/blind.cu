@@ -34,74 +34,108 @@ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // conj(a) * b
 // mode 1: dX[s] = sum_n conj(H[n]) dY[s-pre+n]
 // mode 2: dH[n] (+)= sum_t conj(X[t+pre-n]) dY[t]
 constexpr int kFirMaxT = 544, kFirMaxN = 128;
-__global__ void __launch_bounds__(256)
+constexpr int kFirR = 3;   // outputs (modes 0, 1) / taps (mode 2) per thread or warp: every loaded value feeds kFirR MACs
+// The signal row lives in shared memory with kFirMaxN zeros on both sides, so no tap needs a bounds check:
+// sa[kFirMaxN + s] = a[s] for 0 <= s < Tx, 0 elsewhere.
+__global__ void __launch_bounds__(192)
 subband_fir_kernel(const float2* __restrict__ A, const float2* __restrict__ Hh, long long h_bs, float2* __restrict__ O,
                    int F, int Tx, int Nf, int pre, int mode, int accumulate) {
-  __shared__ float2 sa[kFirMaxT];
-  __shared__ float2 sh[kFirMaxN];
+  __shared__ float2 sa[kFirMaxT + 2 * kFirMaxN + kFirR];
+  __shared__ float2 sh[kFirMaxN + kFirR];
   __shared__ float2 sg[kFirMaxT];
   const int f = blockIdx.x, b = blockIdx.y;
   const long long row = (static_cast<long long>(b) * F + f);
   const float2* a = A + row * Tx;
-  for (int i = threadIdx.x; i < Tx; i += blockDim.x) sa[i] = a[i];
+  for (int i = threadIdx.x; i < kFirMaxT + 2 * kFirMaxN + kFirR; i += blockDim.x) {
+    const int s0 = i - kFirMaxN;
+    sa[i] = (s0 >= 0 && s0 < Tx) ? a[s0] : make_float2(0.f, 0.f);
+  }
   if (mode != 2) {
     const float2* h = Hh + b * h_bs + static_cast<long long>(f) * Nf;
-    for (int i = threadIdx.x; i < Nf; i += blockDim.x) sh[i] = h[i];
+    for (int i = threadIdx.x; i < kFirMaxN + kFirR; i += blockDim.x) sh[i] = i < Nf ? h[i] : make_float2(0.f, 0.f);
   } else {
     const float2* g = Hh + row * Tx;  // in mode 2 the second operand is dY
     for (int i = threadIdx.x; i < Tx; i += blockDim.x) sg[i] = g[i];
   }
   __syncthreads();
+  const float2* sa0 = sa + kFirMaxN;   // sa0[s] valid for -kFirMaxN <= s < Tx + kFirMaxN
   if (mode == 0) {
+    // y[t] = sum_n h[n] x[t + pre - n]: thread = kFirR consecutive outputs, sliding window over x
     float2* o = O + row * Tx;
-    for (int t = threadIdx.x; t < Tx; t += blockDim.x) {
-      float2 acc = make_float2(0.f, 0.f);
-      for (int n = 0; n < Nf; ++n) {
-        const int s = t + pre - n;
-        if (s >= 0 && s < Tx) {
-          const float2 v = cmulf(sh[n], sa[s]);
-          acc.x += v.x;
-          acc.y += v.y;
-        }
+    for (int t0 = threadIdx.x * kFirR; t0 < Tx; t0 += blockDim.x * kFirR) {
+      float2 acc[kFirR], win[kFirR];
+#pragma unroll
+      for (int r = 0; r < kFirR; ++r) {
+        acc[r] = make_float2(0.f, 0.f);
+        win[r] = sa0[t0 + pre + r];            // x[(t0 + r) + pre - 0]
       }
-      o[t] = acc;
+      for (int n = 0; n < Nf; ++n) {
+        const float2 h = sh[n];
+#pragma unroll
+        for (int r = 0; r < kFirR; ++r) {
+          acc[r].x = fmaf(h.x, win[r].x, fmaf(-h.y, win[r].y, acc[r].x));
+          acc[r].y = fmaf(h.x, win[r].y, fmaf(h.y, win[r].x, acc[r].y));
+        }
+#pragma unroll
+        for (int r = kFirR - 1; r > 0; --r) win[r] = win[r - 1];
+        win[0] = sa0[t0 + pre - n - 1];        // the next tap reads one sample earlier
+      }
+#pragma unroll
+      for (int r = 0; r < kFirR; ++r)
+        if (t0 + r < Tx) o[t0 + r] = acc[r];
     }
   } else if (mode == 1) {
+    // dx[s] = sum_n conj(h[n]) dy[s - pre + n]
     float2* o = O + row * Tx;
-    for (int s = threadIdx.x; s < Tx; s += blockDim.x) {
-      float2 acc = make_float2(0.f, 0.f);
-      for (int n = 0; n < Nf; ++n) {
-        const int t = s - pre + n;
-        if (t >= 0 && t < Tx) {
-          const float2 v = cmulc(sh[n], sa[t]);
-          acc.x += v.x;
-          acc.y += v.y;
-        }
+    for (int s0 = threadIdx.x * kFirR; s0 < Tx; s0 += blockDim.x * kFirR) {
+      float2 acc[kFirR], win[kFirR];
+#pragma unroll
+      for (int r = 0; r < kFirR; ++r) {
+        acc[r] = make_float2(0.f, 0.f);
+        win[r] = sa0[s0 - pre + r];
       }
-      o[s] = acc;
+      for (int n = 0; n < Nf; ++n) {
+        const float2 h = sh[n];
+#pragma unroll
+        for (int r = 0; r < kFirR; ++r) {       // conj(h) * v
+          acc[r].x = fmaf(h.x, win[r].x, fmaf(h.y, win[r].y, acc[r].x));
+          acc[r].y = fmaf(h.x, win[r].y, fmaf(-h.y, win[r].x, acc[r].y));
+        }
+#pragma unroll
+        for (int r = 0; r < kFirR - 1; ++r) win[r] = win[r + 1];
+        win[kFirR - 1] = sa0[s0 - pre + n + kFirR];
+      }
+#pragma unroll
+      for (int r = 0; r < kFirR; ++r)
+        if (s0 + r < Tx) o[s0 + r] = acc[r];
     }
   } else {
+    // dH[n] = sum_t conj(x[t + pre - n]) dy[t]: warp = kFirR consecutive taps, lanes stride over t
     float2* o = O + row * Nf;
-    // each warp owns taps n = warp, warp+8, ...; lanes stride over t
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int n = warp; n < Nf; n += (blockDim.x >> 5)) {
-      float ax = 0.f, ay = 0.f;
+    for (int n0 = warp * kFirR; n0 < Nf; n0 += (blockDim.x >> 5) * kFirR) {
+      float2 acc[kFirR];
+#pragma unroll
+      for (int r = 0; r < kFirR; ++r) acc[r] = make_float2(0.f, 0.f);
       for (int t = lane; t < Tx; t += 32) {
-        const int s = t + pre - n;
-        if (s >= 0 && s < Tx) {
-          const float2 v = cmulc(sa[s], sg[t]);
-          ax += v.x;
-          ay += v.y;
+        const float2 g = sg[t];
+#pragma unroll
+        for (int r = 0; r < kFirR; ++r) {       // conj(x) * g
+          const float2 x = sa0[t + pre - n0 - r];
+          acc[r].x = fmaf(x.x, g.x, fmaf(x.y, g.y, acc[r].x));
+          acc[r].y = fmaf(x.x, g.y, fmaf(-x.y, g.x, acc[r].y));
         }
       }
-      ax = warp_sum(ax);
-      ay = warp_sum(ay);
-      if (lane == 0) {
-        if (accumulate) {
-          ax += o[n].x;
-          ay += o[n].y;
+#pragma unroll
+      for (int r = 0; r < kFirR; ++r) {
+        float ax = warp_sum(acc[r].x), ay = warp_sum(acc[r].y);
+        if (lane == 0 && n0 + r < Nf) {
+          if (accumulate) {
+            ax += o[n0 + r].x;
+            ay += o[n0 + r].y;
+          }
+          o[n0 + r] = make_float2(ax, ay);
         }
-        o[n] = make_float2(ax, ay);
       }
     }
   }
@@ -382,7 +416,7 @@ extern "C" int buddy_subband_fir(const float* a, const float* h_or_dy, int64_t h
     set_last_error("buddy_subband_fir: unsupported size Tx=%d Nf=%d mode=%d", Tx, Nf, mode);
     return BUDDY_ERR_UNSUPPORTED;
   }
-  subband_fir_kernel<<<dim3(F, batch), 256, 0, STREAM>>>(reinterpret_cast<const float2*>(a),
+  subband_fir_kernel<<<dim3(F, batch), 192, 0, STREAM>>>(reinterpret_cast<const float2*>(a),
                                                          reinterpret_cast<const float2*>(h_or_dy), h_batch_stride / 2,
                                                          reinterpret_cast<float2*>(out), F, Tx, Nf, pre, mode,
                                                          accumulate);

@@ -433,23 +433,39 @@ static int grid1(long long items, int threads, int cap = 148 * 8) {
 //   synthesis: fr[b][t][n]  = w[n] * Re( sum_f a[f] S[b][f][t] e^{+2 pi i f n / 1024} )
 // ------------------------------------------------------------------------------------------------
 constexpr int kFftN = 1024;
-constexpr int kFftFrames = 8;   // 68 KB of shared memory per CTA: three CTAs per SM hide the stage barriers
+constexpr int kFftFrames = 8;   // 74 KB of shared memory per CTA: three CTAs per SM hide the stage barriers
+// Shared-memory index of element k of frame fr: one padding slot after every 32 elements and an odd frame stride, so
+// that neither the bit-reversed gathers (addresses 32 elements apart across a warp) nor the frame-fastest loops
+// (addresses one frame apart) land in one bank (both were 8- to 16-way conflicts with the dense [frame][1024] layout).
+constexpr int kFftStride = kFftN + kFftN / 32 + 1;   // 1057
+__device__ __forceinline__ int fidx(int fr, int k) { return fr * kFftStride + k + (k >> 5); }
 __device__ __forceinline__ int bitrev10(int k) { return static_cast<int>(__brev(static_cast<unsigned>(k)) >> 22); }
+// per-stage twiddle tables: stage lh (butterfly span 2^lh) reads tws[2^lh - 1 + pos] = exp(-2 pi i pos / 2^(lh+1)),
+// pos < 2^lh — consecutive threads read consecutive entries (the single 512-entry table was read with strides of
+// 2^(9-lh) entries: 16-way shared-memory bank conflicts in the middle stages)
+__device__ __forceinline__ void fft_twiddles_to_smem(float2* tws, const float2* __restrict__ tw_g) {
+  for (int i = threadIdx.x; i < 1023; i += blockDim.x) {
+    const int lh = 31 - __clz(i + 1);
+    const int pos = i + 1 - (1 << lh);
+    tws[i] = tw_g[pos << (9 - lh)];
+  }
+}
 // in-place radix-2 decimation-in-frequency over `kFftFrames` frames [frame][1024] (natural order in, bit-reversed
-// out); tw[k] = exp(-2 pi i k / 1024), k < 512; conj_tw: inverse transform (unnormalised)
+// out); tw = per-stage tables (fft_twiddles_to_smem); conj_tw: inverse transform (unnormalised)
 __device__ __forceinline__ void fft1024_dif(float2* s, const float2* tw, bool conj_tw) {
   for (int lh = 9; lh >= 0; --lh) {          // butterfly span = 2^lh
     const int half = 1 << lh;
     for (int i = threadIdx.x; i < kFftFrames * 512; i += blockDim.x) {
       const int fr = i >> 9, j = i & 511;
       const int pos = j & (half - 1);
-      const int i0 = fr * kFftN + ((j >> lh) << (lh + 1)) + pos;
-      const float2 a = s[i0], b = s[i0 + half];
-      float2 w = tw[pos << (9 - lh)];
+      const int k0 = ((j >> lh) << (lh + 1)) + pos;
+      const int i0 = fidx(fr, k0), i1 = fidx(fr, k0 + half);
+      const float2 a = s[i0], b = s[i1];
+      float2 w = tw[half - 1 + pos];
       if (conj_tw) w.y = -w.y;
       const float2 d = make_float2(a.x - b.x, a.y - b.y);
       s[i0] = make_float2(a.x + b.x, a.y + b.y);
-      s[i0 + half] = make_float2(d.x * w.x - d.y * w.y, d.x * w.y + d.y * w.x);
+      s[i1] = make_float2(d.x * w.x - d.y * w.y, d.x * w.y + d.y * w.x);
     }
     __syncthreads();
   }
@@ -459,17 +475,17 @@ fft_analysis_kernel(const float* __restrict__ sig, long long sig_ld, const float
                     const float* __restrict__ av, const float2* __restrict__ tw_g, int bins, int K, int hop,
                     int frames, int Tout, float2* __restrict__ out) {
   extern __shared__ float2 fsm[];
-  float2* s = fsm;                       // [16][1024]
-  float2* tw = fsm + kFftFrames * kFftN;  // [512]
+  float2* s = fsm;                            // [kFftFrames] frames, padded (fidx)
+  float2* tw = fsm + kFftFrames * kFftStride;  // [1023] per-stage tables
   const int b = blockIdx.y, t0 = blockIdx.x * kFftFrames;
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) tw[i] = tw_g[i];
+  fft_twiddles_to_smem(tw, tw_g);
   const float* sb = sig + static_cast<long long>(b) * sig_ld;
   for (int i = threadIdx.x; i < kFftFrames * kFftN; i += blockDim.x) {
     const int fr = i >> 10, n = i & 1023;
     const int t = t0 + fr;
     float v = 0.f;
     if (n < K && t < frames) v = __ldg(wv + n) * __ldg(sb + static_cast<long long>(t) * hop + n);
-    s[i] = make_float2(v, 0.f);
+    s[fidx(fr, n)] = make_float2(v, 0.f);
   }
   __syncthreads();
   fft1024_dif(s, tw, false);
@@ -480,7 +496,7 @@ fft_analysis_kernel(const float* __restrict__ sig, long long sig_ld, const float
     if (t >= Tout) continue;
     float2 v = make_float2(0.f, 0.f);
     if (t < frames) {
-      const float2 x = s[fr * kFftN + bitrev10(f)];
+      const float2 x = s[fidx(fr, bitrev10(f))];
       const float a = __ldg(av + f);
       // DC and Nyquist of a real signal are real: exact zeros as in the matrix form (-sin rows vanish) — a rounding-
       // level residue here would be a spurious non-zero gradient for Adam, which normalises every element
@@ -494,9 +510,9 @@ fft_synthesis_kernel(const float2* __restrict__ S, int Tin, const float* __restr
                      const float2* __restrict__ tw_g, int bins, int K, int frames, float* __restrict__ fr_out) {
   extern __shared__ float2 fsm[];
   float2* s = fsm;
-  float2* tw = fsm + kFftFrames * kFftN;
+  float2* tw = fsm + kFftFrames * kFftStride;
   const int b = blockIdx.y, t0 = blockIdx.x * kFftFrames;
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) tw[i] = tw_g[i];
+  fft_twiddles_to_smem(tw, tw_g);
   const float2* Sb = S + static_cast<long long>(b) * bins * Tin;
   for (int i = threadIdx.x; i < kFftFrames * kFftN; i += blockDim.x) {
     const int f = i / kFftFrames, fr = i % kFftFrames;     // frames fastest: contiguous global segments per bin
@@ -507,7 +523,7 @@ fft_synthesis_kernel(const float2* __restrict__ S, int Tin, const float* __restr
       const float a = __ldg(av + f);
       v = make_float2(a * x.x, (f == 0 || 2 * f == kFftN) ? 0.f : a * x.y);   // imaginary DC / Nyquist do not contribute
     }
-    s[fr * kFftN + f] = v;
+    s[fidx(fr, f)] = v;
   }
   __syncthreads();
   fft1024_dif(s, tw, true);
@@ -515,7 +531,7 @@ fft_synthesis_kernel(const float2* __restrict__ S, int Tin, const float* __restr
     const int fr = i / K, n = i - fr * K;
     const int t = t0 + fr;
     if (t < frames)
-      fr_out[(static_cast<long long>(b) * frames + t) * K + n] = __ldg(wv + n) * s[fr * kFftN + bitrev10(n)].x;
+      fr_out[(static_cast<long long>(b) * frames + t) * K + n] = __ldg(wv + n) * s[fidx(fr, bitrev10(n))].x;
   }
 }
 
@@ -547,7 +563,7 @@ extern "C" int buddy_dft_synthesis(const float* S, int batch, int Tin, const flo
 static int fft_smem_attr() {
   static bool done = false;
   if (!done) {
-    const int bytes = (kFftFrames * kFftN + 512) * sizeof(float2);
+    const int bytes = (kFftFrames * kFftStride + 1024) * sizeof(float2);
     int e = check_cuda(cudaFuncSetAttribute(fft_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes),
                        "cudaFuncSetAttribute(fft_analysis_kernel)");
     if (e) return e;
@@ -567,7 +583,7 @@ extern "C" int buddy_fft_analysis(const float* sig, int64_t sig_ld, int batch, c
   }
   int e = fft_smem_attr();
   if (e) return e;
-  const size_t smem = (kFftFrames * kFftN + 512) * sizeof(float2);
+  const size_t smem = (kFftFrames * kFftStride + 1024) * sizeof(float2);
   dim3 grid((Tout + kFftFrames - 1) / kFftFrames, batch);
   fft_analysis_kernel<<<grid, 256, smem, STREAM>>>(sig, sig_ld, wv, av, reinterpret_cast<const float2*>(tw1024), bins,
                                                    K, hop, frames, Tout, reinterpret_cast<float2*>(out));
@@ -581,7 +597,7 @@ extern "C" int buddy_fft_synthesis(const float* S, int batch, int Tin, const flo
   }
   int e = fft_smem_attr();
   if (e) return e;
-  const size_t smem = (kFftFrames * kFftN + 512) * sizeof(float2);
+  const size_t smem = (kFftFrames * kFftStride + 1024) * sizeof(float2);
   dim3 grid((frames + kFftFrames - 1) / kFftFrames, batch);
   fft_synthesis_kernel<<<grid, 256, smem, STREAM>>>(reinterpret_cast<const float2*>(S), Tin, wv, av,
                                                     reinterpret_cast<const float2*>(tw1024), bins, K, frames, fr);

@@ -21,7 +21,7 @@ namespace buddy {
 extern std::atomic<long long> g_launches;
 
 constexpr int kWpeMaxTaps = 64;
-constexpr int kWpeMaxT = 2048;
+constexpr int kWpeMaxT = 4096;   // frames per utterance (30 s at shift 128: 3754)
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -198,6 +198,10 @@ extern "C" int buddy_wpe(const float* Y, int batch, int F, int T, int taps, int 
   }
   const size_t smem = sizeof(double) * (static_cast<size_t>(5) * T + 2 * static_cast<size_t>(taps) * taps + 2 * taps + 32) +
                       sizeof(int) * taps;
+  if (smem > 227 * 1024) {
+    set_last_error("buddy_wpe: %d frames x %d taps need %zu bytes of shared memory (> 227 KB)", T, taps, smem);
+    return BUDDY_ERR_UNSUPPORTED;
+  }
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
     int e = check_cuda(cudaFuncSetAttribute(wpe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),

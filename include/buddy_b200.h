@@ -160,7 +160,8 @@ int buddy_pack_weights(const buddy_pack_desc* d, void* stream);
 /* Weighted prediction error (WPE) dereverberation, one channel, per (utterance, frequency bin) — the
  * `wpe_scaled` warm start of the blind sampler.  Replaces nara_wpe.wpe.wpe(Y, taps, delay, iterations,
  * statistics_mode='full') as called by testing/EulerHeunSamplerDPS.py:32-54 (numpy, CPU, complex128).
- * Y, Z: fp32 [batch][F][T][2] (re, im); arithmetic in fp64.  taps <= 64, T <= 2048. */
+ * Y, Z: fp32 [batch][F][T][2] (re, im); arithmetic in fp64.  taps <= 64, T <= 4096 (and 40 T + 16 taps^2 bytes of
+ * shared memory <= 227 KB). */
 int buddy_wpe(const float* Y, int batch, int F, int T, int taps, int delay, int iterations, float* Z, void* stream);
 
 /* upfirdn2d: zero-insertion upsample -> pad / crop -> 2-D FIR -> downsample, fp32 — the reference's only native
