@@ -428,7 +428,7 @@ def run_ours(args):
                      "fp16_pass_equivalents_per_product": np_, "launches": calls,
                      "share_of_step": conv_ms / total_ms_ops if total_ms_ops else None},
         "kernel_time_share": {k: round(v[1] / total_ms_ops, 4) for k, v in
-                              sorted(summ.items(), key=lambda kv: -kv[1][1])[:6]},
+                              sorted(summ.items(), key=lambda kv: -kv[1][1])[:(16 if blind else 6)]},
         "roofline_secondary": [
             {"kernel": k, "bound": "hbm", "achieved": summ[k][2] / (summ[k][1] * 1e-3) / 1e9, "peak": peak_gbs,
              "unit": "GB/s", "frac": summ[k][2] / (summ[k][1] * 1e-3) / 1e9 / peak_gbs, "launches": summ[k][0],
