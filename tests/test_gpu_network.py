@@ -172,3 +172,29 @@ def test_long_form_30s_forward_and_vjp_vs_oracle(sd):
     e_out, e_vjp = rel(out.detach(), ref), rel(gout, gref)
     print(f"\n[net 30 s] fwd rel-L2 {e_out:.2e}  vjp rel-L2 {e_vjp:.2e}")
     assert e_out < TOL and e_vjp < TOL
+
+
+@pytest.mark.parametrize("n,B", [(2048, 3), (4000, 1), (131072, 2)])
+def test_edge_lengths_forward_and_vjp_vs_oracle(sd, n, B):
+    """Very short (0.13 s: 17 frames -> 32 padded, 4-frame bottleneck), ragged (4000 samples) and 8 s utterances, batched:
+    forward and data-gradient vs the oracle on the GPU (tile shapes, stacked-tile and narrow-N heuristics all change
+    with the size)."""
+    from buddy_b200.ncsnpp import NCSNppTime
+    from oracle import net as onet
+    net = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    x = (randn(40, B, 1, n) * 0.2).cuda()
+    tc = (0.25 * torch.log(torch.linspace(0.02, 0.4, B))).cuda()
+    cot = randn(41, B, 1, n).cuda() * 1e-3
+    xr = x.clone().requires_grad_(True)
+    ref = onet.ncsnpp_time_forward(sdc, xr, tc)
+    (gref,) = torch.autograd.grad((ref * cot).sum(), xr)
+    xg = x.clone().requires_grad_(True)
+    out = net(xg, tc)
+    (gout,) = torch.autograd.grad((out * cot).sum(), xg)
+    for b in range(B):
+        e_out, e_vjp = rel(out[b].detach(), ref[b].detach()), rel(gout[b], gref[b])
+        print(f"\n[net n={n} utt {b}] fwd rel-L2 {e_out:.2e}  vjp rel-L2 {e_vjp:.2e}")
+        assert e_out < TOL and e_vjp < TOL
