@@ -305,6 +305,7 @@ def run_ours(args):
         smp._bind_operator(op, y, False)
     t = smp.create_schedule()
     gamma = smp.get_gamma(t)
+    smp._start_run()                                   # run seed = seed_base (what predict*() does first)
     x = smp.initialize_x((B, N_SAMPLES), dev, t)
 
     def barrier():
