@@ -231,3 +231,39 @@ def test_wpe_oracle_conventions():
     y = np.convolve(s, h)[:n]
     d = ow.wpe_dereverb(y)
     assert d.shape == (n,) and np.linalg.norm(d - s) < 0.7 * np.linalg.norm(y - s)
+
+
+def test_checkpoint_loader_strategies(tmp_path):
+    """buddy_b200.checkpoint.load_checkpoint: the strategy chain of the reference's loaders (tester.py:60-98,
+    training_utils.py:5-98) on reference-format checkpoint dictionaries — EMA preferred, strict, non-strict,
+    shape-matched, legacy 'ema_weights' — into the drop-in network (same 271 keys as the reference's)."""
+    import pytest
+    import torch
+    from buddy_b200.checkpoint import CheckpointError, load_checkpoint
+    from buddy_b200.ncsnpp import NCSNppTime
+    from oracle.weights import make_state_dict
+    mk = lambda: NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    ema, other = make_state_dict(0), make_state_dict(1)
+    path = str(tmp_path / "ckpt.pt")
+    torch.save({"it": 190000, "network": other, "ema": ema, "optimizer": {}}, path)
+    net = mk()
+    info = load_checkpoint(path, net, log=lambda *a: None)
+    assert info["strategy"] == 1 and info["source"] == "ema" and info["it"] == 190000 and info["loaded"] == 271
+    assert all(torch.equal(v, ema[k]) for k, v in net.state_dict().items())
+    # non-strict: one tensor missing, one unexpected
+    part = {k: v for k, v in ema.items() if k != "output_layer.bias"}
+    part["extra.weight"] = torch.zeros(3)
+    info = load_checkpoint({"ema": part}, mk(), log=lambda *a: None)
+    assert info["strategy"] == 2 and info["missing"] == ["output_layer.bias"] and info["unexpected"] == ["extra.weight"]
+    # shape-matched: a tensor of the wrong shape is skipped, the rest is loaded
+    bad = dict(ema)
+    bad["output_layer.bias"] = torch.zeros(5)
+    net = mk()
+    info = load_checkpoint({"network": bad}, net, log=lambda *a: None)
+    assert info["strategy"] == 3 and info["loaded"] == 270 and info["source"] == "network"
+    assert torch.equal(net.state_dict()["all_modules.3.weight"], ema["all_modules.3.weight"])
+    # legacy layout
+    info = load_checkpoint({"model": other, "ema_weights": [ema[k] for k in other]}, net, log=lambda *a: None)
+    assert info["strategy"] == 4 and torch.equal(net.state_dict()["all_modules.1.weight"], ema["all_modules.1.weight"])
+    with pytest.raises(CheckpointError):
+        load_checkpoint({"it": 3}, mk(), log=lambda *a: None)
