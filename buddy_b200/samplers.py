@@ -320,7 +320,8 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
         if ps.rec_loss.name != "l2_comp_stft_summean":
             raise NotImplementedError(f"rec_loss {ps.rec_loss.name}: only l2_comp_stft_summean is on the hot path")
         self._Y = self._loss_stft.forward(y)
-        self._is_blind = bool(blind)
+        self._is_blind = bool(blind)          # operator parameters are optimised along the trajectory
+        self._subband = bool(blind)           # the likelihood goes through the sub-band (STFT-domain) operator
         self._eval_index = 0
         if blind:
             from .blind import BlindEngine
@@ -338,6 +339,19 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
                                   crop_min=float(reg.crop_sigma_min))
             return
         rir = getattr(operator, "params", None)
+        H = getattr(operator, "H", None)
+        if torch.is_tensor(H) and H.is_complex() and not torch.is_tensor(rir):
+            # informed SubbandFiltering operator (subband_filtering.py:8-113, `update_H(rir=...)` / `update_H(H=...)`): a
+            # KNOWN filter H (513, 100) or one per utterance (B, 513, 100); same likelihood chain as the blind path,
+            # nothing is optimised
+            from .blind import BlindEngine
+            B = y.shape[0]
+            self._blind = BlindEngine(n, dev, op_hp=getattr(operator, "op_hp", None),
+                                      sample_rate=self.args.exp.sample_rate)
+            z = torch.zeros(1, 25, device=dev)
+            self._blind.init_state(B, z, z, torch.zeros(self._blind.F, self._blind.NF, device=dev), H)
+            self._subband = True
+            return
         if rir is None:
             raise ValueError("operator has no RIR (`.params`): call operator.update_params(rir) first")
         self._rir = RirConv(rir.detach().to(dev), n, dev)
@@ -352,7 +366,9 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
         cskip, cout, cin, _ = self._edm_scalars(sigma)
         net = self.model
         eng, st = net.engine(), net.stft_engine()
-        if self._is_blind:
+        if self._subband:
+            if not self._is_blind:
+                self._blind.select(slice(first, first + B))
             gd, loss = self._blind.likelihood_grad(x_den, Y, self._loss_w, self._loss_c)
         else:
             y_hat = self._rir.forward(x_den, first)

@@ -82,7 +82,7 @@ def _likelihood(sd, x_in, sigma, y, degrade, zeta, audio_len, rescale):
 
 
 def dps_informed(sd, y, rir, T, noise, zeta=2.75, Schurn=10, order=2, audio_len=65536, warm="reverb_scaled",
-                 rescale=False):
+                 rescale=False, degrade_fn=None):
     """y (1,N) observation, rir (M,).  Informed DPS (conf/tester/informed_dereverberation_DPS.yaml).
     rescale = constraint_speech_magnitude.use: applied after the FIRST evaluation of a step only — the reference's
     Heun correction (EulerHeunSamplerDPS.py:136-150) has no rescale line."""
@@ -92,7 +92,8 @@ def dps_informed(sd, y, rir, T, noise, zeta=2.75, Schurn=10, order=2, audio_len=
     x = t[0] * next(it)
     if warm == "reverb_scaled":
         x = SIGMA_DATA * y.clone() / y.std() + x
-    degrade = lambda v: oop.fast_apply_rir(v, rir)
+    # degrade_fn: any other known operator, e.g. an informed SubbandFiltering (subband_filtering.py:82-101) with fixed H
+    degrade = degrade_fn or (lambda v: oop.fast_apply_rir(v, rir))
     x_den = None
     for i in range(T):
         x_hat, t_hat = _perturb(x, t[i], gamma[i], next(it))
