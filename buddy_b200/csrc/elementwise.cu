@@ -971,6 +971,45 @@ extern "C" int buddy_transpose_h(const void* in, int batch, int R, int Cc, int64
                                                        static_cast<__half*>(out), ld_out, bs_out);
   LAUNCH_END("transpose_h_kernel");
 }
+// fp32 [B][H][W][C] -> tensor-core operand of scale * x (fp16, + e4m3 pair when out8 is given), optionally through a
+// nearest-neighbour x2 upsampling (up = 1: out is [B][2H][2W][C]).  For the convolutions that take a RAW tensor: the
+// Downsample / Upsample modules of the `resblock_type: ddpm` variant (layerspp.py:93-160) and their data-gradients.
+__global__ void cast_operand_kernel(const float* __restrict__ x, int B, int H, int W, int C, int up, float scale,
+                                    __half* __restrict__ out, uint8_t* __restrict__ out8, int split) {
+  const int c4n = C >> 2;
+  const int Ho = up ? 2 * H : H, Wo = up ? 2 * W : W;
+  const long long total = static_cast<long long>(B) * Ho * Wo * c4n;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c4n) * 4;
+    const long long po = i / c4n;                       // output pixel (b, ho, wo) linear
+    long long pi = po;
+    if (up) {
+      const int wo = static_cast<int>(po % Wo);
+      const long long r = po / Wo;
+      const int ho = static_cast<int>(r % Ho);
+      const long long b = r / Ho;
+      pi = (b * H + (ho >> 1)) * W + (wo >> 1);
+    }
+    float4 v = __ldg(reinterpret_cast<const float4*>(x + pi * C + c));
+    v = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+    store_op4(out, out8, static_cast<size_t>(po), C, c, split, v);
+  }
+}
+
+extern "C" int buddy_cast_operand(const float* x, int batch, int H, int W, int C, int upsample, float scale, void* out16,
+                                  void* out8, int split, void* stream) {
+  if (!x || !out16 || C % 4 || batch <= 0 || H <= 0 || W <= 0) {
+    set_last_error("buddy_cast_operand: invalid argument (C %% 4 == 0 required)");
+    return BUDDY_ERR_INVALID;
+  }
+  const long long total = static_cast<long long>(batch) * H * W * (upsample ? 4 : 1) * (C / 4);
+  cast_operand_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(x, batch, H, W, C, upsample, scale,
+                                                                static_cast<__half*>(out16),
+                                                                static_cast<uint8_t*>(out8), split);
+  LAUNCH_END("cast_operand_kernel");
+}
+
 extern "C" int buddy_cast_scale_h(const float* x, int64_t n, float scale, void* y, void* stream) {
   if (n % 8) {
     set_last_error("buddy_cast_scale_h: n %% 8 != 0");

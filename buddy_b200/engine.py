@@ -13,7 +13,7 @@ import math
 
 import torch
 
-from . import ops
+from . import ops, upfirdn2d
 from .ops import MODE_DOWN, MODE_NONE, MODE_UP
 
 INV_SQRT2 = 1.0 / math.sqrt(2.0)
@@ -88,8 +88,11 @@ class Engine:
     # 1.52 -> 1.34 fp16-pass equivalents per product.
     BWD_X1_POLICY = "E"
 
-    def __init__(self, state_dict, device, precision="mixed"):
-        """precision: operand scheme of the conv GEMMs (all accumulate in fp32 on tcgen05):
+    def __init__(self, state_dict, device, precision="mixed", resblock_type="biggan"):
+        """resblock_type: "biggan" (shipped configuration) or "ddpm": ResnetBlockDDPMpp blocks — the same two-conv block,
+           skip through NIN_0 — and, in the place of the resampling ResBlocks, Downsample / Upsample modules with one 3x3
+           convolution on the RAW tensor (layerspp.py:93-216; ncsnpp.py:141-144,200-201,262-263).
+           precision: operand scheme of the conv GEMMs (all accumulate in fp32 on tcgen05):
              "fp16"   one pass, 11-bit significands (what cuDNN's default TF32 path gives the reference on a GPU)
              "fp16x2" activations split hi+lo (fp16), weights single
              "fp16x3" activations and weights split hi+lo (fp16): three fp16 passes in one launch, fp32-class products
@@ -98,6 +101,11 @@ class Engine:
                       the cost of two fp16 passes
              "mixed"  fp16c8, except the few largest convolutions which run single-pass (see MIXED_X1_THRESHOLD)"""
         self.device = torch.device(device)
+        assert resblock_type in ("biggan", "ddpm"), resblock_type
+        self.ddpm = resblock_type == "ddpm"
+        self.resamp = {}        # ddpm: module index -> Downsample / Upsample convolution
+        self._k1 = torch.ones(1, 1, device=self.device)         # upfirdn taps: pick / zero-stuff
+        self._k22 = torch.ones(2, 2, device=self.device)        # ... and the 2x2 sum (adjoint of nearest x2)
         self.precision = precision
         self.np = self.PRECISIONS[precision]
         self.c8 = precision in ("fp16c8", "mixed")
@@ -139,7 +147,10 @@ class Engine:
             self._pack_rb(i, lvl)
             i += 1
             if lvl != top:
-                self._pack_rb(i, lvl + 1)       # `down` block: its convolutions run at the next (coarser) level
+                if self.ddpm:
+                    self._pack_resample(i)
+                else:
+                    self._pack_rb(i, lvl + 1)   # `down` block: its convolutions run at the next (coarser) level
                 i += 1
                 self.comb[i] = (f32(sd[f"all_modules.{i}.Conv_0.weight"].reshape(-1, 2)),
                                 f32(sd[f"all_modules.{i}.Conv_0.bias"]))
@@ -160,7 +171,10 @@ class Engine:
             i += 2
             upb = None
             if lvl != 0:
-                self._pack_rb(i, lvl - 1)       # `up` block: its convolutions run at the next (finer) level
+                if self.ddpm:
+                    self._pack_resample(i)
+                else:
+                    self._pack_rb(i, lvl - 1)   # `up` block: its convolutions run at the next (finer) level
                 upb = i
                 i += 1
             self.up_levels.append((blocks, head, upb))
@@ -270,15 +284,26 @@ class Engine:
         r.w1, r.wd1 = self._pack3x3(sd[p + "Conv_1.weight"], r.x1[1], r.x1b[1])
         r.bias0 = sd[p + "Conv_0.bias"].contiguous()
         r.dense = (sd[p + "Dense_0.weight"].contiguous(), sd[p + "Dense_0.bias"].contiguous())
-        r.has_skip_conv = (p + "Conv_2.weight") in sd
+        nin = (p + "NIN_0.W") in sd                                 # ddpm blocks: skip = NIN_0, W stored (in, out)
+        r.has_skip_conv = nin or (p + "Conv_2.weight") in sd
         if r.has_skip_conv:
-            w2 = sd[p + "Conv_2.weight"].contiguous()               # [Cout, Cin, 1, 1]
+            w2 = sd[p + "NIN_0.W"].t().contiguous() if nin else sd[p + "Conv_2.weight"].contiguous()   # [Cout, Cin(,1,1)]
             r.w2 = self._packv(w2, 1, r.cout, r.cin, r.x1[1], sn=(r.cout, 0, r.cin), sk=(r.cin, 0, 1))   # fused into conv 1
             r.wd2 = self._packv(w2, 1, r.cin, r.cout, r.x1b[1], sn=(r.cin, 0, 1), sk=(r.cout, 0, r.cin))
-            r.bias1 = (sd[p + "Conv_1.bias"] + sd[p + "Conv_2.bias"]).contiguous()
+            r.bias1 = (sd[p + "Conv_1.bias"] + sd[p + ("NIN_0.b" if nin else "Conv_2.bias")]).contiguous()
         else:
             r.bias1 = sd[p + "Conv_1.bias"].contiguous()
         self.rb[i] = r
+
+    def _pack_resample(self, i):
+        """ddpm Downsample / Upsample (layerspp.py:93-160, with_conv, fir = False): one 3x3 convolution with bias."""
+        sd, p = self.sd, f"all_modules.{i}."
+        m = _RB()
+        w = sd[p + "Conv_0.weight"]
+        m.c = w.shape[0]
+        m.w, m.wd = self._pack3x3(w)
+        m.bias = sd[p + "Conv_0.bias"].contiguous()
+        self.resamp[i] = m
 
     def _pack_attn(self, i):
         sd, p = self.sd, f"all_modules.{i}."
@@ -411,6 +436,63 @@ class Engine:
         if g16a:
             self._record(("x", i), g16a)
         return dxa, g16a, dxb
+
+    # ------------------------------------------------------------------ ddpm Downsample / Upsample
+    def _add32(self, a, b):
+        B = a.shape[0]
+        one = torch.ones(B, device=self.device)
+        return ops.lincomb3(torch.empty(B, a[0].numel(), device=self.device), a.view(B, -1), one, b.view(B, -1),
+                            one).view(a.shape)
+
+    def _down_fwd(self, i, x):
+        """Downsample (layerspp.py:147-154): zero-pad right/bottom by one, 3x3 convolution with stride 2.  Output pixel
+        (r, c) is pixel (2r+1, 2c+1) of the stride-1 'same' convolution, so the tensor-core kernel runs unchanged at
+        the input resolution and upfirdn2d (1 tap, down 2, origin -1) keeps the odd pixels."""
+        m = self.resamp[i]
+        B, H, W, C = x.shape
+        a = self._operand(B, H, W, C)
+        ops.cast_operand(x, a.t16, a.t8, split=self.split)
+        full = torch.empty(B, H, W, C, device=self.device)
+        self._conv(a, m.w, full, taps=9, n_total=C, bias=m.bias)
+        return upfirdn2d._launch(full, self._k1, (1, 1), (2, 2), (-1, 0, -1, 0))
+
+    def _down_bwd(self, i, d32, extra, consumer):
+        """d32 fp32 = gradient w.r.t. the module's output; returns the gradient w.r.t. its input (+ `extra`) in fp32
+        and as the fp16(/sqrt2) operand of the producing ResBlock."""
+        m = self.resamp[i]
+        B, h, w, C = d32.shape
+        zs = upfirdn2d._launch(d32, self._k1, (2, 2), (1, 1), (1, -1, 1, -1))     # zero-stuffed: (2r+1, 2c+1) <- (r, c)
+        op = self._operand(B, 2 * h, 2 * w, C, self._gscale(("dn", i)))
+        ops.cast_operand(zs, op.t16, op.t8, scale=op.gs, split=self.split)
+        self._record(("dn", i), op)
+        del zs
+        dx = torch.empty(B, 2 * h, 2 * w, C, device=self.device)
+        self._conv(op, m.wd, dx, taps=9, n_total=C)
+        if extra is not None:
+            dx = self._add32(dx, extra)
+        g = self._operand(B, 2 * h, 2 * w, C, self._gscale(("dnx", i)), need8=not self._x1(consumer, 1))
+        ops.cast_operand(dx, g.t16, g.t8, scale=INV_SQRT2 * g.gs, split=self.split)
+        self._record(("dnx", i), g)
+        return dx, g
+
+    def _up_fwd(self, i, x):
+        """Upsample (layerspp.py:113-118): nearest x2 (folded into the operand cast), then the 3x3 convolution."""
+        m = self.resamp[i]
+        B, H, W, C = x.shape
+        a = self._operand(B, 2 * H, 2 * W, C)
+        ops.cast_operand(x, a.t16, a.t8, upsample=True, split=self.split)
+        out = torch.empty(B, 2 * H, 2 * W, C, device=self.device)
+        so = self._zeros_stats(B, C)
+        self._conv(a, m.w, out, taps=9, n_total=C, bias=m.bias, stats=so)
+        return out, so
+
+    def _up_bwd(self, i, g16):
+        """g16 = operand of the gradient w.r.t. the module's output (scale 1) -> fp32 gradient w.r.t. its input."""
+        m = self.resamp[i]
+        B, H2, W2, _ = g16.t16.shape
+        da = torch.empty(B, H2, W2, m.c, device=self.device)
+        self._conv(g16, m.wd, da, taps=9, n_total=m.c)
+        return upfirdn2d._launch(da, self._k22, (1, 1), (2, 2), (0, 0, 0, 0))         # 2x2 sums
 
     # ------------------------------------------------------------------ attention
     # Attention over N = H*W tokens (AttnBlockpp, layerspp.py:75-91).  Up to ATTN_DENSE_BYTES of logits + probabilities
@@ -677,7 +759,10 @@ class Engine:
             i += 1
             hs.append((h, sh))
             if lvl != 3:
-                h, sh = self._rb_fwd(i, h, sh, None, None, tb, MODE_DOWN, ctx)
+                if self.ddpm:
+                    h = self._down_fwd(i, h)
+                else:
+                    h, sh = self._rb_fwd(i, h, sh, None, None, tb, MODE_DOWN, ctx)
                 i += 1
                 w, b = self.comb[i]
                 hc = ops.combine_fwd(h, pyr[lvl + 1], w, b, torch.empty_like(h))
@@ -700,7 +785,10 @@ class Engine:
             else:
                 pyramid = ops.resample_c2(pyramid, 1, torch.empty_like(ph), add=ph)
             if upb is not None:
-                h, sh = self._rb_fwd(upb, h, sh, None, None, tb, MODE_UP, ctx)
+                if self.ddpm:
+                    h, sh = self._up_fwd(upb, h)
+                else:
+                    h, sh = self._rb_fwd(upb, h, sh, None, None, tb, MODE_UP, ctx)
         assert not hs
         out = ops.affine_c2(pyramid, self.out_m, self.out_b, torch.empty_like(pyramid))
         if save:
@@ -732,7 +820,10 @@ class Engine:
             blocks, head, upb = self.up_levels[lvl_pos]
             if upb is not None:
                 # `up` block: consumes h (also seen by this level's head) -> partial gradient only
-                carry32, _, _ = self._rb_bwd(upb, ctx, g16, None, want_a32=True, want_a16=False)
+                if self.ddpm:
+                    carry32 = self._up_bwd(upb, g16)
+                else:
+                    carry32, _, _ = self._rb_bwd(upb, ctx, g16, None, want_a32=True, want_a16=False)
             else:
                 carry32 = None
             h, sh = ctx["head_in"][head]
@@ -747,7 +838,10 @@ class Engine:
                     cons = blocks[0]
                 else:
                     cons = self.up_levels[lvl_pos - 1][2] if lvl_pos > 0 else self.attn_idx + 1
-                d32, g16, dxb = self._rb_bwd(bi, ctx, g16, None, want_a32=need32, want_a16=True, consumer=cons)
+                # ddpm: the h-part of a level's first block comes straight out of the Upsample convolution (no /sqrt2)
+                a16s = 1.0 if (self.ddpm and first_of_level and lvl_pos > 0) else INV_SQRT2
+                d32, g16, dxb = self._rb_bwd(bi, ctx, g16, None, want_a32=need32, want_a16=True, a16_scale=a16s,
+                                             consumer=cons)
                 partial_hs[hs_idx] = dxb
                 hs_idx += 1
         # bottleneck: RB16 <- attention <- RB14
@@ -762,12 +856,16 @@ class Engine:
         i = self.attn_idx - 2       # 13
         for lvl in (3, 2, 1):
             # plain block at this level: input is the Combine output hs[2*lvl]
-            d32, g16, _ = self._rb_bwd(i, ctx, g16, d32, extra_a=partial_hs[2 * lvl], want_a32=True, consumer=i - 2)
+            d32, g16, _ = self._rb_bwd(i, ctx, g16, d32, extra_a=partial_hs[2 * lvl], want_a32=True,
+                                       want_a16=not self.ddpm, consumer=i - 2)
             w, _ = self.comb[i - 1]
             dpyr[lvl] = ops.combine_bwd(d32, w, torch.empty(B, d32.shape[1], d32.shape[2], 2, device=dev))
-            # down block (has skip conv): input hs[2*lvl-1]
-            d32, g16, _ = self._rb_bwd(i - 2, ctx, g16, None, extra_a=partial_hs[2 * lvl - 1], want_a32=True,
-                                       consumer=i - 3)
+            # down block (has skip conv) / ddpm Downsample: input hs[2*lvl-1]
+            if self.ddpm:
+                d32, g16 = self._down_bwd(i - 2, d32, partial_hs[2 * lvl - 1], consumer=i - 3)
+            else:
+                d32, g16, _ = self._rb_bwd(i - 2, ctx, g16, None, extra_a=partial_hs[2 * lvl - 1], want_a32=True,
+                                           consumer=i - 3)
             i -= 3
         # RB4 (identity skip) : input hs[0]; its producer is the input conv -> fp16 at scale 1
         _, g16, _ = self._rb_bwd(4, ctx, g16, d32, extra_a=partial_hs[0], want_a32=False, a16_scale=1.0)

@@ -56,18 +56,23 @@ class NCSNpp(nn.Module):
         super().__init__()
         import os
         self.precision = precision or os.environ.get("BUDDY_PRECISION", "mixed")
+        # resblock_type: "biggan" (shipped) or "ddpm" — ResnetBlockDDPMpp blocks (skip through a NIN) with separate
+        # Downsample / Upsample modules carrying a 3x3 convolution (layerspp.py:93-216); same module indices
+        self.resblock_type = str(kwargs.get("resblock_type", "biggan")).lower()
         for k, v in kwargs.items():
             if k in _SUPPORTED:
                 want = _SUPPORTED[k]
                 got = tuple(v) if isinstance(want, tuple) else v
                 got = got.lower() if isinstance(got, str) else got
+                if k == "resblock_type" and got in ("biggan", "ddpm"):
+                    continue
                 if got != want:
                     raise NotImplementedError(
                         f"buddy_b200.NCSNpp implements the shipped BUDDy configuration only: {k}={v!r} (need {want!r})")
         self.time_conditional = True
         self.spatial_channels, self.input_channels = 1, 2
         self.FORCE_STFT_OUT = False
-        for key, shape in netspec.param_spec():
+        for key, shape in netspec.param_spec(self.resblock_type):
             leaf = key.split(".")[-1]
             owner = key.split(".")[-2]
             if key == "all_modules.0.W":
@@ -103,7 +108,8 @@ class NCSNpp(nn.Module):
                                "(there is no CPU fallback)")
         key = (str(dev), self.precision, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
         if self._engine is None or key != self._engine_key:
-            self._engine = Engine(self.state_dict(), dev, precision=self.precision)
+            self._engine = Engine(self.state_dict(), dev, precision=self.precision,
+                                  resblock_type=self.resblock_type)
             self._engine_key = key
         return self._engine
 

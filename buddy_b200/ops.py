@@ -262,6 +262,15 @@ def transpose_h(x, out):
     return out
 
 
+def cast_operand(x, out16, out8=None, scale=1.0, upsample=False, split=0):
+    """x fp32 [B,H,W,C] -> operand of scale*x (see buddy_cast_operand); out16 [B,H',W',C (2C for split 1)]."""
+    B, H, W, C = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and out16.dtype == torch.float16
+    check(lib().buddy_cast_operand(ptr(x), c_int(B), c_int(H), c_int(W), c_int(C), c_int(int(upsample)), c_float(scale),
+                                   ptr(out16), ptr(out8), c_int(int(split)), stream_ptr()), "buddy_cast_operand")
+    return out16
+
+
 def cast_scale_h(x, scale, y):
     check(lib().buddy_cast_scale_h(ptr(x), c_i64(x.numel()), c_float(scale), ptr(y), stream_ptr()),
           "buddy_cast_scale_h")
@@ -521,7 +530,7 @@ conv_gemm = _timed(conv_gemm, _conv_flops, _conv_tag)
 gn_apply = _timed(gn_apply, _gn_apply_bytes)
 gn_bwd = _timed(gn_bwd, _gn_bwd_bytes)
 for _n in ("gn_stats", "im2col_c2", "col2im_c2", "resample_c2", "combine_fwd", "combine_bwd",
-           "affine_c2", "softmax_fwd", "softmax_bwd", "transpose_h", "cast_scale_h", "dft_analysis", "dft_synthesis", "fft_analysis", "fft_synthesis",
+           "affine_c2", "softmax_fwd", "softmax_bwd", "transpose_h", "cast_scale_h", "cast_operand", "dft_analysis", "dft_synthesis", "fft_analysis", "fft_synthesis",
            "ola_gather", "pad_signal", "reflect_fold", "comp_loss", "row_stats", "fftconv", "fourier_features",
            "dense", "philox_normal", "lincomb3"):
     globals()[_n] = _timed(globals()[_n])

@@ -255,6 +255,12 @@ int buddy_softmax_bwd(const void* p, int ldp, const float* dp, int64_t rows, int
 int buddy_transpose_h(const void* in, int batch, int R, int C, int64_t ld_in, int64_t bs_in, void* out,
                       int64_t ld_out, int64_t bs_out, void* stream);
 int buddy_cast_scale_h(const float* x, int64_t n, float scale, void* y, void* stream);
+/* fp32 [batch][H][W][C] -> tensor-core operand of scale * x: fp16 `out16` (split 1: [hi | lo]) and, for split 2 with
+ * out8 != NULL, the e4m3 pair (buddy_gemm_desc.a8); upsample = 1 goes through nearest-neighbour x2 first
+ * (out [batch][2H][2W][..]).  Feeds the convolutions that take a RAW tensor: Downsample / Upsample with_conv of the
+ * `resblock_type: ddpm` variant (networks/ncsnpp_utils/layerspp.py:93-160) and their data-gradients. */
+int buddy_cast_operand(const float* x, int batch, int H, int W, int C, int upsample, float scale, void* out16,
+                       void* out8, int split, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * STFT / iSTFT as fp32 DFT-GEMMs with exact frame indexing (torch.stft / torch.istft semantics of

@@ -87,10 +87,11 @@ def install():
         sys.path.insert(0, REF_ROOT)
 
 
-def build_network(state_dict=None):
+def build_network(state_dict=None, **overrides):
+    """The reference's own NCSNppTime; `overrides` replace entries of the shipped configuration (resblock_type=...)."""
     install()
     from networks.ncsnpp import NCSNppTime
-    net = NCSNppTime(stft=AD(n_fft=510, hop_length=128, center=True), **NCSNPP_CFG)
+    net = NCSNppTime(stft=AD(n_fft=510, hop_length=128, center=True), **dict(NCSNPP_CFG, **overrides))
     if state_dict is not None:
         net.load_state_dict(state_dict)
     return net.eval()

@@ -74,10 +74,11 @@ def param_spec():
     return keys
 
 
-def make_state_dict(seed=0, dtype=torch.float32):
+def make_state_dict(seed=0, dtype=torch.float32, spec=None):
+    """spec: [(key, shape)] of another variant (e.g. the reference module's own state_dict layout); default shipped."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
-    for key, shape in param_spec():
+    for key, shape in (spec or param_spec()):
         if key == "all_modules.0.W":
             t = torch.randn(shape, generator=g) * 16.0  # GaussianFourierProjection, fourier_scale 16
         elif "GroupNorm" in key or key.split(".")[-2] in ("19", "24", "29", "34"):

@@ -163,6 +163,31 @@ def test_softmax_transpose_cast():
     assert rel(yh.float(), xf * 0.5) < 1e-3
 
 
+def test_cast_operand():
+    """Raw fp32 tensor -> tensor-core operand (fp16, fp16 hi|lo, fp16 + e4m3 pair), optional nearest x2 upsampling."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(12)
+    B, H, W, C = 2, 6, 10, 128
+    x = torch.randn(B, H, W, C, device="cuda", generator=g)
+    for up in (False, True):
+        ref = nhwc(resample(nchw(x), 1)) * 0.5 if up else x * 0.5
+        Ho, Wo = ref.shape[1:3]
+        o = ops.cast_operand(x, torch.empty(B, Ho, Wo, C, device="cuda", dtype=torch.float16), scale=0.5, upsample=up)
+        assert torch.equal(o, ref.half())
+        o2 = ops.cast_operand(x, torch.empty(B, Ho, Wo, 2 * C, device="cuda", dtype=torch.float16), scale=0.5,
+                              upsample=up, split=1)
+        assert torch.equal(o2[..., :C], ref.half()) and rel(o2[..., :C].float() + o2[..., C:].float(), ref) < 1e-6
+        o8 = torch.empty(B, Ho, Wo, 2 * C, device="cuda", dtype=torch.uint8)
+        o3 = ops.cast_operand(x, torch.empty(B, Ho, Wo, C, device="cuda", dtype=torch.float16), o8, scale=0.5,
+                              upsample=up, split=2)
+        assert torch.equal(o3, ref.half())
+        # e4m3 pair = [e4m3(lo * 2^9) | e4m3(hi)], the layout gn_apply writes (elementwise.cu store_op4)
+        hi = ref.half().float()
+        f8 = o8.view(torch.float8_e4m3fn).float()
+        assert torch.equal(f8[..., C:], hi.to(torch.float8_e4m3fn).float())
+        assert torch.equal(f8[..., :C], ((ref - hi) * 512.0).to(torch.float8_e4m3fn).float())
+
+
 def test_upfirdn2d_vs_reference_fixture_and_oracle():
     """sm_100a upfirdn2d (the reference's only native operator, op/upfirdn2d_kernel.cu:107-207) against outputs of the
     reference's own CPU branch (tests/golden/upfirdn2d.pt), its data-gradient against autograd through the oracle, the

@@ -7,6 +7,7 @@ the blind path — call `sampler.operator.get_time_RIR()` on the reference objec
 from the reference's own sampler + network run on the same GPU (fp32, TF32 off) with identical injected noise.
 """
 import copy
+import math
 
 import pytest
 import torch
@@ -156,3 +157,33 @@ def test_api_operator_classes_match_reference(rh):
     bop.params[0] = torch.full((1, 25), float("nan"), device="cuda")
     with pytest.raises(AssertionError):
         bop.project_params()
+
+
+def test_ddpm_resblock_variant_vs_reference_network(rh):
+    """`resblock_type: ddpm` (ResnetBlockDDPMpp + Downsample / Upsample with a 3x3 convolution, layerspp.py:93-216):
+    the reference network built with that option, trained-like weights in ITS state_dict layout loaded into ours,
+    forward and data-gradient through the time-domain wrapper against the reference on this GPU (fp32, TF32 off)."""
+    from buddy_b200.ncsnpp import NCSNppTime
+    from oracle.weights import make_state_dict
+    ref_net = rh.build_network(resblock_type="ddpm")
+    spec = [(k, tuple(v.shape)) for k, v in ref_net.state_dict().items()]
+    assert len(spec) == 211 and any(k.endswith("NIN_0.W") for k, _ in spec)
+    ref_net.load_state_dict(make_state_dict(3, spec=spec))
+    ref_net = ref_net.cuda()
+    ours = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2],
+                      resblock_type="ddpm")
+    ours.load_state_dict(ref_net.state_dict())
+    ours = ours.cuda().eval()
+    B = 2
+    x = (randn(400, B, 1, 16384) * 0.05).cuda()
+    tc = torch.tensor([0.25 * math.log(0.3), 0.25 * math.log(0.02)], device="cuda")
+    cot = randn(401, B, 1, 16384).cuda()
+    xr = x.clone().requires_grad_(True)
+    want = ref_net(xr, tc)
+    (gw,) = torch.autograd.grad((want * cot).sum(), xr)
+    xo = x.clone().requires_grad_(True)
+    got = ours(xo, tc)
+    (gg,) = torch.autograd.grad((got * cot).sum(), xo)
+    ef, eb = rel(got, want.detach()), rel(gg, gw)
+    print(f"\n[ddpm variant vs the reference network] forward {ef:.2e}  data-gradient {eb:.2e}")
+    assert ef < TOL and eb < TOL
