@@ -10,6 +10,7 @@ This module only orchestrates kernels (pointers, shapes, order); it contains no 
 the one-time weight repacking.  Host-side tensors are torch CUDA tensors used as device-memory handles.
 """
 import math
+import os
 
 import torch
 
@@ -88,10 +89,13 @@ class Engine:
     # 1.52 -> 1.34 fp16-pass equivalents per product.
     BWD_X1_POLICY = "E"
 
-    def __init__(self, state_dict, device, precision="mixed", resblock_type="biggan"):
+    def __init__(self, state_dict, device, precision="mixed", resblock_type="biggan", progressive="output_skip",
+                 progressive_input="input_skip"):
         """resblock_type: "biggan" (shipped configuration) or "ddpm": ResnetBlockDDPMpp blocks — the same two-conv block,
            skip through NIN_0 — and, in the place of the resampling ResBlocks, Downsample / Upsample modules with one 3x3
            convolution on the RAW tensor (layerspp.py:93-216; ncsnpp.py:141-144,200-201,262-263).
+           progressive / progressive_input other than the shipped output_skip / input_skip run on the general module
+           walk of engine_generic.py (same kernels, gradients kept in fp32 between modules).
            precision: operand scheme of the conv GEMMs (all accumulate in fp32 on tcgen05):
              "fp16"   one pass, 11-bit significands (what cuDNN's default TF32 path gives the reference on a GPU)
              "fp16x2" activations split hi+lo (fp16), weights single
@@ -103,6 +107,9 @@ class Engine:
         self.device = torch.device(device)
         assert resblock_type in ("biggan", "ddpm"), resblock_type
         self.ddpm = resblock_type == "ddpm"
+        # (BUDDY_GENERIC_WALK=1 runs the shipped graph through the general walk as well: tests compare the two)
+        self.generic = ((progressive, progressive_input) != ("output_skip", "input_skip")
+                        or os.environ.get("BUDDY_GENERIC_WALK", "0") == "1")
         self.resamp = {}        # ddpm: module index -> Downsample / Upsample convolution
         self._k1 = torch.ones(1, 1, device=self.device)         # upfirdn taps: pick / zero-stuff
         self._k22 = torch.ones(2, 2, device=self.device)        # ... and the 2x2 sum (adjoint of nearest x2)
@@ -112,7 +119,6 @@ class Engine:
         self.mixed = precision == "mixed"
         self.x1_convs = set()   # (module index, conv index) whose DATA-GRADIENT launch runs single-pass (mixed mode)
         self.x1_fwd = set()     # ... whose forward launch does
-        import os
         # BUDDY_FUSE_GNB=1 folds GroupNorm-backward's statistics pass into the producing dgrad convolution's epilogue
         # where the geometry allows (no resample, single input tensor).  Correct (tests) but OFF by default: measured
         # on B200 it removes 19 ms of GroupNorm time per B=32 step and adds 51 ms to the convolutions (the epilogue's
@@ -137,48 +143,52 @@ class Engine:
         self.in_w = self._packv(w3, 1, NF, 64, sn=(NF, 0, 18), sk=(2, 1, 9), k_valid=18)     # [1, NF, p*64]
         self.in_wd = self._packv(w3, 1, 32, NF, sn=(2, 1, 9), sk=(NF, 0, 18), n_valid=18)    # [1, 32, p*NF]
         self.in_b = f32(sd["all_modules.3.bias"])
-        # ---- walk the module list exactly as the reference builds it
         self.rb = {}
         self.comb = {}
         self.heads = {}
-        i = 4
-        top = len(CH_MULT) - 1
-        for lvl in range(len(CH_MULT)):
-            self._pack_rb(i, lvl)
-            i += 1
-            if lvl != top:
-                if self.ddpm:
-                    self._pack_resample(i)
-                else:
-                    self._pack_rb(i, lvl + 1)   # `down` block: its convolutions run at the next (coarser) level
+        if self.generic:
+            from . import engine_generic
+            engine_generic.build(self, resblock_type, progressive, progressive_input)
+        else:
+            # ---- walk the module list exactly as the reference builds it
+            i = 4
+            top = len(CH_MULT) - 1
+            for lvl in range(len(CH_MULT)):
+                self._pack_rb(i, lvl)
                 i += 1
-                self.comb[i] = (f32(sd[f"all_modules.{i}.Conv_0.weight"].reshape(-1, 2)),
-                                f32(sd[f"all_modules.{i}.Conv_0.bias"]))
-                i += 1
-        self._pack_rb(i, top)
-        self.attn_idx = i + 1
-        self._pack_attn(i + 1)
-        self._pack_rb(i + 2, top)
-        i += 3
-        self.up_levels = []
-        for lvl in reversed(range(len(CH_MULT))):
-            blocks = [i, i + 1]
-            self._pack_rb(i, lvl)
-            self._pack_rb(i + 1, lvl)
-            i += 2
-            self._pack_head(i)
-            head = i
-            i += 2
-            upb = None
-            if lvl != 0:
-                if self.ddpm:
-                    self._pack_resample(i)
-                else:
-                    self._pack_rb(i, lvl - 1)   # `up` block: its convolutions run at the next (finer) level
-                upb = i
-                i += 1
-            self.up_levels.append((blocks, head, upb))
-        assert i == 36
+                if lvl != top:
+                    if self.ddpm:
+                        self._pack_resample(i)
+                    else:
+                        self._pack_rb(i, lvl + 1)   # `down` block: its convolutions run at the next (coarser) level
+                    i += 1
+                    self.comb[i] = (f32(sd[f"all_modules.{i}.Conv_0.weight"].reshape(-1, 2)),
+                                    f32(sd[f"all_modules.{i}.Conv_0.bias"]))
+                    i += 1
+            self._pack_rb(i, top)
+            self.attn_idx = i + 1
+            self._pack_attn(i + 1)
+            self._pack_rb(i + 2, top)
+            i += 3
+            self.up_levels = []
+            for lvl in reversed(range(len(CH_MULT))):
+                blocks = [i, i + 1]
+                self._pack_rb(i, lvl)
+                self._pack_rb(i + 1, lvl)
+                i += 2
+                self._pack_head(i)
+                head = i
+                i += 2
+                upb = None
+                if lvl != 0:
+                    if self.ddpm:
+                        self._pack_resample(i)
+                    else:
+                        self._pack_rb(i, lvl - 1)   # `up` block: its convolutions run at the next (finer) level
+                    upb = i
+                    i += 1
+                self.up_levels.append((blocks, head, upb))
+            assert i == 36
         ow = sd["output_layer.weight"].reshape(2, 2)
         self.out_m = [float(v) for v in ow.reshape(-1).tolist()]
         self.out_mT = [float(v) for v in ow.t().reshape(-1).tolist()]
@@ -212,7 +222,6 @@ class Engine:
         return fwd, dgr
 
     def _bwd_extra_x1(self, level, cin, cout):
-        import os
         pol = os.environ.get("BUDDY_X1_BWD", self.BWD_X1_POLICY)
         m = cin * cout / 4 ** level
         if pol == "E":
@@ -300,7 +309,7 @@ class Engine:
         sd, p = self.sd, f"all_modules.{i}."
         m = _RB()
         w = sd[p + "Conv_0.weight"]
-        m.c = w.shape[0]
+        m.cout, m.cin = w.shape[:2]
         m.w, m.wd = self._pack3x3(w)
         m.bias = sd[p + "Conv_0.bias"].contiguous()
         self.resamp[i] = m
@@ -452,24 +461,26 @@ class Engine:
         B, H, W, C = x.shape
         a = self._operand(B, H, W, C)
         ops.cast_operand(x, a.t16, a.t8, split=self.split)
-        full = torch.empty(B, H, W, C, device=self.device)
-        self._conv(a, m.w, full, taps=9, n_total=C, bias=m.bias)
+        full = torch.empty(B, H, W, m.cout, device=self.device)
+        self._conv(a, m.w, full, taps=9, n_total=m.cout, bias=m.bias)
         return upfirdn2d._launch(full, self._k1, (1, 1), (2, 2), (-1, 0, -1, 0))
 
-    def _down_bwd(self, i, d32, extra, consumer):
-        """d32 fp32 = gradient w.r.t. the module's output; returns the gradient w.r.t. its input (+ `extra`) in fp32
-        and as the fp16(/sqrt2) operand of the producing ResBlock."""
+    def _down_bwd(self, i, d32, extra, consumer, scale=1.0, want_g=True):
+        """d32 fp32 = gradient w.r.t. the module's output (times `scale`); returns the gradient w.r.t. its input
+        (+ `extra`) in fp32 and, want_g, as the fp16(/sqrt2) operand of the producing ResBlock."""
         m = self.resamp[i]
         B, h, w, C = d32.shape
         zs = upfirdn2d._launch(d32, self._k1, (2, 2), (1, 1), (1, -1, 1, -1))     # zero-stuffed: (2r+1, 2c+1) <- (r, c)
         op = self._operand(B, 2 * h, 2 * w, C, self._gscale(("dn", i)))
-        ops.cast_operand(zs, op.t16, op.t8, scale=op.gs, split=self.split)
+        ops.cast_operand(zs, op.t16, op.t8, scale=scale * op.gs, split=self.split)
         self._record(("dn", i), op)
         del zs
-        dx = torch.empty(B, 2 * h, 2 * w, C, device=self.device)
-        self._conv(op, m.wd, dx, taps=9, n_total=C)
+        dx = torch.empty(B, 2 * h, 2 * w, m.cin, device=self.device)
+        self._conv(op, m.wd, dx, taps=9, n_total=m.cin)
         if extra is not None:
             dx = self._add32(dx, extra)
+        if not want_g:
+            return dx, None
         g = self._operand(B, 2 * h, 2 * w, C, self._gscale(("dnx", i)), need8=not self._x1(consumer, 1))
         ops.cast_operand(dx, g.t16, g.t8, scale=INV_SQRT2 * g.gs, split=self.split)
         self._record(("dnx", i), g)
@@ -481,17 +492,17 @@ class Engine:
         B, H, W, C = x.shape
         a = self._operand(B, 2 * H, 2 * W, C)
         ops.cast_operand(x, a.t16, a.t8, upsample=True, split=self.split)
-        out = torch.empty(B, 2 * H, 2 * W, C, device=self.device)
-        so = self._zeros_stats(B, C)
-        self._conv(a, m.w, out, taps=9, n_total=C, bias=m.bias, stats=so)
+        out = torch.empty(B, 2 * H, 2 * W, m.cout, device=self.device)
+        so = self._zeros_stats(B, m.cout)
+        self._conv(a, m.w, out, taps=9, n_total=m.cout, bias=m.bias, stats=so)
         return out, so
 
     def _up_bwd(self, i, g16):
         """g16 = operand of the gradient w.r.t. the module's output (scale 1) -> fp32 gradient w.r.t. its input."""
         m = self.resamp[i]
         B, H2, W2, _ = g16.t16.shape
-        da = torch.empty(B, H2, W2, m.c, device=self.device)
-        self._conv(g16, m.wd, da, taps=9, n_total=m.c)
+        da = torch.empty(B, H2, W2, m.cin, device=self.device)
+        self._conv(g16, m.wd, da, taps=9, n_total=m.cin)
         return upfirdn2d._launch(da, self._k22, (1, 1), (2, 2), (0, 0, 0, 0))         # 2x2 sums
 
     # ------------------------------------------------------------------ attention
@@ -738,6 +749,9 @@ class Engine:
         assert spec.dtype == torch.float32 and spec.is_contiguous() and spec.shape[1] == 256 and spec.shape[3] == 2
         B, H, W, _ = spec.shape
         assert W % 16 == 0, "frame count must be a multiple of 16 (NCSNppTime.stft pads to it)"
+        if self.generic:
+            from . import engine_generic
+            return engine_generic.forward(self, spec, time_cond, save)
         dev = self.device
         ctx = {} if save else None
         tb = self.time_bias(time_cond)
@@ -798,6 +812,9 @@ class Engine:
 
     # ------------------------------------------------------------------ data-gradient
     def _vjp_impl(self, ctx, dout):
+        if self.generic:
+            from . import engine_generic
+            return engine_generic.vjp(self, ctx, dout)
         B, H, W = ctx["shape"]
         dev = self.device
         assert dout.shape == (B, H, W, 2) and dout.is_contiguous()

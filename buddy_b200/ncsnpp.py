@@ -55,30 +55,40 @@ class NCSNpp(nn.Module):
     def __init__(self, init_scale=0., fourier_scale=16, fir_kernel=(1, 3, 3, 1), precision=None, **kwargs):
         super().__init__()
         import os
-        self.precision = precision or os.environ.get("BUDDY_PRECISION", "mixed")
-        # resblock_type: "biggan" (shipped) or "ddpm" — ResnetBlockDDPMpp blocks (skip through a NIN) with separate
-        # Downsample / Upsample modules carrying a 3x3 convolution (layerspp.py:93-216); same module indices
+        # Variants of the graph (ncsnpp.py:127-150): resblock_type "biggan" (shipped) | "ddpm" (ResnetBlockDDPMpp blocks,
+        # skip through a NIN, separate Downsample / Upsample modules with a 3x3 convolution, layerspp.py:93-216);
+        # progressive "output_skip" (shipped) | "residual" | "none"; progressive_input "input_skip" (shipped) |
+        # "residual" | "none".  Module indices and state_dict keys follow the reference for every combination.
+        variants = dict(resblock_type=netspec.RESBLOCK_TYPES, progressive=netspec.PROGRESSIVE,
+                        progressive_input=netspec.PROGRESSIVE_INPUT)
         self.resblock_type = str(kwargs.get("resblock_type", "biggan")).lower()
+        self.progressive = str(kwargs.get("progressive", "output_skip")).lower()
+        self.progressive_input = str(kwargs.get("progressive_input", "input_skip")).lower()
         for k, v in kwargs.items():
             if k in _SUPPORTED:
                 want = _SUPPORTED[k]
                 got = tuple(v) if isinstance(want, tuple) else v
                 got = got.lower() if isinstance(got, str) else got
-                if k == "resblock_type" and got in ("biggan", "ddpm"):
+                if k in variants and got in variants[k]:
                     continue
                 if got != want:
                     raise NotImplementedError(
                         f"buddy_b200.NCSNpp implements the shipped BUDDy configuration only: {k}={v!r} (need {want!r})")
+        self.variant = (self.resblock_type, self.progressive, self.progressive_input)
+        gn_modules, scaled_convs = netspec.init_roles(*self.variant)
+        # the `mixed` single-pass policy is tuned (and measured) on the shipped progressive graph; the other progressive
+        # variants keep the e4m3 corrections on every convolution unless told otherwise
+        shipped = self.variant[1:] == ("output_skip", "input_skip")
+        self.precision = precision or os.environ.get("BUDDY_PRECISION", "mixed" if shipped else "fp16c8")
         self.time_conditional = True
         self.spatial_channels, self.input_channels = 1, 2
         self.FORCE_STFT_OUT = False
-        for key, shape in netspec.param_spec(self.resblock_type):
+        for key, shape in netspec.param_spec(*self.variant):
             leaf = key.split(".")[-1]
             owner = key.split(".")[-2]
             if key == "all_modules.0.W":
                 t = torch.randn(shape) * fourier_scale
-            elif "GroupNorm" in key or (owner.isdigit() and len(shape) == 1 and leaf in ("weight", "bias")
-                                        and int(owner) in (19, 24, 29, 34)):
+            elif "GroupNorm" in key or (owner.isdigit() and int(owner) in gn_modules):
                 t = torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
             elif leaf in ("bias", "b"):
                 t = torch.zeros(shape)
@@ -89,7 +99,7 @@ class NCSNpp(nn.Module):
                 t = _default_init((shape[1], shape[0]), sc).t().contiguous()
             else:
                 sc = 1.0
-                if owner == "Conv_1" or (owner.isdigit() and int(owner) in (20, 25, 30, 35)):
+                if owner == "Conv_1" or (owner.isdigit() and int(owner) in scaled_convs):
                     sc = init_scale
                 t = _default_init(shape, sc)
             _assign(self, key, t)
@@ -108,8 +118,8 @@ class NCSNpp(nn.Module):
                                "(there is no CPU fallback)")
         key = (str(dev), self.precision, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
         if self._engine is None or key != self._engine_key:
-            self._engine = Engine(self.state_dict(), dev, precision=self.precision,
-                                  resblock_type=self.resblock_type)
+            self._engine = Engine(self.state_dict(), dev, precision=self.precision, resblock_type=self.resblock_type,
+                                  progressive=self.progressive, progressive_input=self.progressive_input)
             self._engine_key = key
         return self._engine
 

@@ -159,31 +159,73 @@ def test_api_operator_classes_match_reference(rh):
         bop.project_params()
 
 
-def test_ddpm_resblock_variant_vs_reference_network(rh):
-    """`resblock_type: ddpm` (ResnetBlockDDPMpp + Downsample / Upsample with a 3x3 convolution, layerspp.py:93-216):
-    the reference network built with that option, trained-like weights in ITS state_dict layout loaded into ours,
-    forward and data-gradient through the time-domain wrapper against the reference on this GPU (fp32, TF32 off)."""
+def _variant_pair(rh, seed, **variant):
+    """(reference network, ours) for one NCSN++ variant, trained-like weights drawn in the REFERENCE module's layout."""
     from buddy_b200.ncsnpp import NCSNppTime
     from oracle.weights import make_state_dict
-    ref_net = rh.build_network(resblock_type="ddpm")
+    ref_net = rh.build_network(**variant)
     spec = [(k, tuple(v.shape)) for k, v in ref_net.state_dict().items()]
-    assert len(spec) == 211 and any(k.endswith("NIN_0.W") for k, _ in spec)
-    ref_net.load_state_dict(make_state_dict(3, spec=spec))
+    ref_net.load_state_dict(make_state_dict(seed, spec=spec))
     ref_net = ref_net.cuda()
-    ours = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2],
-                      resblock_type="ddpm")
-    ours.load_state_dict(ref_net.state_dict())
-    ours = ours.cuda().eval()
-    B = 2
-    x = (randn(400, B, 1, 16384) * 0.05).cuda()
-    tc = torch.tensor([0.25 * math.log(0.3), 0.25 * math.log(0.02)], device="cuda")
-    cot = randn(401, B, 1, 16384).cuda()
+    ours = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2], **variant)
+    ours.load_state_dict(ref_net.state_dict())          # the reference module's own state_dict loads as is
+    return ref_net, ours.cuda().eval(), spec
+
+
+def _fwd_vjp_errors(ref_net, ours, B=2, n=16384, seed=400):
+    x = (randn(seed, B, 1, n) * 0.05).cuda()
+    tc = torch.tensor([0.25 * math.log(0.3), 0.25 * math.log(0.02)], device="cuda")[:B]
+    cot = randn(seed + 1, B, 1, n).cuda()
     xr = x.clone().requires_grad_(True)
     want = ref_net(xr, tc)
     (gw,) = torch.autograd.grad((want * cot).sum(), xr)
     xo = x.clone().requires_grad_(True)
     got = ours(xo, tc)
     (gg,) = torch.autograd.grad((got * cot).sum(), xo)
-    ef, eb = rel(got, want.detach()), rel(gg, gw)
+    return rel(got, want.detach()), rel(gg, gw)
+
+
+def test_ddpm_resblock_variant_vs_reference_network(rh):
+    """`resblock_type: ddpm` (ResnetBlockDDPMpp + Downsample / Upsample with a 3x3 convolution, layerspp.py:93-216):
+    the reference network built with that option, trained-like weights in ITS state_dict layout loaded into ours,
+    forward and data-gradient through the time-domain wrapper against the reference on this GPU (fp32, TF32 off)."""
+    ref_net, ours, spec = _variant_pair(rh, 3, resblock_type="ddpm")
+    assert len(spec) == 211 and any(k.endswith("NIN_0.W") for k, _ in spec)
+    ef, eb = _fwd_vjp_errors(ref_net, ours)
     print(f"\n[ddpm variant vs the reference network] forward {ef:.2e}  data-gradient {eb:.2e}")
     assert ef < TOL and eb < TOL
+
+
+@pytest.mark.parametrize("variant", [
+    dict(progressive="residual", progressive_input="residual"),
+    dict(progressive="none", progressive_input="none"),
+    dict(progressive="residual", progressive_input="input_skip", resblock_type="ddpm"),
+    dict(progressive="output_skip", progressive_input="residual", resblock_type="ddpm"),
+    dict(progressive="none", progressive_input="residual"),
+], ids=lambda v: "-".join(f"{k[:8]}={x}" for k, x in v.items()))
+def test_progressive_variants_vs_reference_network(rh, variant):
+    """`progressive` / `progressive_input` variants of NCSN++ (ncsnpp.py:127-150, 196-274, 340-445) on the general module
+    walk (buddy_b200/engine_generic.py): forward and data-gradient against the reference network built with the same
+    options, on this GPU."""
+    ref_net, ours, _ = _variant_pair(rh, 4, **variant)
+    ef, eb = _fwd_vjp_errors(ref_net, ours)
+    print(f"\n[{variant}] forward {ef:.2e}  data-gradient {eb:.2e}")
+    assert ef < TOL and eb < TOL
+
+
+def test_general_walk_matches_scheduled_walk_on_shipped_graph(rh, nets, monkeypatch):
+    """The shipped graph through engine_generic's tape (BUDDY_GENERIC_WALK=1) against the hand-scheduled walk of
+    engine.py: same kernels, fp32 gradients between the modules instead of fp16 operands — equal to rounding."""
+    from buddy_b200.ncsnpp import NCSNppTime
+    ref_net, fast = nets
+    assert not fast.engine().generic
+    monkeypatch.setenv("BUDDY_GENERIC_WALK", "1")
+    slow = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    slow.load_state_dict(ref_net.state_dict())
+    slow = slow.cuda().eval()
+    assert slow.engine().generic
+    ef, eb = _fwd_vjp_errors(fast, slow)
+    ef_ref, eb_ref = _fwd_vjp_errors(ref_net, slow)
+    print(f"\n[general vs scheduled walk, shipped graph] forward {ef:.2e} data-gradient {eb:.2e}; "
+          f"general walk vs reference {ef_ref:.2e} / {eb_ref:.2e}")
+    assert ef < 1e-6 and eb < 5e-4 and ef_ref < TOL and eb_ref < TOL
