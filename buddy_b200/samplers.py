@@ -58,11 +58,23 @@ class Sampler:
         self.use_graphs = True            # replay captured CUDA graphs of the network forward / VJP for small batches
         self._draw = 0
 
+    ACT_BYTES_PER_SAMPLE = 1.9e9 / 65536    # saved activations of one network evaluation, per audio sample
+
     def _for_micro_batches(self, B, body):
         """Run body(slice) for every micro-batch, round-robin over `n_streams` CUDA streams forked from / joined
         to the current stream.  Micro-batches touch disjoint utterances, so the order of execution is free."""
         slices = [slice(s, min(B, s + self.micro_batch)) for s in range(0, B, self.micro_batch)]
         ns = min(self.n_streams, len(slices))
+        if ns > 1:
+            # every micro-batch in flight keeps its saved activations (1.9 GB per 4.096 s utterance); past the device's
+            # memory the caching allocator falls back to synchronous cudaFree / cudaMalloc retries and the run crawls
+            # (seen on B200 with 2 x 32 utterances in the blind configuration) — refuse instead
+            n = getattr(self, "y", None).shape[1] if getattr(self, "y", None) is not None else 65536
+            need = ns * min(self.micro_batch, B) * self.ACT_BYTES_PER_SAMPLE * n
+            total = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
+            if need > 0.6 * total:
+                raise ValueError(f"n_streams={ns} x micro_batch={self.micro_batch} needs ~{need / 2**30:.0f} GiB of saved "
+                                 f"activations ({total / 2**30:.0f} GiB on this device): lower micro_batch or n_streams")
         if ns <= 1:
             for sl in slices:
                 body(sl)
