@@ -7,16 +7,21 @@ result (per-utterance GroupNorm statistics, norms, noise streams; see samplers.p
 cannot be padded into one batch exactly — GroupNorm statistics and the attention span the whole spectrogram — so the
 front-end buckets by exact length and runs each bucket in chunks of `max_batch`.
 
-`BatchedDereverb.informed / .blind` take and return tensors; `AsyncWavWriter` is the I/O half
+`BatchedDereverb.informed / .blind` take and return tensors; `AsyncWavWriter` is the output half of the I/O
 (`utils/log.py:90-110 write_audio_file`, five synchronous wav writes per utterance in the reference loop): device ->
 pinned host copies on a side stream and the file writes on worker threads, so that writing utterance i overlaps the
-sampling of the next batch.
+sampling of the next batch.  `read_wav` / `PairedWavSet` are the input half (`datasets/vctk.py:148-226`
+`VCTKTestPaired`: clean/<speaker>/<id>.wav paired with rir/<speaker>/<id>.wav, RIR cropped at its direct path and
+peak-normalised) with the files decoded on worker threads, and `BatchedDereverb.test_dereverberation` is the loop of
+tester.py:123-163 over such a set, writing the reference's directory layout (tester.py:167-203).
 """
+import glob
 import os
 import struct
 import threading
 from concurrent.futures import ThreadPoolExecutor
 
+import numpy as np
 import torch
 
 from .operators import RIROperator
@@ -83,6 +88,83 @@ class AsyncWavWriter:
         return [f.result() for f in fs]
 
 
+def read_wav(path):
+    """(float32 tensor [frames] or [frames, channels] in [-1, 1), sample rate) of a RIFF/WAVE file: PCM 8/16/24/32-bit
+    or IEEE float 32/64, plain or WAVE_FORMAT_EXTENSIBLE (soundfile's `sf.read` on the files the reference uses)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if len(raw) < 12 or raw[:4] != b"RIFF" or raw[8:12] != b"WAVE":
+        raise ValueError(f"{path}: not a RIFF/WAVE file")
+    pos, fmt, data = 12, None, None
+    while pos + 8 <= len(raw):
+        cid, size = raw[pos:pos + 4], struct.unpack("<I", raw[pos + 4:pos + 8])[0]
+        body = raw[pos + 8:pos + 8 + size]
+        if cid == b"fmt ":
+            tag, ch, sr, _, _, bits = struct.unpack("<HHIIHH", body[:16])
+            if tag == 0xFFFE and len(body) >= 26:           # extensible: the sub-format GUID starts with the real tag
+                tag = struct.unpack("<H", body[24:26])[0]
+            fmt = (tag, ch, sr, bits)
+        elif cid == b"data":
+            data = body
+        pos += 8 + size + (size & 1)
+    if fmt is None or data is None:
+        raise ValueError(f"{path}: missing fmt or data chunk")
+    tag, ch, sr, bits = fmt
+    if tag == 3 and bits in (32, 64):
+        x = np.frombuffer(data, dtype="<f4" if bits == 32 else "<f8").astype(np.float32)
+    elif tag == 1 and bits == 16:
+        x = np.frombuffer(data, dtype="<i2").astype(np.float32) / 32768.0
+    elif tag == 1 and bits == 32:
+        x = (np.frombuffer(data, dtype="<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
+    elif tag == 1 and bits == 24:
+        b = np.frombuffer(data[:len(data) // 3 * 3], dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        x = ((v ^ 0x800000) - 0x800000).astype(np.float32) / 8388608.0
+    elif tag == 1 and bits == 8:
+        x = (np.frombuffer(data, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+    else:
+        raise ValueError(f"{path}: unsupported WAVE format tag {tag}, {bits} bits")
+    x = x[:len(x) // ch * ch]
+    t = torch.from_numpy(np.ascontiguousarray(x))
+    return (t if ch == 1 else t.view(-1, ch)), int(sr)
+
+
+class PairedWavSet:
+    """datasets/vctk.py:148-226 (`VCTKTestPaired`): every clean/<speaker>/<id>.wav of the test speakers with its
+    rir/<speaker>/<id>.wav.  Items are (clean float32 [n], rir float32 [m], file name); the RIR starts at its direct
+    path (arg-max of |h|) and is divided by its peak (:213-216).  Files are decoded on `workers` threads ahead of use."""
+
+    def __init__(self, path, speakers_test=None, speakers_discard=(), fs=16000, num_examples=-1, workers=4):
+        self.fs = int(fs)
+        self.samples, self.rirs = [], []
+        for spk in sorted(os.listdir(os.path.join(path, "clean"))):
+            if spk in speakers_discard or (speakers_test is not None and spk not in speakers_test):
+                continue
+            for f in sorted(glob.glob(os.path.join(path, "clean", spk, "*.wav"))):
+                self.samples.append(f)
+                self.rirs.append(os.path.join(path, "rir", spk, os.path.basename(f)))
+        if num_examples > 0:
+            assert len(self.samples) >= num_examples, "error in dataloading: not enough examples"
+            self.samples, self.rirs = self.samples[:num_examples], self.rirs[:num_examples]
+        self.filenames = [os.path.basename(f) for f in self.samples]
+        self._pool = ThreadPoolExecutor(max_workers=workers)
+        self._items = [self._pool.submit(self._load, i) for i in range(len(self.samples))]
+
+    def _load(self, i):
+        x, sr = read_wav(self.samples[i])
+        h, sr_h = read_wav(self.rirs[i])
+        assert sr == self.fs and sr_h == self.fs, "wrong sampling rate"
+        assert x.dim() == 1 and h.dim() == 1, "wrong number of channels"
+        h = h[int(h.abs().argmax()):]
+        return x, h / h.abs().max(), self.filenames[i]
+
+    def __len__(self):
+        return len(self.samples)
+
+    def __getitem__(self, i):
+        return self._items[i].result()
+
+
 def length_buckets(lengths, max_batch):
     """[(indices)] — indices grouped by equal length (first-seen order), each group split into chunks <= max_batch."""
     groups = {}
@@ -138,6 +220,42 @@ class BatchedDereverb:
         self.sampler.utterance_ids = None
         self.sampler.seed_base = restore
         return preds
+
+    def test_dereverberation(self, test_set, out_dir, mode="informed_dereverberation", blind=False, device="cuda",
+                             writer=None):
+        """tester.py:123-163 over a whole test set: scale every utterance to sigma_data, reverberate it with its RIR,
+        reconstruct (informed: with the true RIR; blind: operator estimated along the way), and write
+        <out_dir>/{original, degraded, reconstructed, true_rir[, estimated_rir]}/<name>.wav (tester.py:167-203) through an
+        `AsyncWavWriter`.  Returns the list of reconstructed-file paths in set order."""
+        sr = self.sampler.args.exp.sample_rate
+        own = writer is None
+        writer = AsyncWavWriter() if own else writer
+        items = [test_set[i] for i in range(len(test_set))]
+        segs, ys, rirs = [], [], []
+        for x, h, _ in items:
+            seg, y = self.observe(torch.as_tensor(x).to(device), torch.as_tensor(h).to(device))
+            segs.append(seg)
+            ys.append(y)
+            rirs.append(torch.as_tensor(h).to(device))
+        sub = lambda k: os.path.join(out_dir, k)
+        for (x, h, name), seg, y in zip(items, segs, ys):
+            stem = os.path.basename(name)[:-4]
+            writer.write(seg, sr, stem, sub("original"))
+            writer.write(y, sr, stem, sub("degraded"))
+            writer.write(torch.as_tensor(h), sr, stem, sub("true_rir"))
+        if blind:
+            preds, est = self.blind(ys)
+        else:
+            preds, est = self.informed(ys, rirs), None
+        paths = []
+        for k, (_, _, name) in enumerate(items):
+            stem = os.path.basename(name)[:-4]
+            paths.append(writer.write(preds[k], sr, stem, sub("reconstructed")))
+            if blind:
+                writer.write(est[k], sr, stem, sub("estimated_rir"))
+        if own:
+            writer.close()
+        return paths
 
     def init_blind_operator(self, B, device, generator=None):
         """The state tester.py:147-151 builds per utterance — `BlindSubbandFiltering(op_hp)` then

@@ -158,6 +158,54 @@ def test_factored_stft_matrices_equal_the_dft_matrices():
         assert (got - want).abs().max().item() < 1e-7 * want.abs().max().item()
 
 
+def test_wav_reader_and_paired_set(tmp_path):
+    """Input half of the tester front-end: `read_wav` against scipy's reader on every sample format, and
+    `PairedWavSet` (datasets/vctk.py:148-226: clean/<spk>/<id>.wav + rir/<spk>/<id>.wav, RIR cropped at its direct
+    path and peak-normalised)."""
+    import numpy as np
+    from scipy.io import wavfile
+    from buddy_b200.tester import AsyncWavWriter, PairedWavSet, read_wav
+    rs = np.random.RandomState(0)
+    x = np.clip(rs.randn(3001) * 0.2, -0.99, 0.99).astype(np.float32)
+    cases = dict(f32=x, f64=x.astype(np.float64), i16=(x * 32767).astype(np.int16),
+                 i32=(x.astype(np.float64) * 2147483647).astype(np.int32), u8=(x * 127 + 128).astype(np.uint8))
+    for name, arr in cases.items():
+        p = str(tmp_path / (name + ".wav"))
+        wavfile.write(p, 16000, arr)
+        y, sr = read_wav(p)
+        sr2, z = wavfile.read(p)
+        z = {"i16": lambda a: a / 32768.0, "i32": lambda a: a / 2147483648.0,
+             "u8": lambda a: (a.astype(np.float32) - 128.0) / 128.0}.get(name, lambda a: a)(z)
+        assert sr == sr2 == 16000 and y.dtype == torch.float32 and np.abs(y.numpy() - z).max() < 1e-7, name
+    # 24-bit PCM and two channels, written by hand
+    v = (x[:100].astype(np.float64) * 8388607).astype(np.int32)
+    b = np.stack([v & 255, (v >> 8) & 255, (v >> 16) & 255], 1).astype(np.uint8).tobytes()
+    hdr = b"RIFF" + (36 + len(b)).to_bytes(4, "little") + b"WAVEfmt " + (16).to_bytes(4, "little") \
+        + (1).to_bytes(2, "little") + (2).to_bytes(2, "little") + (8000).to_bytes(4, "little") \
+        + (8000 * 6).to_bytes(4, "little") + (6).to_bytes(2, "little") + (24).to_bytes(2, "little") + b"data" \
+        + len(b).to_bytes(4, "little")
+    (tmp_path / "s24.wav").write_bytes(hdr + b)
+    y, sr = read_wav(str(tmp_path / "s24.wav"))
+    assert sr == 8000 and y.shape == (50, 2) and np.abs(y.numpy().ravel() - v / 8388608.0).max() < 1e-7
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.wav").write_bytes(b"not a wave file at all")
+        read_wav(str(tmp_path / "bad.wav"))
+    # paired set in the reference's directory layout (written with our own writer: float32 files)
+    w = AsyncWavWriter(pcm16=False)
+    h = np.zeros(500, np.float32)
+    h[37], h[60], h[200] = -0.5, 0.2, 0.1
+    for spk, uid in (("p1", "p1_001"), ("p1", "p1_002"), ("p2", "p2_001")):
+        w.write(torch.from_numpy(x), 16000, uid, str(tmp_path / "set" / "clean" / spk))
+        w.write(torch.from_numpy(h), 16000, uid, str(tmp_path / "set" / "rir" / spk))
+    w.close()
+    ds = PairedWavSet(str(tmp_path / "set"), speakers_test=["p1"])
+    assert len(ds) == 2 and ds.filenames == ["p1_001.wav", "p1_002.wav"]
+    c, r, name = ds[1]
+    assert name == "p1_002.wav" and torch.equal(c, torch.from_numpy(x))
+    assert r.shape == (463,) and r[0] == -1.0 and abs(float(r[23]) - 0.4) < 1e-7      # cropped at |h| max, / peak
+    assert len(PairedWavSet(str(tmp_path / "set"))) == 3
+
+
 def test_async_wav_writer_roundtrip(tmp_path):
     """I/O half of the tester front-end (reference utils/log.py:90-110): 16-bit PCM mono files, written off-thread."""
     import wave
