@@ -16,6 +16,14 @@ import torch
 from . import ops
 from .spectral import LossSTFT, _dft_mats, _use_fft, irfft_weights
 
+LOSS_NORMS = {"l2_comp_stft_summean": "summean", "l2_comp_stft_sum": "sum", "l2_comp_stft_mean": "mean"}
+
+
+def loss_norm(norm, bins, frames):
+    """Factor on `weight` for the compressed-STFT loss variants of utils/losses.py:48-67, relative to the kernel's
+    built-in mean over frames of the sum over bins (`summean`): plain sum / mean over all bins and frames."""
+    return {"summean": 1.0, "sum": float(frames), "mean": 1.0 / bins}[norm]
+
 EQ_FREQS = [0, 125, 250, 375, 500, 625, 750, 875, 1000, 1250, 1500, 1750, 2000, 2250, 2500, 2750, 3000, 3500, 4000,
             4500, 5000, 5500, 6000, 6500, 7000, 7500, 8000]
 
@@ -236,7 +244,7 @@ class BlindEngine:
         H = self.state["H"] if H is None else H
         return self.degradation_from_stft(self.buf["Xd"][:H.shape[0]], H, self.RIR_LEN)
 
-    def likelihood_grad(self, x_den, Y, weight, comp):
+    def likelihood_grad(self, x_den, Y, weight, comp, norm="summean"):
         """rec = loss(y, A_H(x_den)) per utterance and d rec / d x_den, with the current (detached) H."""
         n = x_den.shape[1]
         B = x_den.shape[0]
@@ -246,7 +254,7 @@ class BlindEngine:
         Yh = self.loss_stft.forward(y_hat)
         loss = torch.empty(B, device=self.device, dtype=torch.float64)
         G = torch.empty_like(Yh)
-        ops.comp_loss(Y, Yh, Yh.shape[2], comp, weight, loss, G)
+        ops.comp_loss(Y, Yh, Yh.shape[2], comp, weight * loss_norm(norm, Yh.shape[1], Yh.shape[2]), loss, G)
         gYs = self.apply_istft_adjoint(self.loss_stft.adjoint(G, n))
         gX = ops.subband_fir(gYs, H, torch.empty_like(gYs), Nf=self.NF, pre=1, mode=1)
         return self.loss_stft.adjoint(gX, n), loss
@@ -266,7 +274,8 @@ class BlindEngine:
             Yh = self.loss_stft.forward(y_hat)
             loss = torch.empty(B, device=dev, dtype=torch.float64)
             G = torch.empty_like(Yh)
-            ops.comp_loss(Y, Yh, Yh.shape[2], hp["comp"], hp["w_rec"], loss, G)
+            ops.comp_loss(Y, Yh, Yh.shape[2], hp["comp"],
+                          hp["w_rec"] * loss_norm(hp.get("norm_rec", "summean"), Yh.shape[1], Yh.shape[2]), loss, G)
             gYs = self.apply_istft_adjoint(self.loss_stft.adjoint(G, n))
             dH = torch.empty_like(H)
             ops.subband_fir(X, gYs, dH, Nf=self.NF, pre=1, mode=2)
@@ -278,7 +287,8 @@ class BlindEngine:
             R, Rt = self.loss_stft.forward(rir), self.loss_stft.forward(noisy)
             lreg = torch.empty(B, device=dev, dtype=torch.float64)
             Gr = torch.empty_like(R)
-            ops.comp_loss(Rt, R, R.shape[2], hp["comp"], hp["w_reg"], lreg, Gr)
+            ops.comp_loss(Rt, R, R.shape[2], hp.get("comp_reg", hp["comp"]),
+                          hp["w_reg"] * loss_norm(hp.get("norm_reg", "summean"), R.shape[1], R.shape[2]), lreg, Gr)
             gYd = self.apply_istft_adjoint(self.loss_stft.adjoint(Gr, self.RIR_LEN))
             ops.subband_fir(Xd, gYd, dH, Nf=self.NF, pre=1, mode=2, accumulate=True)
             dd, dw, dph = self.update_H_backward(dH)

@@ -329,8 +329,11 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
         ps = self.args.tester.posterior_sampling
         self._loss_w = float(ps.rec_loss.weight)
         self._loss_c = float(ps.rec_loss.compression_factor)
-        if ps.rec_loss.name != "l2_comp_stft_summean":
-            raise NotImplementedError(f"rec_loss {ps.rec_loss.name}: only l2_comp_stft_summean is on the hot path")
+        from .blind import LOSS_NORMS
+        if ps.rec_loss.name not in LOSS_NORMS:
+            raise NotImplementedError(f"rec_loss {ps.rec_loss.name}: the compressed-STFT losses {sorted(LOSS_NORMS)} "
+                                      "are on the hot path (utils/losses.py:48-67)")
+        self._loss_norm = LOSS_NORMS[ps.rec_loss.name]
         self._Y = self._loss_stft.forward(y)
         self._is_blind = bool(blind)          # operator parameters are optimised along the trajectory
         self._subband = bool(blind)           # the likelihood goes through the sub-band (STFT-domain) operator
@@ -339,8 +342,8 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
             from .blind import BlindEngine
             hp = ps.blind_hp
             rp, reg = ps.rec_loss_params, ps.RIR_noise_regularization
-            if rp.name != "l2_comp_stft_summean" or reg.loss.name != "l2_comp_stft_summean":
-                raise NotImplementedError("blind path: only l2_comp_stft_summean losses are on the hot path")
+            if rp.name not in LOSS_NORMS or reg.loss.name not in LOSS_NORMS:
+                raise NotImplementedError(f"blind path: the compressed-STFT losses {sorted(LOSS_NORMS)} are on the hot path")
             self._blind = BlindEngine(n, dev, op_hp=getattr(operator, "op_hp", None),
                                       sample_rate=self.args.exp.sample_rate)
             self._blind.init_state(y.shape[0], operator.params[0], operator.params[1], operator.params_phases[0],
@@ -348,7 +351,9 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
             self._blind_hp = dict(iters=int(hp.op_updates_per_step), lr=float(hp.lr_op), beta1=float(hp.beta1),
                                   beta2=float(hp.beta2), comp=float(rp.compression_factor), w_rec=float(rp.weight),
                                   w_reg=float(reg.loss.weight), crop_max=float(reg.crop_sigma_max),
-                                  crop_min=float(reg.crop_sigma_min))
+                                  crop_min=float(reg.crop_sigma_min), norm_rec=LOSS_NORMS[rp.name],
+                                  norm_reg=LOSS_NORMS[reg.loss.name],
+                                  comp_reg=float(_get(reg.loss, "compression_factor", rp.compression_factor)))
             return
         rir = getattr(operator, "params", None)
         H = getattr(operator, "H", None)
@@ -381,13 +386,15 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
         if self._subband:
             if not self._is_blind:
                 self._blind.select(slice(first, first + B))
-            gd, loss = self._blind.likelihood_grad(x_den, Y, self._loss_w, self._loss_c)
+            gd, loss = self._blind.likelihood_grad(x_den, Y, self._loss_w, self._loss_c, self._loss_norm)
         else:
             y_hat = self._rir.forward(x_den, first)
             Yh = self._loss_stft.forward(y_hat)
             loss = torch.empty(B, device=dev, dtype=torch.float64)
             G = torch.empty_like(Yh)
-            ops.comp_loss(Y, Yh, Yh.shape[2], self._loss_c, self._loss_w, loss, G)
+            from .blind import loss_norm
+            ops.comp_loss(Y, Yh, Yh.shape[2], self._loss_c,
+                          self._loss_w * loss_norm(self._loss_norm, Yh.shape[1], Yh.shape[2]), loss, G)
             gd = self._rir.adjoint(self._loss_stft.adjoint(G, n), first)    # d loss / d x_den
         dspec = eng.vjp(ctx, st.inverse_adjoint(gd))
         v = st.forward_adjoint(dspec, n, scale_b=_vec(cin * cout, B, dev))

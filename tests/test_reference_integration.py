@@ -79,6 +79,41 @@ def test_informed_with_reference_operator_and_edm(rh, nets):
     assert e < TOL
 
 
+@pytest.mark.parametrize("name", ["l2_comp_stft_sum", "l2_comp_stft_mean"])
+def test_compressed_stft_loss_variants(rh, nets, name):
+    """The `sum` / `mean` normalisations of the compressed-STFT loss (utils/losses.py:48-60) next to the shipped
+    `summean`: informed trajectory against the reference sampler configured the same way, and the loss value of the
+    kernel against the reference's `get_loss` on the same pair of signals."""
+    from buddy_b200 import ops
+    from buddy_b200.blind import LOSS_NORMS, loss_norm
+    from buddy_b200.samplers import EulerHeunSamplerDPS as Ours
+    from testing.EulerHeunSamplerDPS import EulerHeunSamplerDPS as Ref
+    from utils.losses import get_loss
+    ref_net, our_net = nets
+    T = 2
+    op, y = _observation(rh, 500)
+    noise = [randn(510 + i, 1, NS) for i in range(T + 1)]
+    edm = rh.build_edm()
+    args = rh.make_args("informed", T)
+    args.tester.posterior_sampling.rec_loss["name"] = name
+    with rh.injected_noise(noise):
+        want = Ref(ref_net, edm, args).predict_conditional(y, op, shape=(1, NS), blind=False)
+    smp = Ours(our_net, edm, args)
+    smp.noise_source = iter(noise)
+    got = smp.predict_conditional(y, op, shape=(1, NS), blind=False)
+    assert rel(got, want) < TOL
+    with torch.no_grad():
+        y_hat = op.degradation(got)
+        want_loss = float(get_loss(args.tester.posterior_sampling.rec_loss, operator=op)(y, y_hat))
+    Y, Yh = smp._loss_stft.forward(y.contiguous()), smp._loss_stft.forward(y_hat.contiguous())
+    loss = torch.empty(1, device="cuda", dtype=torch.float64)
+    rl = args.tester.posterior_sampling.rec_loss
+    ops.comp_loss(Y, Yh, Yh.shape[2], float(rl.compression_factor),
+                  float(rl.weight) * loss_norm(LOSS_NORMS[name], Yh.shape[1], Yh.shape[2]), loss, torch.empty_like(Yh))
+    print(f"\n[{name}] trajectory {rel(got, want):.2e}; loss {float(loss):.6g} vs reference {want_loss:.6g}")
+    assert abs(float(loss) - want_loss) < 1e-4 * abs(want_loss)
+
+
 def test_blind_with_reference_operator_object(rh, nets):
     """tester.py:147-161: BlindSubbandFiltering object in, estimated filter written back, `get_time_RIR()` afterwards."""
     from buddy_b200.samplers import EulerHeunSamplerDPS as Ours
