@@ -269,28 +269,31 @@ class BlindEngine:
         t_op = max(min(float(t_hat), hp["crop_max"]), hp["crop_min"])
         for _ in range(hp["iters"]):
             H = self.update_H()
-            # reconstruction loss
-            y_hat = self.degradation_from_stft(X, H, n)
-            Yh = self.loss_stft.forward(y_hat)
-            loss = torch.empty(B, device=dev, dtype=torch.float64)
-            G = torch.empty_like(Yh)
-            ops.comp_loss(Y, Yh, Yh.shape[2], hp["comp"],
-                          hp["w_rec"] * loss_norm(hp.get("norm_rec", "summean"), Yh.shape[1], Yh.shape[2]), loss, G)
-            gYs = self.apply_istft_adjoint(self.loss_stft.adjoint(G, n))
-            dH = torch.empty_like(H)
-            ops.subband_fir(X, gYs, dH, Nf=self.NF, pre=1, mode=2)
-            # RIR-noise regulariser: loss(rir, (rir + t_op * noise).detach())
-            Xd = self.buf["Xd"]
-            rir = self.degradation_from_stft(Xd, H, self.RIR_LEN)
-            noisy = ops.lincomb3(torch.empty_like(rir), rir, torch.ones(B, device=dev), noise_fn((B, self.RIR_LEN)),
-                                 torch.full((B,), t_op, device=dev))
-            R, Rt = self.loss_stft.forward(rir), self.loss_stft.forward(noisy)
-            lreg = torch.empty(B, device=dev, dtype=torch.float64)
-            Gr = torch.empty_like(R)
-            ops.comp_loss(Rt, R, R.shape[2], hp.get("comp_reg", hp["comp"]),
-                          hp["w_reg"] * loss_norm(hp.get("norm_reg", "summean"), R.shape[1], R.shape[2]), lreg, Gr)
-            gYd = self.apply_istft_adjoint(self.loss_stft.adjoint(Gr, self.RIR_LEN))
-            ops.subband_fir(Xd, gYd, dH, Nf=self.NF, pre=1, mode=2, accumulate=True)
+            dH = torch.empty_like(H) if hp.get("use_rec", True) else torch.zeros_like(H)
+            loss = lreg = None
+            if hp.get("use_rec", True):
+                # reconstruction loss
+                y_hat = self.degradation_from_stft(X, H, n)
+                Yh = self.loss_stft.forward(y_hat)
+                loss = torch.empty(B, device=dev, dtype=torch.float64)
+                G = torch.empty_like(Yh)
+                ops.comp_loss(Y, Yh, Yh.shape[2], hp["comp"],
+                              hp["w_rec"] * loss_norm(hp.get("norm_rec", "summean"), Yh.shape[1], Yh.shape[2]), loss, G)
+                gYs = self.apply_istft_adjoint(self.loss_stft.adjoint(G, n))
+                ops.subband_fir(X, gYs, dH, Nf=self.NF, pre=1, mode=2)
+            if hp.get("use_reg", True):
+                # RIR-noise regulariser: loss(rir, (rir + t_op * noise).detach())
+                Xd = self.buf["Xd"]
+                rir = self.degradation_from_stft(Xd, H, self.RIR_LEN)
+                noisy = ops.lincomb3(torch.empty_like(rir), rir, torch.ones(B, device=dev),
+                                     noise_fn((B, self.RIR_LEN)), torch.full((B,), t_op, device=dev))
+                R, Rt = self.loss_stft.forward(rir), self.loss_stft.forward(noisy)
+                lreg = torch.empty(B, device=dev, dtype=torch.float64)
+                Gr = torch.empty_like(R)
+                ops.comp_loss(Rt, R, R.shape[2], hp.get("comp_reg", hp["comp"]),
+                              hp["w_reg"] * loss_norm(hp.get("norm_reg", "summean"), R.shape[1], R.shape[2]), lreg, Gr)
+                gYd = self.apply_istft_adjoint(self.loss_stft.adjoint(Gr, self.RIR_LEN))
+                ops.subband_fir(Xd, gYd, dH, Nf=self.NF, pre=1, mode=2, accumulate=True)
             dd, dw, dph = self.update_H_backward(dH)
             self.steps[st["key"]] += 1
             step = self.steps[st["key"]]

@@ -342,18 +342,23 @@ class EulerHeunSamplerDPS(EulerHeunSampler):
             from .blind import BlindEngine
             hp = ps.blind_hp
             rp, reg = ps.rec_loss_params, ps.RIR_noise_regularization
-            if rp.name not in LOSS_NORMS or reg.loss.name not in LOSS_NORMS:
-                raise NotImplementedError(f"blind path: the compressed-STFT losses {sorted(LOSS_NORMS)} are on the hot path")
+            # utils/losses.py:19-20: name "none" switches a term off (EulerHeunSamplerDPS.py:87-104)
+            names = (rp.name, reg.loss.name)
+            if any(nm != "none" and nm not in LOSS_NORMS for nm in names) or names == ("none", "none"):
+                raise NotImplementedError(f"blind path: losses {names}: the compressed-STFT losses {sorted(LOSS_NORMS)} "
+                                          "(or 'none' for one of the two terms) are on the hot path")
             self._blind = BlindEngine(n, dev, op_hp=getattr(operator, "op_hp", None),
                                       sample_rate=self.args.exp.sample_rate)
             self._blind.init_state(y.shape[0], operator.params[0], operator.params[1], operator.params_phases[0],
                                    operator.H)
             self._blind_hp = dict(iters=int(hp.op_updates_per_step), lr=float(hp.lr_op), beta1=float(hp.beta1),
-                                  beta2=float(hp.beta2), comp=float(rp.compression_factor), w_rec=float(rp.weight),
-                                  w_reg=float(reg.loss.weight), crop_max=float(reg.crop_sigma_max),
-                                  crop_min=float(reg.crop_sigma_min), norm_rec=LOSS_NORMS[rp.name],
-                                  norm_reg=LOSS_NORMS[reg.loss.name],
-                                  comp_reg=float(_get(reg.loss, "compression_factor", rp.compression_factor)))
+                                  beta2=float(hp.beta2), comp=float(_get(rp, "compression_factor", 1.0)),
+                                  w_rec=float(_get(rp, "weight", 1.0)), w_reg=float(_get(reg.loss, "weight", 1.0)),
+                                  crop_max=float(reg.crop_sigma_max),
+                                  crop_min=float(reg.crop_sigma_min), use_rec=rp.name != "none",
+                                  use_reg=reg.loss.name != "none", norm_rec=LOSS_NORMS.get(rp.name, "summean"),
+                                  norm_reg=LOSS_NORMS.get(reg.loss.name, "summean"),
+                                  comp_reg=float(_get(reg.loss, "compression_factor", _get(rp, "compression_factor", 1.0))))
             return
         rir = getattr(operator, "params", None)
         H = getattr(operator, "H", None)

@@ -149,6 +149,36 @@ def test_blind_with_reference_operator_object(rh, nets):
     assert e < TOL and er < 5e-3 and eH < 5e-3
 
 
+def test_blind_without_the_rir_noise_regulariser(rh, nets):
+    """`RIR_noise_regularization.loss.name: none` (utils/losses.py:19-20 -> EulerHeunSamplerDPS.py:95): the operator
+    update runs on the reconstruction loss alone and draws no RIR noise."""
+    from buddy_b200.samplers import EulerHeunSamplerDPS as Ours
+    from testing.EulerHeunSamplerDPS import EulerHeunSamplerDPS as Ref
+    from testing.operators.subband_filtering import BlindSubbandFiltering
+    ref_net, our_net = nets
+    T = 2
+    _, y = _observation(rh, 600)
+    torch.manual_seed(12)
+    bop = BlindSubbandFiltering(rh.op_hp(), sample_rate=16000)
+    with torch.no_grad():
+        bop.update_H(use_noise=True)
+    bop2 = copy.deepcopy(bop)
+    noise = [randn(610 + i, 1, NS) for i in range(T + 1)]
+    args = rh.make_args("blind", T)
+    args.tester.posterior_sampling.blind_hp["op_updates_per_step"] = 1
+    args.tester.posterior_sampling.RIR_noise_regularization.loss["name"] = "none"
+    edm = rh.build_edm()
+    with rh.injected_noise(noise):
+        want = Ref(ref_net, edm, args).predict_conditional(y, bop, shape=(1, NS), blind=True)
+    smp = Ours(our_net, edm, args)
+    smp.noise_source = iter(noise)
+    got = smp.predict_conditional(y, bop2, shape=(1, NS), blind=True)
+    e = rel(got, want)
+    eH = rel(torch.view_as_real(bop2.H), torch.view_as_real(bop.H.detach()))
+    print(f"\n[blind T2, no regulariser] pred {e:.2e}  H {eH:.2e}")
+    assert e < TOL and eH < 5e-3
+
+
 def test_api_operator_classes_match_reference(rh):
     """buddy_b200.operators.{RIROperator, BlindSubbandFiltering} against the reference classes, method by method."""
     from buddy_b200 import operators as ours
