@@ -158,6 +158,33 @@ def test_factored_stft_matrices_equal_the_dft_matrices():
         assert (got - want).abs().max().item() < 1e-7 * want.abs().max().item()
 
 
+def test_netspec_variant_layouts():
+    """Module plan / state_dict layout of every NCSN++ graph variant.  The (tensor count, module count) pairs were read
+    off the instantiated reference (`NCSNppTime(resblock_type=..., progressive=..., progressive_input=...)`,
+    networks/ncsnpp.py:196-274) in the build container, where `param_spec` was compared key by key and shape by shape."""
+    from buddy_b200 import netspec
+    from buddy_b200.ncsnpp import NCSNppTime
+    want = {("biggan", "output_skip", "input_skip"): (271, 36), ("biggan", "output_skip", "residual"): (271, 36),
+            ("biggan", "output_skip", "none"): (265, 33), ("biggan", "residual", "input_skip"): (269, 35),
+            ("biggan", "residual", "residual"): (269, 35), ("biggan", "residual", "none"): (263, 32),
+            ("biggan", "none", "input_skip"): (259, 30), ("biggan", "none", "residual"): (259, 30),
+            ("biggan", "none", "none"): (253, 27), ("ddpm", "output_skip", "input_skip"): (211, 36),
+            ("ddpm", "output_skip", "residual"): (211, 36), ("ddpm", "output_skip", "none"): (205, 33),
+            ("ddpm", "residual", "input_skip"): (209, 35), ("ddpm", "residual", "residual"): (209, 35),
+            ("ddpm", "residual", "none"): (203, 32), ("ddpm", "none", "input_skip"): (199, 30),
+            ("ddpm", "none", "residual"): (199, 30), ("ddpm", "none", "none"): (193, 27)}
+    for v, (n_keys, n_mod) in want.items():
+        spec = netspec.param_spec(*v)
+        assert (len(spec), netspec.plan(*v)[1]) == (n_keys, n_mod), v
+        assert len({k for k, _ in spec}) == n_keys
+    net = NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2],
+                     resblock_type="ddpm", progressive="residual", progressive_input="residual")
+    sd = net.state_dict()
+    assert [(k, tuple(t.shape)) for k, t in sd.items()] == netspec.param_spec("ddpm", "residual", "residual")
+    assert sum(t.numel() for t in NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128,
+                                             ch_mult=[1, 2, 2, 2]).state_dict().values()) == 27_736_590
+
+
 def test_wav_reader_and_paired_set(tmp_path):
     """Input half of the tester front-end: `read_wav` against scipy's reader on every sample format, and
     `PairedWavSet` (datasets/vctk.py:148-226: clean/<spk>/<id>.wav + rir/<spk>/<id>.wav, RIR cropped at its direct
