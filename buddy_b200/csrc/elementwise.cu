@@ -903,6 +903,36 @@ extern "C" int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, 
   LAUNCH_END("gn_bwd_kernel<apply>");
 }
 
+// GroupNorm (+SiLU) of one tensor written as fp32 (no resample, no operand packing): the `fir: True` variant puts a
+// FIR resampler (upfirdn2d) between the activation and the convolution (layerspp.py:252-259), which needs the
+// activation itself; the operand is made afterwards by cast_operand_kernel.
+__global__ void __launch_bounds__(256) gn_act32_kernel(GnSrc s, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, long long P, int G, int cpg,
+                                                       float eps, int silu, float* __restrict__ out) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int b = blockIdx.y;
+  const int C = s.Ca;
+  group_stats_to_smem(s_mean, s_rstd, s, b, G, cpg, static_cast<double>(cpg) * static_cast<double>(P), eps);
+  __syncthreads();
+  const int c4n = C >> 2;
+  const long long total = P * c4n;
+  const float* x = s.xa + static_cast<size_t>(b) * P * C;
+  float* o = out + static_cast<size_t>(b) * P * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c4n) * 4;
+    const long long p = i / c4n;
+    const int grp = c / cpg;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float rs = s_rstd[grp], mu = s_mean[grp];
+    const float sc[4] = {rs * g.x, rs * g.y, rs * g.z, rs * g.w};
+    const float sh[4] = {be.x - mu * sc[0], be.y - mu * sc[1], be.z - mu * sc[2], be.w - mu * sc[3]};
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * C + c));
+    *reinterpret_cast<float4*>(o + p * C + c) = act4(v, sc, sh, silu);
+  }
+}
+
 extern "C" int buddy_im2col_c2(const float* x, int B, int H, int W, void* col, int split, void* col8, float in_scale,
                                void* stream) {
   const long long items = static_cast<long long>(B) * H * W * 8;
@@ -995,6 +1025,24 @@ __global__ void cast_operand_kernel(const float* __restrict__ x, int B, int H, i
     v = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
     store_op4(out, out8, static_cast<size_t>(po), C, c, split, v);
   }
+}
+
+extern "C" int buddy_gn_act32(const float* x, const double* stats, const float* gamma, const float* beta, int batch,
+                              int64_t pixels, int C, int groups, float eps, int silu, float* out, void* stream) {
+  int e = check_gn(C, 0, groups, "buddy_gn_act32");
+  if (e) return e;
+  if (!x || !stats || !gamma || !beta || !out || batch <= 0 || pixels <= 0) {
+    set_last_error("buddy_gn_act32: invalid argument");
+    return BUDDY_ERR_INVALID;
+  }
+  GnSrc s = {x, nullptr, C, 0, stats, nullptr};
+  const long long total = pixels * (C / 4);
+  long long gx = (total + 256 * 8 - 1) / (256 * 8);
+  if (gx > 148 * 8) gx = 148 * 8;
+  if (gx < 1) gx = 1;
+  gn_act32_kernel<<<dim3((unsigned)gx, batch), 256, 0, STREAM>>>(s, gamma, beta, pixels, groups, C / groups, eps, silu,
+                                                                 out);
+  LAUNCH_END("gn_act32_kernel");
 }
 
 extern "C" int buddy_cast_operand(const float* x, int batch, int H, int W, int C, int upsample, float scale, void* out16,

@@ -90,12 +90,14 @@ class Engine:
     BWD_X1_POLICY = "E"
 
     def __init__(self, state_dict, device, precision="mixed", resblock_type="biggan", progressive="output_skip",
-                 progressive_input="input_skip"):
+                 progressive_input="input_skip", fir=False, fir_kernel=(1, 3, 3, 1)):
         """resblock_type: "biggan" (shipped configuration) or "ddpm": ResnetBlockDDPMpp blocks — the same two-conv block,
            skip through NIN_0 — and, in the place of the resampling ResBlocks, Downsample / Upsample modules with one 3x3
            convolution on the RAW tensor (layerspp.py:93-216; ncsnpp.py:141-144,200-201,262-263).
            progressive / progressive_input other than the shipped output_skip / input_skip run on the general module
            walk of engine_generic.py (same kernels, gradients kept in fp32 between modules).
+           fir: the resampling ResBlocks and the pyramids resample with the FIR `fir_kernel` through upfirdn2d
+           (up_or_down_sampling.py:195-256) instead of nearest / 2x2-mean; biggan blocks, no pyramid convolutions.
            precision: operand scheme of the conv GEMMs (all accumulate in fp32 on tcgen05):
              "fp16"   one pass, 11-bit significands (what cuDNN's default TF32 path gives the reference on a GPU)
              "fp16x2" activations split hi+lo (fp16), weights single
@@ -108,8 +110,17 @@ class Engine:
         assert resblock_type in ("biggan", "ddpm"), resblock_type
         self.ddpm = resblock_type == "ddpm"
         # (BUDDY_GENERIC_WALK=1 runs the shipped graph through the general walk as well: tests compare the two)
-        self.generic = ((progressive, progressive_input) != ("output_skip", "input_skip")
+        self.fir = bool(fir)
+        self.generic = ((progressive, progressive_input) != ("output_skip", "input_skip") or self.fir
                         or os.environ.get("BUDDY_GENERIC_WALK", "0") == "1")
+        if self.fir:
+            assert not self.ddpm and progressive != "residual" and progressive_input != "residual"
+            k1 = torch.tensor([float(v) for v in fir_kernel])
+            k2 = torch.outer(k1, k1)
+            k2 = k2 / k2.sum()                                    # _setup_kernel (up_or_down_sampling.py:181-188)
+            p = k2.shape[0] - 2
+            self._fir_k = {True: (k2 * 4.0).to(self.device).contiguous(), False: k2.to(self.device).contiguous()}
+            self._fir_pad = {True: ((p + 1) // 2 + 1, p // 2), False: ((p + 1) // 2, p // 2)}
         self.resamp = {}        # ddpm: module index -> Downsample / Upsample convolution
         self._k1 = torch.ones(1, 1, device=self.device)         # upfirdn taps: pick / zero-stuff
         self._k22 = torch.ones(2, 2, device=self.device)        # ... and the 2x2 sum (adjoint of nearest x2)
@@ -373,6 +384,24 @@ class Engine:
             out[i] = o
         return out
 
+    # ------------------------------------------------------------------ FIR resampling (fir: True)
+    def _fir_fwd(self, x4, up):
+        """upsample_2d / downsample_2d by 2 (up_or_down_sampling.py:195-256) of fp32 [B, H, W, C]."""
+        p0, p1 = self._fir_pad[up]
+        return upfirdn2d._launch(x4, self._fir_k[up], (2, 2) if up else (1, 1), (1, 1) if up else (2, 2),
+                                 (p0, p1, p0, p1))
+
+    def _fir_bwd(self, g4, up, in_h, in_w):
+        """Adjoint of `_fir_fwd` (op/upfirdn2d.py:104-107,124-139: flipped kernel, up and down exchanged, complementary
+        padding): gradient w.r.t. an [B, in_h, in_w, C] input."""
+        k = self._fir_k[up]
+        kk = k.shape[0]
+        p0, _ = self._fir_pad[up]
+        u, d = (2, 1) if up else (1, 2)
+        oh, ow = g4.shape[1], g4.shape[2]
+        g_pad = (kk - p0 - 1, in_w * u - ow * d + p0 - u + 1, kk - p0 - 1, in_h * u - oh * d + p0 - u + 1)
+        return upfirdn2d._launch(g4.contiguous(), torch.flip(k, [0, 1]).contiguous(), (d, d), (u, u), g_pad)
+
     # ------------------------------------------------------------------ ResBlock
     def _rb_fwd(self, i, xa, sa, xb, sb, tb, mode, save):
         r = self.rb[i]
@@ -383,8 +412,17 @@ class Engine:
         dev = self.device
         a0 = self._operand(B, Ho, Wo, C, need8=not r.x1[0])
         raw = self._operand(B, Ho, Wo, C, need8=not r.x1[1]) if r.has_skip_conv else None
-        ops.gn_apply(xa, sa, r.g0, r.b0, a0.t16, xb=xb, sb=sb, silu=True, mode=mode,
-                     out_raw=raw.t16 if raw else None, split=self.split, out8=a0.t8, out_raw8=raw.t8 if raw else None)
+        if self.fir and mode != MODE_NONE:
+            # layerspp.py:252-259 with fir: h = resample_fir(act(GroupNorm_0(x))), x = resample_fir(x)
+            assert xb is None and raw is not None
+            act = self._fir_fwd(ops.gn_act32(xa, sa, r.g0, r.b0, torch.empty_like(xa)), mode == MODE_UP)
+            ops.cast_operand(act, a0.t16, a0.t8, split=self.split)
+            del act
+            ops.cast_operand(self._fir_fwd(xa, mode == MODE_UP), raw.t16, raw.t8, split=self.split)
+        else:
+            ops.gn_apply(xa, sa, r.g0, r.b0, a0.t16, xb=xb, sb=sb, silu=True, mode=mode,
+                         out_raw=raw.t16 if raw else None, split=self.split, out8=a0.t8,
+                         out_raw8=raw.t8 if raw else None)
         h1 = torch.empty(B, Ho, Wo, r.cout, device=dev)
         s1 = self._zeros_stats(B, r.cout)
         self._conv(a0, r.w0, h1, taps=9, n_total=r.cout, bias=r.bias0, bias_b=tb[i], stats=s1)
@@ -433,6 +471,11 @@ class Engine:
             skip_scale = 1.0
         else:
             dsk, skip_scale = dout32, INV_SQRT2
+        if self.fir and mode != MODE_NONE:
+            # pull both gradients back through the FIR resampler; the GroupNorm backward then sees no resampling
+            da0 = self._fir_bwd(da0, mode == MODE_UP, xa.shape[1], xa.shape[2])
+            dsk = self._fir_bwd(dsk, mode == MODE_UP, xa.shape[1], xa.shape[2])
+            mode = MODE_NONE
         Ca = xa.shape[3]
         dxa = torch.empty_like(xa) if want_a32 else None
         g16a = (self._operand(*xa.shape[:3], Ca, self._gscale(("x", i)), need8=not self._x1(consumer, 1))

@@ -156,7 +156,10 @@ def forward(eng, spec, time_cond, save=True):
             h = o
         elif kind == "combine":
             p = pyr.t
-            p2 = Val(ops.resample_c2(p, 0, torch.empty(B, p.shape[1] // 2, p.shape[2] // 2, 2, device=dev)))
+            if eng.fir:       # pyramid_downsample = Downsample(fir=True, with_conv=False): downsample_2d
+                p2 = Val(eng._fir_fwd(p, False))
+            else:
+                p2 = Val(ops.resample_c2(p, 0, torch.empty(B, p.shape[1] // 2, p.shape[2] // 2, 2, device=dev)))
             tape.append(("avgpool", None, (pyr,), p2))
             pyr = p2
             w, b = eng.comb[i]
@@ -185,7 +188,10 @@ def forward(eng, spec, time_cond, save=True):
             elif kind == "final":
                 out2 = ph
             else:
-                pn = Val(ops.resample_c2(pyramid.t, 1, torch.empty_like(ph.t), add=ph.t))
+                if eng.fir:   # pyramid_upsample = Upsample(fir=True, with_conv=False): upsample_2d
+                    pn = Val(eng._add32(eng._fir_fwd(pyramid.t, True), ph.t))
+                else:
+                    pn = Val(ops.resample_c2(pyramid.t, 1, torch.empty_like(ph.t), add=ph.t))
                 tape.append(("upadd", None, (pyramid, ph), pn))
                 pyramid = pn
         elif kind == "gnconv":
@@ -241,7 +247,10 @@ def vjp(eng, ctx, dout):
         elif kind == "upadd":
             pold, ph = ins
             add(ph, g)
-            add(pold, ops.resample_c2(g, 3, torch.empty(B, g.shape[1] // 2, g.shape[2] // 2, 2, device=dev)))
+            if eng.fir:
+                add(pold, eng._fir_bwd(g, True, pold.t.shape[1], pold.t.shape[2]))
+            else:
+                add(pold, ops.resample_c2(g, 3, torch.empty(B, g.shape[1] // 2, g.shape[2] // 2, 2, device=dev)))
         elif kind == "rb":
             xa, xb = ins
             g16 = _cast(eng, g, ("gx", i), INV_SQRT2, need8=not eng.rb[i].x1b[1])
@@ -258,7 +267,10 @@ def vjp(eng, ctx, dout):
         elif kind == "up":
             add(ins[0], eng._up_bwd(i, _cast(eng, g, ("gu", i))))
         elif kind == "avgpool":
-            add(ins[0], ops.resample_c2(g, 2, torch.empty(B, 2 * g.shape[1], 2 * g.shape[2], 2, device=dev)))
+            if eng.fir:
+                add(ins[0], eng._fir_bwd(g, False, ins[0].t.shape[1], ins[0].t.shape[2]))
+            else:
+                add(ins[0], ops.resample_c2(g, 2, torch.empty(B, 2 * g.shape[1], 2 * g.shape[2], 2, device=dev)))
         elif kind == "combine":
             h, p = ins
             add(h, g)

@@ -69,16 +69,25 @@ class NCSNpp(nn.Module):
                 want = _SUPPORTED[k]
                 got = tuple(v) if isinstance(want, tuple) else v
                 got = got.lower() if isinstance(got, str) else got
-                if k in variants and got in variants[k]:
+                if (k in variants and got in variants[k]) or k == "fir":
                     continue
                 if got != want:
                     raise NotImplementedError(
                         f"buddy_b200.NCSNpp implements the shipped BUDDy configuration only: {k}={v!r} (need {want!r})")
         self.variant = (self.resblock_type, self.progressive, self.progressive_input)
+        # fir: FIR resampling (upfirdn2d) in the BigGAN blocks and the parameter-free pyramids; the fused FIR convolutions
+        # (`up_or_down_sampling.Conv2d`: ddpm Upsample / Downsample, residual pyramids) are not implemented
+        self.fir = bool(kwargs.get("fir", False))
+        self.fir_kernel = tuple(float(v) for v in fir_kernel)
+        if self.fir and (self.resblock_type != "biggan" or "residual" in self.variant[1:]):
+            raise NotImplementedError("buddy_b200.NCSNpp: fir=True is implemented for resblock_type='biggan' with "
+                                      "progressive / progressive_input in {output_skip, input_skip, none}")
+        if self.fir and (len(self.fir_kernel) % 2 or len(self.fir_kernel) < 2):
+            raise NotImplementedError("fir_kernel must have an even number of taps")
         gn_modules, scaled_convs = netspec.init_roles(*self.variant)
         # the `mixed` single-pass policy is tuned (and measured) on the shipped progressive graph; the other progressive
         # variants keep the e4m3 corrections on every convolution unless told otherwise
-        shipped = self.variant[1:] == ("output_skip", "input_skip")
+        shipped = self.variant[1:] == ("output_skip", "input_skip") and not self.fir
         self.precision = precision or os.environ.get("BUDDY_PRECISION", "mixed" if shipped else "fp16c8")
         self.time_conditional = True
         self.spatial_channels, self.input_channels = 1, 2
@@ -119,7 +128,8 @@ class NCSNpp(nn.Module):
         key = (str(dev), self.precision, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
         if self._engine is None or key != self._engine_key:
             self._engine = Engine(self.state_dict(), dev, precision=self.precision, resblock_type=self.resblock_type,
-                                  progressive=self.progressive, progressive_input=self.progressive_input)
+                                  progressive=self.progressive, progressive_input=self.progressive_input,
+                                  fir=self.fir, fir_kernel=self.fir_kernel)
             self._engine_key = key
         return self._engine
 

@@ -178,6 +178,16 @@ def gn_apply(xa, sa, gamma, beta, out, *, xb=None, sb=None, groups=32, silu=True
     return out
 
 
+def gn_act32(x, stats, gamma, beta, out, groups=32, eps=1e-6, silu=True):
+    """fp32 GroupNorm(+SiLU) of x [B,H,W,C] (see buddy_gn_act32)."""
+    B, C = x.shape[0], x.shape[-1]
+    P = x.numel() // (B * C)
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.shape == x.shape and out.dtype == torch.float32
+    check(lib().buddy_gn_act32(ptr(x), ptr(stats), ptr(gamma), ptr(beta), c_int(B), c_i64(P), c_int(C), c_int(groups),
+                               c_float(eps), c_int(int(silu)), ptr(out), stream_ptr()), "buddy_gn_act32")
+    return out
+
+
 def gn_bwd(xa, sa, gamma, beta, da, gsum, *, xb=None, sb=None, groups=32, silu=True, mode=MODE_NONE, dskip=None,
            skip_scale=1.0, extra_a=None, extra_b=None, dxa=None, dxb=None, g16a=None, g16b=None, g16_scale=1.0,
            eps=1e-6, split=False, g8a=None, g8b=None, pass0_done=False):

@@ -3,8 +3,9 @@
 autograd through the data) and the FIR resampling helpers built on it (up_or_down_sampling.py:181-256).
 
 CUDA tensors only (no CPU fallback: the reference's `upfirdn2d_native` CPU branch is restated in oracle/upfirdn.py as
-the test oracle).  `fir=True` is not wired into the NCSN++ engine: the shipped configuration has `fir: False`, and the
-reference as published cannot run `fir=True` at all (its import of this operator is commented out,
+the test oracle).  The NCSN++ engine uses `_launch` on its channels-last activations for `fir=True` (engine.py
+`_fir_fwd` / `_fir_bwd`) and for the ddpm Downsample / Upsample modules; the shipped configuration has `fir: False`, and
+the reference as published cannot run `fir=True` at all (its import of this operator is commented out,
 up_or_down_sampling.py:10 -> NameError at :140/:176/:223/:256).
 """
 import ctypes

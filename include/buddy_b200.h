@@ -226,6 +226,10 @@ typedef struct buddy_gn_bwd_desc {
 
 int buddy_gn_stats(const float* x, int batch, int64_t pixels, int C, double* stats /* += */, void* stream);
 int buddy_gn_apply(const buddy_gn_desc* d, void* stream);
+/* GroupNorm (+SiLU) of one tensor x [batch][pixels][C] written as fp32 — the activation that the `fir: True` blocks hand
+ * to upfirdn2d before the convolution (ResnetBlockBigGANpp.forward with fir, layerspp.py:252-259). */
+int buddy_gn_act32(const float* x, const double* stats, const float* gamma, const float* beta, int batch,
+                   int64_t pixels, int C, int groups, float eps, int silu, float* out, void* stream);
 int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, void* stream);
 
 /* 2-channel (re, im) image helpers — the thin ends of the U-Net.

@@ -272,7 +272,8 @@ def test_error_behaviour_without_gpu():
     args.tester.sampling_params["schedule"] = "song"
     with pytest.raises(NotImplementedError):              # Sampler.py:58-65
         EulerHeunSampler(_Net(), edm, args).create_schedule()
-    for bad in (dict(fir=True), dict(resblock_type="ddpmpp"), dict(progressive_combine="cat"), dict(num_res_blocks=2)):
+    for bad in (dict(fir=True, resblock_type="ddpm"), dict(fir=True, progressive="residual"), dict(resblock_type="ddpmpp"),
+                dict(progressive_combine="cat"), dict(num_res_blocks=2)):
         with pytest.raises(NotImplementedError):
             NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2], **bad)
     with pytest.raises(NotImplementedError):              # other STFT sizes

@@ -163,6 +163,19 @@ def test_softmax_transpose_cast():
     assert rel(yh.float(), xf * 0.5) < 1e-3
 
 
+def test_gn_act32():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(13)
+    for C, silu in ((128, True), (256, False), (384, True)):
+        x = torch.randn(2, 6, 10, C, device="cuda", generator=g) * 1.3 + 0.2
+        gamma = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+        beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+        out = ops.gn_act32(x, ops.gn_stats(x), gamma, beta, torch.empty_like(x), silu=silu)
+        y = F.group_norm(nchw(x), 32, gamma, beta, eps=1e-6)
+        y = F.silu(y) if silu else y
+        assert rel(out, nhwc(y)) < 1e-5
+
+
 def test_cast_operand():
     """Raw fp32 tensor -> tensor-core operand (fp16, fp16 hi|lo, fp16 + e4m3 pair), optional nearest x2 upsampling."""
     ops = _ops()

@@ -278,6 +278,20 @@ def test_progressive_variants_vs_reference_network(rh, variant):
     assert ef < TOL and eb < TOL
 
 
+@pytest.mark.parametrize("variant", [dict(fir=True), dict(fir=True, progressive="none", progressive_input="none")],
+                         ids=["fir", "fir-none-none"])
+def test_fir_variant_vs_reference_network(rh, variant):
+    """`fir: True` (FIR [1, 3, 3, 1] resampling through upfirdn2d in the BigGAN blocks and the pyramids,
+    layerspp.py:252-259, up_or_down_sampling.py:195-256).  The published reference cannot run this option (its import of
+    upfirdn2d is commented out); `ref_harness.restore_upfirdn2d` binds the missing name at run time to the operator's
+    plain-PyTorch branch, nothing else changes."""
+    ref_net, ours, spec = _variant_pair(rh, 5, **variant)
+    assert ours.engine().fir and ours.engine().generic
+    ef, eb = _fwd_vjp_errors(ref_net, ours)
+    print(f"\n[{variant}] forward {ef:.2e}  data-gradient {eb:.2e}")
+    assert ef < TOL and eb < TOL
+
+
 def test_general_walk_matches_scheduled_walk_on_shipped_graph(rh, nets, monkeypatch):
     """The shipped graph through engine_generic's tape (BUDDY_GENERIC_WALK=1) against the hand-scheduled walk of
     engine.py: same kernels, fp32 gradients between the modules instead of fp16 operands — equal to rounding."""
