@@ -56,7 +56,9 @@ def test_no_cpu_fallback():
 def test_unsupported_config_raises():
     from buddy_b200.ncsnpp import NCSNppTime
     with pytest.raises(NotImplementedError):
-        NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), fir=True)
+        NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), fir=True, resblock_type="ddpm")
+    with pytest.raises(NotImplementedError):
+        NCSNppTime(stft=dict(n_fft=510, hop_length=128, center=True), nf=64)
     with pytest.raises(NotImplementedError):
         NCSNppTime(stft=dict(n_fft=512, hop_length=128, center=True))
 
