@@ -292,6 +292,33 @@ def test_fir_variant_vs_reference_network(rh, variant):
     assert ef < TOL and eb < TOL
 
 
+@pytest.mark.parametrize("variant", [dict(fir=True), dict(resblock_type="ddpm", progressive="residual",
+                                                         progressive_input="residual")], ids=["fir", "ddpm-residual"])
+def test_variant_networks_in_the_sampler_with_cuda_graphs(rh, variant):
+    """A variant network inside the DPS sampler at B = 1, where the network forward / data-gradient are replayed as CUDA
+    graphs (the general walk's tape, lazily computed statistics and upfirdn2d launches captured): same trajectory as
+    with plain launches, and as the reference sampler driving the reference variant network."""
+    from buddy_b200.samplers import EulerHeunSamplerDPS as Ours
+    from testing.EulerHeunSamplerDPS import EulerHeunSamplerDPS as Ref
+    ref_net, our_net, _ = _variant_pair(rh, 6, **variant)
+    T = 2
+    op, y = _observation(rh, 700)
+    noise = [randn(710 + i, 1, NS) for i in range(T + 1)]
+    edm = rh.build_edm()
+    with rh.injected_noise(noise):
+        want = Ref(ref_net, edm, rh.make_args("informed", T)).predict_conditional(y, op, shape=(1, NS), blind=False)
+    outs = []
+    for graphs in (True, False):
+        smp = Ours(our_net, edm, rh.make_args("informed", T))
+        smp.use_graphs = graphs
+        smp.noise_source = iter(noise)
+        outs.append(smp.predict_conditional(y, op, shape=(1, NS), blind=False).clone())
+    assert our_net.engine()._graphs, "the graph path did not run"
+    e = rel(outs[0], want)
+    print(f"\n[{variant} in the sampler] vs reference {e:.2e}; graphs vs plain launches {rel(outs[0], outs[1]):.1e}")
+    assert torch.equal(outs[0], outs[1]) and e < TOL
+
+
 def test_general_walk_matches_scheduled_walk_on_shipped_graph(rh, nets, monkeypatch):
     """The shipped graph through engine_generic's tape (BUDDY_GENERIC_WALK=1) against the hand-scheduled walk of
     engine.py: same kernels, fp32 gradients between the modules instead of fp16 operands — equal to rounding."""
