@@ -134,7 +134,11 @@ class Engine:
         # where the geometry allows (no resample, single input tensor).  Correct (tests) but OFF by default: measured
         # on B200 it removes 19 ms of GroupNorm time per B=32 step and adds 51 ms to the convolutions (the epilogue's
         # exp/rcp work and x reads no longer hide behind the mainloop at the board's power cap): 398 -> 429 ms.
-        self.fuse_gnb = os.environ.get("BUDDY_FUSE_GNB", "0") == "1"
+        self.fuse_gnb = os.environ.get("BUDDY_FUSE_GNB", "0") in ("1", "2", "3")
+        # "2" / "3": only under data-gradient convolutions with >= 256 output channels (long mainloop per tile: the
+        # epilogue's extra work hides behind it) / additionally only at the coarser levels
+        self.fuse_gnb_min_n = {"1": 0, "2": 256, "3": 256}.get(os.environ.get("BUDDY_FUSE_GNB", "0"), 0)
+        self.fuse_gnb_coarse = os.environ.get("BUDDY_FUSE_GNB", "0") == "3"
         self._graphs = {}
         self.graph_max_batch = 8    # larger batches are GPU-bound: plain launches (no pinned graph memory pool)
         self.graph_cache_size = 4   # captured shapes kept (oldest evicted)
@@ -450,7 +454,8 @@ class Engine:
         dev = self.device
         gsum = self._scratch_gsum(B)
         da1 = torch.empty(B, Ho, Wo, r.cout, device=dev)
-        fuse1 = self.fuse_gnb        # GroupNorm_1 sits directly under conv 1: always the same geometry
+        ok_lvl = not self.fuse_gnb_coarse or Ho < 256
+        fuse1 = self.fuse_gnb and r.cout >= self.fuse_gnb_min_n and ok_lvl   # GroupNorm_1 sits directly under conv 1
         gsum1 = torch.zeros(B, 32, 2, device=dev, dtype=torch.float64) if fuse1 else gsum
         self._conv(g16, r.wd1, da1, taps=9, n_total=r.cout,
                    gnb=(h1, s1, r.g1, r.b1, gsum1, 32, 1e-6, 1) if fuse1 else None)
@@ -460,7 +465,8 @@ class Engine:
         self._record(("h1", i), dh1)
         del da1
         da0 = torch.empty(B, Ho, Wo, r.cin, device=dev)
-        fuse0 = self.fuse_gnb and mode == MODE_NONE and xb is None     # GroupNorm_0 of a plain block
+        fuse0 = (self.fuse_gnb and mode == MODE_NONE and xb is None and r.cin >= self.fuse_gnb_min_n
+                 and ok_lvl)                                              # GroupNorm_0 of a plain block
         gsum0 = torch.zeros(B, 32, 2, device=dev, dtype=torch.float64) if fuse0 else gsum
         self._conv(dh1, r.wd0, da0, taps=9, n_total=r.cin,
                    gnb=(xa, sa, r.g0, r.b0, gsum0, 32, 1e-6, 1) if fuse0 else None)
