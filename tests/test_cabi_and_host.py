@@ -160,6 +160,16 @@ def test_factored_stft_matrices_equal_the_dft_matrices():
         assert (got - want).abs().max().item() < 1e-7 * want.abs().max().item()
 
 
+def test_package_root_exports():
+    """the plug-in classes selectable as `buddy_b200.<Class>` Hydra targets."""
+    import importlib
+    import buddy_b200
+    for name, mod in buddy_b200._EXPORTS.items():
+        assert getattr(buddy_b200, name) is getattr(importlib.import_module("buddy_b200." + mod), name)
+    with pytest.raises(AttributeError):
+        buddy_b200.no_such_thing
+
+
 def test_netspec_variant_layouts():
     """Module plan / state_dict layout of every NCSN++ graph variant.  The (tensor count, module count) pairs were read
     off the instantiated reference (`NCSNppTime(resblock_type=..., progressive=..., progressive_input=...)`,
