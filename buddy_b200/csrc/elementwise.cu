@@ -795,6 +795,21 @@ static int gn_ppt() {
   return v;
 }
 
+// CTAs per image for the GroupNorm kernels: ~gn_ppt() pixels per thread on big images, but never fewer than ~2 x 148 CTAs
+// per image — at the coarse levels (32 x 66 pixels) a 32-pixel-per-thread grid is 17 CTAs of serial, latency-bound
+// loads (ncu, B = 1: 20-28 us per launch for 2 MB of data).  Depends on the image only, never on the batch, so the
+// grouping of the partial sums — and with it every bit of the statistics — is the same for an utterance run alone or in
+// a batch.
+static long long gn_grid(long long P, long long ppb) {
+  long long ppt = P / (ppb * 296);
+  if (ppt < 2) ppt = 2;
+  if (ppt > gn_ppt()) ppt = gn_ppt();
+  long long gx = (P + ppb * ppt - 1) / (ppb * ppt);
+  if (gx > 148 * 16) gx = 148 * 16;
+  if (gx < 1) gx = 1;
+  return gx;
+}
+
 static int check_gn(int Ca, int Cb, int G, const char* who) {
   const int C = Ca + Cb;
   if (Ca % 8 || Cb % 8 || C <= 0 || C > 1024 || G <= 0 || G > 32 || C % G || (C / G) % 4) {
@@ -840,9 +855,7 @@ extern "C" int buddy_gn_apply(const buddy_gn_desc* d, void* stream) {
   const int threads = c4n * (256 / c4n > 0 ? 256 / c4n : 1);
   const long long ppb = threads / c4n;
   const long long Pw = static_cast<long long>(d->mode == 2 ? (d->H / 2) * (d->W / 2) : d->H * d->W);
-  long long gx = (Pw + ppb * gn_ppt() - 1) / (ppb * gn_ppt());   // ~32 pixels per thread
-  if (gx > 148 * 16) gx = 148 * 16;
-  if (gx < 1) gx = 1;
+  const long long gx = gn_grid(Pw, ppb);
   gn_apply_kernel<<<dim3((unsigned)gx, d->batch), threads, 0, STREAM>>>(a);
   LAUNCH_END("gn_apply_kernel");
 }
@@ -886,9 +899,7 @@ extern "C" int buddy_gn_bwd(const buddy_gn_desc* d, const buddy_gn_bwd_desc* g, 
   const int threads = c4n * (256 / c4n > 0 ? 256 / c4n : 1);
   const long long ppb = threads / c4n;
   const long long P = static_cast<long long>(d->H) * d->W;
-  long long gx = (P + ppb * gn_ppt() - 1) / (ppb * gn_ppt());
-  if (gx > 148 * 16) gx = 148 * 16;
-  if (gx < 1) gx = 1;
+  const long long gx = gn_grid(P, ppb);
   if (!g->pass0_done) {
     e = check_cuda(cudaMemsetAsync(g->gsum, 0, sizeof(double) * 2 * d->groups * d->batch, STREAM), "memset gsum");
     if (e) return e;

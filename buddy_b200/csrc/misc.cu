@@ -52,6 +52,29 @@ __global__ void dense_kernel(const float* __restrict__ x, const float* __restric
   }
 }
 
+// Several dense layers on the same input in one launch (the per-ResBlock Dense_0(SiLU(temb)) time biases): W is the row
+// concatenation [Out][In]; row o belongs to the segment starting at row seg[2o] with seg[2o+1] rows, and every segment's
+// output is its own contiguous [B][rows] slab at y + B * seg[2o].
+__global__ void dense_seg_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                 const float* __restrict__ bias, const int* __restrict__ seg, int B, int In, int Out,
+                                 int act_in, float* __restrict__ y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * Out) return;
+  const int b = warp / Out, o = warp % Out;
+  float acc = 0.f;
+  for (int i = lane; i < In; i += 32) {
+    float v = x[b * In + i];
+    if (act_in) v = v / (1.f + expf(-v));
+    acc = fmaf(W[static_cast<long long>(o) * In + i], v, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const int s0 = seg[2 * o], rows = seg[2 * o + 1];
+    y[static_cast<long long>(B) * s0 + static_cast<long long>(b) * rows + (o - s0)] = acc + (bias ? bias[o] : 0.f);
+  }
+}
+
 // ---- Philox4x32-10
 __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
   const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
@@ -162,6 +185,17 @@ extern "C" int buddy_dense(const float* x, const float* W, const float* bias, in
   dense_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, STREAM>>>(x, W, bias, B, In, Out, act_in,
                                                                                 act_out, y);
   LAUNCH_END("dense_kernel");
+}
+extern "C" int buddy_dense_seg(const float* x, const float* W, const float* bias, const int32_t* seg, int B, int In,
+                               int Out, int act_in, float* y, void* stream) {
+  if (!x || !W || !seg || !y || B <= 0 || In <= 0 || Out <= 0) {
+    set_last_error("buddy_dense_seg: invalid argument");
+    return BUDDY_ERR_INVALID;
+  }
+  const long long threads = static_cast<long long>(B) * Out * 32;
+  dense_seg_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, STREAM>>>(x, W, bias, seg, B, In, Out,
+                                                                                    act_in, y);
+  LAUNCH_END("dense_seg_kernel");
 }
 extern "C" int buddy_philox_normal(const int64_t* seeds, uint64_t draw, int batch, int n, float* out, int64_t ld,
                                    void* stream) {

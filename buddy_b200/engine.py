@@ -140,6 +140,7 @@ class Engine:
         self.fuse_gnb_min_n = {"1": 0, "2": 256, "3": 256}.get(os.environ.get("BUDDY_FUSE_GNB", "0"), 0)
         self.fuse_gnb_coarse = os.environ.get("BUDDY_FUSE_GNB", "0") == "3"
         self._graphs = {}
+        self._dense_cat = None
         self.graph_max_batch = 8    # larger batches are GPU-bound: plain launches (no pinned graph memory pool)
         self.graph_cache_size = 4   # captured shapes kept (oldest evicted)
         self.split = 2 if self.c8 else (1 if self.np > 1 else 0)
@@ -381,11 +382,21 @@ class Engine:
         ops.dense(emb, self.lin1[0], self.lin1[1], t1)
         t2 = torch.empty(B, 4 * NF, device=dev)
         ops.dense(t1, self.lin2[0], self.lin2[1], t2, act_in=True)
-        out = {}
+        if self._dense_cat is None:         # all Dense_0 layers as one [sum Cout, 4 nf] matrix: one launch instead of 21
+            ws, bs, seg, r0 = [], [], [], 0
+            for i, r in self.rb.items():
+                ws.append(r.dense[0])
+                bs.append(r.dense[1])
+                seg += [[r0, r.cout]] * r.cout
+                r0 += r.cout
+            self._dense_cat = (torch.cat(ws).contiguous(), torch.cat(bs).contiguous(),
+                               torch.tensor(seg, dtype=torch.int32, device=dev))
+        W, b, seg = self._dense_cat
+        flat = ops.dense_seg(t2, W, b, seg, torch.empty(B * W.shape[0], device=dev), act_in=True)
+        out, r0 = {}, 0
         for i, r in self.rb.items():
-            o = torch.empty(B, r.cout, device=dev)
-            ops.dense(t2, r.dense[0], r.dense[1], o, act_in=True)
-            out[i] = o
+            out[i] = flat[B * r0:B * (r0 + r.cout)].view(B, r.cout)
+            r0 += r.cout
         return out
 
     # ------------------------------------------------------------------ FIR resampling (fir: True)

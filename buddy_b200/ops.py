@@ -415,6 +415,16 @@ def dense(x, W, bias, out, act_in=False, act_out=False):
     return out
 
 
+def dense_seg(x, W, bias, seg, out, act_in=False):
+    """x [B, In]; W [Out, In] = several layers' rows; seg int32 [Out, 2]; out flat [B * Out] (see buddy_dense_seg)."""
+    B, In = x.shape
+    Out = W.shape[0]
+    assert seg.dtype == torch.int32 and seg.shape == (Out, 2) and out.numel() == B * Out
+    check(lib().buddy_dense_seg(ptr(x), ptr(W), ptr(bias), ptr(seg), c_int(B), c_int(In), c_int(Out),
+                                c_int(int(act_in)), ptr(out), stream_ptr()), "buddy_dense_seg")
+    return out
+
+
 def philox_normal(seeds, draw, out):
     B, n = out.shape
     assert seeds.dtype == torch.int64

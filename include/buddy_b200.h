@@ -313,6 +313,12 @@ int buddy_fftconv(const float* x, int64_t x_ld, int batch, int n_in, int log2_n2
 int buddy_fourier_features(const float* t, const float* W, int B, int E, float* out, void* stream);
 int buddy_dense(const float* x, const float* W, const float* bias, int B, int In, int Out, int act_in, int act_out,
                 float* y, void* stream);
+/* Several dense layers on one input in ONE launch — the 21 per-ResBlock Dense_0(act(temb)) time biases
+ * (layerspp.py:248-249).  W / bias: the layers' rows concatenated [Out][In] / [Out]; seg [Out][2] = (first row, row
+ * count) of the layer each row belongs to; layer with first row r0 writes its own contiguous [B][rows] slab at
+ * y + B * r0. */
+int buddy_dense_seg(const float* x, const float* W, const float* bias, const int32_t* seg, int B, int In, int Out,
+                    int act_in, float* y, void* stream);
 /* Philox4x32-10 N(0,1), one stream per utterance (seed[b]), `draw` = running draw index of the sampler. */
 int buddy_philox_normal(const int64_t* seeds, uint64_t draw, int batch, int n, float* out, int64_t ld, void* stream);
 /* out[b][:] = ca[b] x[b][:] + cb[b] y[b][:] + cc[b] z[b][:] — the Euler/Heun/DPS update algebra. */
