@@ -801,7 +801,8 @@ static int gn_ppt() {
 // grouping of the partial sums — and with it every bit of the statistics — is the same for an utterance run alone or in
 // a batch.
 static long long gn_grid(long long P, long long ppb) {
-  long long ppt = P / (ppb * 296);
+  static const long long target = getenv("BUDDY_GN_CTAS") ? atoll(getenv("BUDDY_GN_CTAS")) : 296;
+  long long ppt = P / (ppb * target);
   if (ppt < 2) ppt = 2;
   if (ppt > gn_ppt()) ppt = gn_ppt();
   long long gx = (P + ppb * ppt - 1) / (ppb * ppt);
