@@ -428,7 +428,7 @@ static int grid1(long long items, int threads, int cap = 148 * 8) {
 // FFT-based STFT analysis / synthesis for the 1024-point transforms of the likelihood and the blind operator
 // (apply_stft / apply_istft, testing/operators/subband_filtering.py:41-65): the same linear maps as
 // dft_analysis / dft_synthesis with a matrix  mat[2f+c][n] = a[f] * w[n] * (cos, -sin)(2 pi f n / 1024), but as
-// shared-memory radix-2 FFTs (50 kFLOP per frame instead of 1 MFLOP): 16 frames per CTA.
+// shared-memory radix-4 / radix-16 FFTs (50 kFLOP per frame instead of 1 MFLOP): 8 frames per CTA.
 //   analysis : out[b][f][t] = a[f] * FFT(w * frame_t)[f]
 //   synthesis: fr[b][t][n]  = w[n] * Re( sum_f a[f] S[b][f][t] e^{+2 pi i f n / 1024} )
 // ------------------------------------------------------------------------------------------------
@@ -439,36 +439,89 @@ constexpr int kFftFrames = 8;   // 74 KB of shared memory per CTA: three CTAs pe
 // (addresses one frame apart) land in one bank (both were 8- to 16-way conflicts with the dense [frame][1024] layout).
 constexpr int kFftStride = kFftN + kFftN / 32 + 1;   // 1057
 __device__ __forceinline__ int fidx(int fr, int k) { return fr * kFftStride + k + (k >> 5); }
-__device__ __forceinline__ int bitrev10(int k) { return static_cast<int>(__brev(static_cast<unsigned>(k)) >> 22); }
-// per-stage twiddle tables: stage lh (butterfly span 2^lh) reads tws[2^lh - 1 + pos] = exp(-2 pi i pos / 2^(lh+1)),
-// pos < 2^lh — consecutive threads read consecutive entries (the single 512-entry table was read with strides of
-// 2^(9-lh) entries: 16-way shared-memory bank conflicts in the middle stages)
+// position of output bin k after the in-place radix-4 transform below: base-4 digit reversal of k (= bit reversal of the
+// 10 bits, then the two bits of every digit swapped back)
+__device__ __forceinline__ int digitrev4_1024(int k) {
+  const unsigned r = __brev(static_cast<unsigned>(k)) >> 22;
+  return static_cast<int>(((r & 0x155u) << 1) | ((r >> 1) & 0x155u));
+}
+// per-stage twiddle tables of the radix-4 transform: the stage with butterfly span q = 4^s (s = 4..0) reads
+// tws[(q - 1) + 3 * pos + (m - 1)] = exp(-2 pi i m pos / (4 q)), pos < q, m = 1..3 — 1023 entries in all; consecutive
+// threads (consecutive pos) read consecutive triples.  tw_g[k] = exp(-2 pi i k / 1024), k < 512.
 __device__ __forceinline__ void fft_twiddles_to_smem(float2* tws, const float2* __restrict__ tw_g) {
   for (int i = threadIdx.x; i < 1023; i += blockDim.x) {
-    const int lh = 31 - __clz(i + 1);
-    const int pos = i + 1 - (1 << lh);
-    tws[i] = tw_g[pos << (9 - lh)];
+    const int s2 = (31 - __clz(i + 1)) & ~1;          // 2 s: q = 4^s = largest power of four <= i + 1
+    const int r = i - ((1 << s2) - 1);
+    const int pos = r / 3, m = r - 3 * pos + 1;
+    const int idx = (m * pos) << (8 - s2);            // m * pos * (256 / q) < 768
+    float2 w = tw_g[idx & 511];
+    if (idx >= 512) w = make_float2(-w.x, -w.y);
+    tws[i] = w;
   }
 }
-// in-place radix-2 decimation-in-frequency over `kFftFrames` frames [frame][1024] (natural order in, bit-reversed
-// out); tw = per-stage tables (fft_twiddles_to_smem); conj_tw: inverse transform (unnormalised)
+// radix-4 decimation-in-frequency butterfly on (a0..a3) with output twiddles (w1, w2, w3); inv: conjugate transform
+__device__ __forceinline__ void bfly4(float2& a0, float2& a1, float2& a2, float2& a3, bool inv) {
+  const float2 t0 = make_float2(a0.x + a2.x, a0.y + a2.y), t1 = make_float2(a0.x - a2.x, a0.y - a2.y);
+  const float2 t2 = make_float2(a1.x + a3.x, a1.y + a3.y), d = make_float2(a1.x - a3.x, a1.y - a3.y);
+  const float2 t3 = inv ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);   // +i d  /  -i d
+  a0 = make_float2(t0.x + t2.x, t0.y + t2.y);
+  a1 = make_float2(t1.x + t3.x, t1.y + t3.y);
+  a2 = make_float2(t0.x - t2.x, t0.y - t2.y);
+  a3 = make_float2(t1.x - t3.x, t1.y - t3.y);
+}
+__device__ __forceinline__ float2 cmul(float2 v, float2 w, bool conj_w) {
+  const float wy = conj_w ? -w.y : w.y;
+  return make_float2(v.x * w.x - v.y * wy, v.x * wy + v.y * w.x);
+}
+// in-place 1024-point transform over `kFftFrames` frames [frame][1024] (natural order in, base-4 digit-reversed out):
+// three radix-4 passes through shared memory (spans 256, 64, 16: consecutive threads touch consecutive elements) and one
+// radix-16 pass in registers (spans 4 and 1 on 16 consecutive elements) — 4 barriers and ~2100 instructions per thread
+// where the radix-2 version took 10 and ~4800.  tw = per-stage tables (fft_twiddles_to_smem); conj_tw: inverse
+// transform (unnormalised).
 __device__ __forceinline__ void fft1024_dif(float2* s, const float2* tw, bool conj_tw) {
-  for (int lh = 9; lh >= 0; --lh) {          // butterfly span = 2^lh
-    const int half = 1 << lh;
-    for (int i = threadIdx.x; i < kFftFrames * 512; i += blockDim.x) {
-      const int fr = i >> 9, j = i & 511;
-      const int pos = j & (half - 1);
-      const int k0 = ((j >> lh) << (lh + 1)) + pos;
-      const int i0 = fidx(fr, k0), i1 = fidx(fr, k0 + half);
-      const float2 a = s[i0], b = s[i1];
-      float2 w = tw[half - 1 + pos];
-      if (conj_tw) w.y = -w.y;
-      const float2 d = make_float2(a.x - b.x, a.y - b.y);
-      s[i0] = make_float2(a.x + b.x, a.y + b.y);
-      s[i1] = make_float2(d.x * w.x - d.y * w.y, d.x * w.y + d.y * w.x);
+#pragma unroll 1
+  for (int s2 = 8; s2 >= 4; s2 -= 2) {          // q = 256, 64, 16
+    const int q = 1 << s2;
+    for (int i = threadIdx.x; i < kFftFrames * 256; i += blockDim.x) {
+      const int fr = i >> 8, j = i & 255;
+      const int pos = j & (q - 1);
+      const int k0 = ((j >> s2) << (s2 + 2)) + pos;
+      const int i0 = fidx(fr, k0), i1 = fidx(fr, k0 + q), i2 = fidx(fr, k0 + 2 * q), i3 = fidx(fr, k0 + 3 * q);
+      float2 a0 = s[i0], a1 = s[i1], a2 = s[i2], a3 = s[i3];
+      const float2* w = tw + (q - 1) + 3 * pos;
+      const float2 w1 = w[0], w2 = w[1], w3 = w[2];
+      bfly4(a0, a1, a2, a3, conj_tw);
+      s[i0] = a0;
+      s[i1] = cmul(a1, w1, conj_tw);
+      s[i2] = cmul(a2, w2, conj_tw);
+      s[i3] = cmul(a3, w3, conj_tw);
     }
     __syncthreads();
   }
+  // spans 4 and 1: sixteen consecutive elements per thread (they share one padding offset: 16 | 32)
+  float2 w4[9];                                  // exp(-2 pi i m pos / 16), pos = 1..3, m = 1..3
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w4[k] = tw[3 + 3 + k];
+  for (int g = threadIdx.x; g < kFftFrames * 64; g += blockDim.x) {
+    const int fr = g >> 6, base = fidx(fr, (g & 63) << 4);
+    float2 v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = s[base + e];
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) {
+      bfly4(v[pos], v[pos + 4], v[pos + 8], v[pos + 12], conj_tw);
+      if (pos > 0) {
+        v[pos + 4] = cmul(v[pos + 4], w4[3 * (pos - 1)], conj_tw);
+        v[pos + 8] = cmul(v[pos + 8], w4[3 * (pos - 1) + 1], conj_tw);
+        v[pos + 12] = cmul(v[pos + 12], w4[3 * (pos - 1) + 2], conj_tw);
+      }
+    }
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) bfly4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3], conj_tw);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) s[base + e] = v[e];
+  }
+  __syncthreads();
 }
 __global__ void __launch_bounds__(256)
 fft_analysis_kernel(const float* __restrict__ sig, long long sig_ld, const float* __restrict__ wv,
@@ -496,7 +549,7 @@ fft_analysis_kernel(const float* __restrict__ sig, long long sig_ld, const float
     if (t >= Tout) continue;
     float2 v = make_float2(0.f, 0.f);
     if (t < frames) {
-      const float2 x = s[fidx(fr, bitrev10(f))];
+      const float2 x = s[fidx(fr, digitrev4_1024(f))];
       const float a = __ldg(av + f);
       // DC and Nyquist of a real signal are real: exact zeros as in the matrix form (-sin rows vanish) — a rounding-
       // level residue here would be a spurious non-zero gradient for Adam, which normalises every element
@@ -531,7 +584,7 @@ fft_synthesis_kernel(const float2* __restrict__ S, int Tin, const float* __restr
     const int fr = i / K, n = i - fr * K;
     const int t = t0 + fr;
     if (t < frames)
-      fr_out[(static_cast<long long>(b) * frames + t) * K + n] = __ldg(wv + n) * s[fidx(fr, bitrev10(n))].x;
+      fr_out[(static_cast<long long>(b) * frames + t) * K + n] = __ldg(wv + n) * s[fidx(fr, digitrev4_1024(n))].x;
   }
 }
 
