@@ -7,12 +7,13 @@ __version__ = "0.2.0"
 
 _EXPORTS = {
     "NCSNpp": "ncsnpp", "NCSNppTime": "ncsnpp",
-    "Sampler": "samplers", "EulerHeunSampler": "samplers", "EulerHeunSamplerDPS": "samplers",
+    "Sampler": "samplers", "NoSampler": "samplers", "EulerHeunSampler": "samplers", "EulerHeunSamplerDPS": "samplers",
     "EDM": "edm",
     "Operator": "operators", "RIROperator": "operators", "SubbandFiltering": "operators",
     "BlindSubbandFiltering": "operators",
     "BatchedDereverb": "tester", "AsyncWavWriter": "tester", "PairedWavSet": "tester",
     "load_checkpoint": "checkpoint",
+    "fast_apply_RIR": "functional", "get_loss": "functional",
 }
 
 

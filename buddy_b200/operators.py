@@ -14,7 +14,7 @@ import math
 import torch
 
 from . import ops
-from .spectral import LossSTFT, RirConv
+from .spectral import OperatorSTFT, RirConv
 
 EQ_FREQS = [0, 125, 250, 375, 500, 625, 750, 875, 1000, 1250, 1500, 1750, 2000, 2250, 2500, 2750, 3000, 3500, 4000,
             4500, 5000, 5500, 6000, 6500, 7000, 7500, 8000]
@@ -53,8 +53,17 @@ class RIROperator(Operator):
         self.time_kernel_size = time_kernel_size
         self.sample_rate = sample_rate
         self.params = None
-        self._conv = None
-        self._stft = None
+        self.n_fft = int(_hp(op_hp, "NFFT", 1024))
+        self.win_length = int(_hp(op_hp, "win_length", 512))
+        self.hop_length = int(_hp(op_hp, "hop", 128))
+        window = _hp(op_hp, "window", "hann")
+        if window != "hann":
+            raise NotImplementedError("window type {} not implemented".format(window))
+        if (self.n_fft, self.win_length, self.hop_length) != (1024, 512, 128):
+            raise NotImplementedError("the CUDA kernels implement NFFT 1024 / win_length 512 / hop 128 "
+                                      "(the shipped op_hp) only")
+        self._conv, self._conv_key = None, None
+        self._tf = None
 
     def update_params(self, k, **ignored):
         self.params = torch.as_tensor(k)
@@ -62,20 +71,62 @@ class RIROperator(Operator):
 
     def degradation(self, x, rm_delay=False, **ignored):
         assert self.params is not None, "filter is None"
-        if rm_delay:
-            raise NotImplementedError("rm_delay is not used by the samplers")
         squeeze = x.dim() == 1
         x2 = (x[None] if squeeze else x).float().contiguous()
-        if self._conv is None or self._conv.n != x2.shape[1]:
-            self._conv = RirConv(self.params.to(x2.device), x2.shape[1], x2.device)
+        key = (x2.shape[1], bool(rm_delay))
+        if self._conv is None or self._conv_key != key:
+            h = self.params.to(x2.device)
+            if rm_delay:                                   # reverb_utils.py:27-28: start at the strongest tap
+                h = h[int(torch.argmax(h)):]
+            self._conv, self._conv_key = RirConv(h, x2.shape[1], x2.device), key
         y = self._conv.forward(x2)
         return y[0] if squeeze else y
 
+    def optim_fwd(self, Xden, Y):
+        """sum (A(Xden) - Y)^2 (:43-50)."""
+        d = self.degradation(Xden) if Xden.dim() == 2 else self.degradation(Xden)[None]
+        Y2 = (Y if Y.dim() == 2 else Y[None]).float().contiguous()
+        B = d.shape[0]
+        one = torch.ones(B, device=d.device)
+        e = ops.lincomb3(torch.empty_like(d), d.contiguous(), one, Y2, -one)
+        return ops.row_stats(e)[:, 1].sum().float()
+
+    # ---- transforms "just for computing STFT-based losses" (:52-84)
+    def _transforms(self, device):
+        if self._tf is None:
+            self._tf = OperatorSTFT(device)
+        return self._tf
+
+    @staticmethod
+    def _as_batch(x):
+        if x.dim() == 1:
+            return x[None]
+        if x.dim() == 2:
+            return x
+        raise ValueError("x must have shape (batch, samples) or (samples)")
+
     def apply_stft(self, x):
+        x2 = self._as_batch(x).float().contiguous()
+        return torch.view_as_complex(self._transforms(x2.device).apply_stft(x2))
+
+    def apply_istft(self, X, length=None):
+        if length is None:
+            raise ValueError("apply_istft needs `length` (the reference warns that istft may crash without it)")
+        X3 = X if X.dim() == 3 else X[None]
+        Xr = torch.view_as_real(X3.to(torch.complex64).contiguous()).contiguous()
+        x = self._transforms(Xr.device).apply_istft(Xr, int(length))
+        return x if X.dim() == 3 else x[0]
+
+    def stft(self, x):
         x2 = (x[None] if x.dim() == 1 else x).float().contiguous()
-        if self._stft is None:
-            self._stft = LossSTFT(x2.device)
-        return torch.view_as_complex(self._stft.forward(x2))
+        X = torch.view_as_complex(self._transforms(x2.device).stft(x2))
+        return X[0] if x.dim() == 1 else X
+
+    def istft(self, X, length=None):
+        X3 = X if X.dim() == 3 else X[None]
+        Xr = torch.view_as_real(X3.to(torch.complex64).contiguous()).contiguous()
+        x = self._transforms(Xr.device).istft(Xr, length)
+        return x if X.dim() == 3 else x[0]
 
     def get_time_RIR(self):
         return self.params
@@ -146,6 +197,21 @@ class SubbandFiltering(Operator):
         ops.stft_analysis(xp, self._eng.cons_ana, self.hop_length, frames, frames, out)
         X = torch.view_as_complex(out)
         return X[0] if squeeze else X
+
+    def istft(self, X, length=None):
+        """torch.istft with the same window, NOT normalised (:76-77); length None: hop * (frames - 1) samples."""
+        X3 = X if X.dim() == 3 else X[None]
+        Xr = torch.view_as_real(X3.to(torch.complex64).contiguous()).contiguous()
+        B, _, frames, _ = Xr.shape
+        n = self.hop_length * (frames - 1) if length is None else int(length)
+        if n > self.hop_length * (frames - 1):
+            # beyond the last frame the zero-padded window leaves no overlap-add envelope: torch.istft refuses too
+            raise RuntimeError(f"istft: {frames} frames cannot produce {n} samples (window overlap add min: 1)")
+        fr = torch.empty(B, frames, self.win_length, device=Xr.device)
+        ops.stft_synthesis(Xr, self._eng.cons_syn, frames, fr)
+        x = ops.ola_gather(fr, self.hop_length, self.n_fft // 2, n, torch.empty(B, n, device=Xr.device),
+                           tab=self._eng._inv_env(frames))
+        return x if X.dim() == 3 else x[0]
 
     def subband_filtering(self, X, H):
         Xr = torch.view_as_real(X.to(torch.complex64).contiguous()).contiguous()
@@ -249,16 +315,41 @@ class BlindSubbandFiltering(SubbandFiltering):
         st["weights"].copy_(self.params[1].detach().reshape(1, 25))
         st["phases"].copy_(phases.detach().reshape(1, 513, 100))
 
+    def compute_direct_path_mag_correction(self):
+        """|STFT(h)|[:, 1:] of h = (win_length / (2 hop)) * delta (:206-210)."""
+        h = torch.zeros((self.length_rir,), device=self.device)
+        h[0] = 1 * (self.win_length / (self.hop_length * 2))
+        self.direct_path_mag_correction = self.stft(h)[:, 1:].abs()
+
+    def correct_OLA(self, A, inverse=False):
+        """Divide (inverse: multiply) the first win/hop - 1 frames by sum(w) / sum(w[(K - k) hop:]), in place
+        (:212-222)."""
+        corr = self._eng.tabs["corr"]
+        K = corr.numel()
+        if inverse:
+            A[:, :K] *= corr
+        else:
+            A[:, :K] /= corr
+        return A
+
     def design_filter(self, correct_OLA=True):
         """Magnitudes A (513,100): exponential decays per band -> log-linear interpolation over frequency -> OLA
         correction of the first frames + direct-path magnitude (:224-251)."""
-        if not correct_OLA:
-            raise NotImplementedError("design_filter(correct_OLA=False) is not used on the hot path")
         self._load_state(self.params_phases[0])
         bf = self._eng.buf
         ops.blind_design_fwd(self._eng.state["decays"], self._eng.state["weights"], self._eng.state["phases"],
                              self._eng.tabs, bf["A"], bf["H0"])
-        return bf["A"][0].clone()
+        A = bf["A"][0].clone()
+        if not correct_OLA:      # the kernel fuses the correction: take it back out of the first frames
+            A = self.correct_OLA(A - self.direct_path_mag_correction, inverse=True) + self.direct_path_mag_correction
+        return A
+
+    def design_subband_filter(self):
+        """Band magnitudes interpolated over frequency, before the +1e-6 floor, the OLA correction and the direct-path
+        magnitude (:224-239)."""
+        H2 = self.design_filter(correct_OLA=False) - self.direct_path_mag_correction - 1e-6
+        assert not torch.isnan(H2).any(), "decay is Nan"
+        return H2
 
     def get_noise(self, noise=None):
         if noise is None:

@@ -93,6 +93,19 @@ class Sampler:
         for st in self._streams[:ns]:
             main.wait_stream(st)
 
+    # ---- interface (Sampler.py:23-37: "abstract" placeholders that return None in the base class) -----
+    def predict(self, *args, **kwargs):
+        return None
+
+    def predict_unconditional(self, *args, **kwargs):
+        return None
+
+    def predict_conditional(self, *args, **kwargs):
+        return None
+
+    def step(self, *args, **kwargs):
+        return None
+
     # ---- schedule (Sampler.py:39-56) -----------------------------------------------------------------
     def create_schedule(self, sigma_min=None, sigma_max=None, rho=None, T=None):
         sigma_min = self.sde_hp.sigma_min if sigma_min is None else sigma_min
@@ -154,6 +167,10 @@ class Sampler:
         bad = (~torch.isfinite(st).all(dim=1)).nonzero().flatten().tolist()
         if bad:
             raise FloatingPointError(f"{what} is NaN/Inf for utterance(s) {bad} of the batch")
+
+
+class NoSampler(Sampler):
+    """Sampler.py:74-86: the do-nothing sampler some tester configurations name (every method returns None)."""
 
 
 def _vec(v, B, device):

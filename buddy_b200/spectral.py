@@ -5,6 +5,7 @@ FFT twiddles — and the four linear maps the network and the likelihood need, e
               centre/reflect, 256 bins, frames zero-padded to a multiple of 16, inverse over ALL padded frames.
   LossSTFT  — operator.apply_stft (testing/operators/subband_filtering.py:41-52,79-80 == reverb.py:54-65,83-84):
               right-pad 512, n_fft 1024 with Hann(512)||0(512), hop 128, centre/constant, / sqrt(sum w^2).
+  OperatorSTFT — the operators' own stft / istft / apply_stft / apply_istft (API-compatible operator classes).
   RirConv   — fast_apply_RIR (utils/reverb_utils.py:25-60).
 """
 import math
@@ -150,6 +151,73 @@ class LossSTFT:
         ops.stft_synthesis(G, self.ana, F, fr)
         out = torch.empty(B, n, device=G.device)
         return ops.ola_gather(fr, self.HOP, self.N_FFT // 2, n, out, scale_b=scale_b)
+
+
+class OperatorSTFT:
+    """The STFT pair both degradation operators define for themselves (testing/operators/reverb.py:54-84 ==
+    subband_filtering.py:41-80): n_fft 1024 with Hann(512)||0(512), hop 128, centre / constant padding.
+
+      stft / istft              — torch.stft / torch.istft with that window, not normalised (:79-84);
+      apply_stft / apply_istft  — right-pad 512 and divide by sqrt(sum w^2) / multiply back and drop the 256-sample
+                                  delay (:41-65).
+    Spectra are fp32 [B, 513, frames, 2] (= view_as_real of the reference's complex tensors)."""
+    N_FFT, WIN, HOP, BINS = 1024, 512, 128, 513
+
+    def __init__(self, device):
+        self.device = device
+        w = torch.hann_window(self.WIN, dtype=torch.float64)
+        self.norm = math.sqrt(float((w ** 2).sum()))
+        aw = irfft_weights(self.BINS, self.N_FFT)
+        one = torch.ones(self.BINS, dtype=torch.float64)
+        self.ana = ops.FftMat(one, w, device)                    # stft
+        self.ana_n = ops.FftMat(one / self.norm, w, device)      # apply_stft
+        self.syn = ops.FftMat(aw, w, device)                     # istft (irfft * window)
+        self.syn_n = ops.FftMat(aw * self.norm, w, device)       # apply_istft: X * sqrt(sum w^2) first
+        self._env = {}
+
+    def _inv_env(self, frames):
+        """1 / OLA(window^2) over `frames` frames, padded-signal coordinates (torch.istft's envelope)."""
+        if frames not in self._env:
+            total = (frames - 1) * self.HOP + self.WIN
+            w2 = torch.hann_window(self.WIN, dtype=torch.float64) ** 2
+            env = torch.zeros(total, dtype=torch.float64)
+            for t in range(frames):
+                env[t * self.HOP:t * self.HOP + self.WIN] += w2
+            self._env[frames] = torch.where(env > 1e-11, 1 / env, torch.zeros_like(env)).float().to(self.device)
+        return self._env[frames]
+
+    def _analysis(self, x, mat, right_pad):
+        B, n = x.shape
+        frames = 1 + (n + right_pad) // self.HOP
+        total = (frames - 1) * self.HOP + self.WIN
+        xp = torch.empty(B, total, device=x.device)
+        ops.pad_signal(x, self.N_FFT // 2, total, 0, xp)
+        out = torch.empty(B, self.BINS, frames, 2, device=x.device)
+        return ops.stft_analysis(xp, mat, self.HOP, frames, frames, out)
+
+    def _synthesis(self, X, mat, skip, n):
+        B, _, frames, _ = X.shape
+        if skip + n > (frames - 1) * self.HOP + self.WIN:
+            # beyond the last frame the zero-padded window leaves no overlap-add envelope: torch.istft refuses too
+            raise RuntimeError(f"istft: {frames} frames cannot produce {n} samples (window overlap add min: 1)")
+        fr = torch.empty(B, frames, self.WIN, device=X.device)
+        ops.stft_synthesis(X, mat, frames, fr)
+        out = torch.empty(B, n, device=X.device)
+        return ops.ola_gather(fr, self.HOP, skip, n, out, tab=self._inv_env(frames))
+
+    def stft(self, x):
+        return self._analysis(x, self.ana, 0)
+
+    def apply_stft(self, x):
+        return self._analysis(x, self.ana_n, self.WIN)
+
+    def istft(self, X, length=None):
+        """length None: hop * (frames - 1) samples, as torch.istft."""
+        n = self.HOP * (X.shape[2] - 1) if length is None else int(length)
+        return self._synthesis(X, self.syn, self.N_FFT // 2, n)
+
+    def apply_istft(self, X, length):
+        return self._synthesis(X, self.syn_n, self.N_FFT // 2 + self.WIN // 2, int(length))
 
 
 class RirConv:

@@ -355,3 +355,49 @@ def test_checkpoint_loader_strategies(tmp_path):
     assert info["strategy"] == 4 and torch.equal(net.state_dict()["all_modules.1.weight"], ema["all_modules.1.weight"])
     with pytest.raises(CheckpointError):
         load_checkpoint({"it": 3}, mk(), log=lambda *a: None)
+
+
+def test_sampler_placeholders_and_function_mirrors_without_gpu():
+    """Sampler base-class placeholders / NoSampler (testing/Sampler.py:23-37,74-86) return None; `get_loss`
+    (utils/losses.py:17-95) resolves names like the reference; operator hyper-parameters outside the kernels' geometry
+    are refused at construction."""
+    import torch
+    from buddy_b200 import functional as F
+    from buddy_b200.edm import EDM
+    from buddy_b200.operators import RIROperator
+    from buddy_b200.samplers import NoSampler, Sampler
+    from oracle import ref_harness as rh
+    edm = EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10))
+
+    class _Net(torch.nn.Module):
+        pass
+    for cls in (Sampler, NoSampler):
+        s = cls(_Net(), edm, rh.make_args("unconditional", 3))
+        assert s.predict() is None and s.predict_unconditional((1, 8), "cpu") is None
+        assert s.predict_conditional(None, None) is None and s.step(None, 0, 0, 0) is None
+        assert s.T == 3 and s.step_counter == 0 and len(s.create_schedule()) == 4
+    assert F.get_loss(rh.AD(name="none")) is None
+    ok = rh.AD(name="l2_comp_stft_summean", weight=512, compression_factor=0.667)
+    assert callable(F.get_loss(ok)) and callable(F.get_loss(rh.AD(name="hybrid", loss_1=ok, loss_2=ok)))
+    for bad in (rh.AD(name="l2_sum"), rh.AD(name="l2_stft_sum"),
+                rh.AD(name="l2_comp_stft_sum", compression_factor=0.5, freq_weighting="sqrt")):
+        with pytest.raises(NotImplementedError):
+            F.get_loss(bad)
+    with pytest.raises(AssertionError):                   # losses.py:49: compression factor outside (0, 1]
+        F.get_loss(rh.AD(name="l2_comp_stft_sum", compression_factor=1.5))
+
+    class _Op:
+        n_fft, win_length, hop_length = 2048, 512, 128
+    with pytest.raises(NotImplementedError):
+        F.get_loss(ok, operator=_Op())
+    with pytest.raises(NotImplementedError):              # reverb.py:29
+        RIROperator(rh.AD(NFFT=1024, win_length=512, hop=128, window="hamming"))
+    with pytest.raises(NotImplementedError):
+        RIROperator(rh.AD(NFFT=2048, win_length=512, hop=128, window="hann"))
+    op = RIROperator(rh.op_hp(), time_kernel_size=10)
+    with pytest.raises(AssertionError):                   # reverb.py:34 "filter is None"
+        op.degradation(torch.zeros(1, 16))
+    with pytest.raises(ValueError):                       # reverb.py:61
+        op.apply_stft(torch.zeros(1, 1, 16))
+    with pytest.raises(ValueError):
+        F.fast_apply_RIR(torch.zeros(16), torch.zeros(4))
