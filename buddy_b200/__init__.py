@@ -13,7 +13,8 @@ _EXPORTS = {
     "BlindSubbandFiltering": "operators",
     "BatchedDereverb": "tester", "AsyncWavWriter": "tester", "PairedWavSet": "tester",
     "load_checkpoint": "checkpoint",
-    "fast_apply_RIR": "functional", "get_loss": "functional",
+    "fast_apply_RIR": "functional", "get_loss": "functional", "hilbert": "functional",
+    "minimum_phase_version": "functional",
 }
 
 

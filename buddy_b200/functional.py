@@ -1,6 +1,9 @@
 """Function-level mirrors of the reference helpers the hot path is written with
-(utils/reverb_utils.py:25-60 `fast_apply_RIR`, utils/losses.py:17-95 `get_loss`), for code that calls them directly
-instead of going through the samplers.  CUDA tensors only; every function is a sequence of buddy_b200 kernels."""
+(utils/reverb_utils.py:3-60 `hilbert`, `minimum_phase_version`, `fast_apply_RIR`; utils/losses.py:17-95 `get_loss`),
+for code that calls them directly instead of going through the samplers.  CUDA tensors only; every function is a
+sequence of buddy_b200 kernels."""
+import math
+
 import torch
 
 from . import ops
@@ -26,6 +29,66 @@ def fast_apply_RIR(y, filter, rm_delay=False, zero_pad=False):
         h = h[int(torch.argmax(h)):]
     y2 = y.float().contiguous()
     return RirConv(h, y2.shape[1], y2.device).forward(y2)
+
+
+# The blind operator's filter projection is the only caller of `minimum_phase_version` (subband_filtering.py:341): one
+# length, 12 928 = 12 800 + 128 samples, zero-padded to 25 856 = 101 * 256 points — the size `buddy_fft_mixed` implements.
+_MP_T, _MP_N1 = 12928, 101
+_tw512 = {}
+
+
+def _twiddles(device):
+    if device not in _tw512:
+        k = torch.arange(256, dtype=torch.float64)
+        _tw512[device] = torch.stack([torch.cos(2 * math.pi * k / 512), -torch.sin(2 * math.pi * k / 512)],
+                                     -1).float().to(device)
+    return _tw512[device]
+
+
+def hilbert(h):
+    """ifft(w * fft(h)), w = 2 on the first half of the bins, 0 on the second (reverb_utils.py:3-7); last dimension
+    25 856 (real or complex input), complex64 result."""
+    N = h.shape[-1]
+    if N != 2 * _MP_T:
+        raise NotImplementedError(f"hilbert: the mixed-radix FFT kernel implements {2 * _MP_T} points, got {N}")
+    lead = h.shape[:-1]
+    real = not torch.is_complex(h)
+    x = (h.reshape(-1, N).float() if real else torch.view_as_real(h.reshape(-1, N).to(torch.complex64))).contiguous()
+    B, dev = x.shape[0], x.device
+    work, c1, c2 = (torch.empty(B, N, 2, device=dev) for _ in range(3))
+    ops.fft_mixed(x, real, work, c1, _MP_N1, -1, _twiddles(dev))
+    ops.minphase_pw(1, B, N, _MP_T, c0=c1, oc=c2, scale_inv_n=True)
+    ops.fft_mixed(c2, False, work, c1, _MP_N1, +1, _twiddles(dev))
+    return torch.view_as_complex(c1).reshape(*lead, N)
+
+
+def minimum_phase_version(h):
+    """Minimum-phase-lag version of a time-domain RIR through the real cepstrum (reverb_utils.py:9-23): pad to twice
+    the length, |H| e^{-j Im hilbert(log(|H| + 1e-8))}, back, keep the original length.  Last dimension 12 928 (the
+    length the blind operator's `cons` uses)."""
+    T = h.shape[-1]
+    if T != _MP_T:
+        raise NotImplementedError(f"minimum_phase_version: the CUDA chain implements {_MP_T} samples, got {T}")
+    lead = h.shape[:-1]
+    hb = h.reshape(-1, T).float()
+    B, N, dev = hb.shape[0], 2 * T, hb.device
+    tw = _twiddles(dev)
+    u = torch.zeros(B, N, device=dev)
+    u[:, :T] = hb
+    work, Hf, c1, c2 = (torch.empty(B, N, 2, device=dev) for _ in range(4))
+    m, phi = torch.empty(B, N, device=dev), torch.empty(B, N, device=dev)
+    ops.fft_mixed(u, True, work, Hf, _MP_N1, -1, tw)
+    ops.minphase_pw(0, B, N, T, c0=Hf, or0=m, oc=c1)
+    ops.fft_mixed(c1, False, work, c2, _MP_N1, -1, tw)
+    ops.minphase_pw(1, B, N, T, c0=c2, oc=c1)
+    ops.fft_mixed(c1, False, work, c2, _MP_N1, +1, tw)
+    ops.minphase_pw(2, B, N, T, c0=c2, r0=m, or0=phi, oc=c1)
+    ops.fft_mixed(c1, False, work, c2, _MP_N1, +1, tw)
+    out = torch.empty(B, T, device=dev)
+    # stage 3 writes the blind operator's direct-path constant into sample 0 (fix_direct_path): put the sample back
+    ops.minphase_pw(3, B, N, T, c0=c2, r0=torch.zeros(1, device=dev), or0=out)
+    out[:, 0] = c2[:, 0, 0] / N
+    return out.reshape(*lead, T)
 
 
 class _CompStftLoss(torch.autograd.Function):

@@ -401,3 +401,7 @@ def test_sampler_placeholders_and_function_mirrors_without_gpu():
         op.apply_stft(torch.zeros(1, 1, 16))
     with pytest.raises(ValueError):
         F.fast_apply_RIR(torch.zeros(16), torch.zeros(4))
+    with pytest.raises(NotImplementedError):              # the mixed-radix FFT chain exists at the blind operator's size
+        F.minimum_phase_version(torch.zeros(4096))
+    with pytest.raises(NotImplementedError):
+        F.hilbert(torch.zeros(2, 8192))

@@ -266,6 +266,20 @@ def test_api_operator_remaining_methods_match_reference(rh):
         # function-level helpers
         assert rel(F.fast_apply_RIR(x, h), fast_apply_RIR(x, h)) < 1e-5
         assert rel(F.fast_apply_RIR(x, h, rm_delay=True, zero_pad=True), fast_apply_RIR(x, h, rm_delay=True, zero_pad=True)) < 1e-5
+    # minimum-phase helpers (reverb_utils.py:3-23) at the one size the blind operator uses them with
+    from utils.reverb_utils import hilbert, minimum_phase_version
+    hm = (randn(710, 2, 12928) * torch.exp(-torch.arange(12928) / 2000.0)).cuda()
+    with torch.no_grad():
+        got = F.minimum_phase_version(hm)                  # batched; the reference function handles 1-D input only
+        for b in range(2):
+            assert rel(got[b], minimum_phase_version(hm[b])) < 1e-4
+        assert rel(F.minimum_phase_version(hm[0]), got[0]) < 1e-6
+        xr = randn(711, 2, 25856).cuda()
+        assert rel(cplx(F.hilbert(xr)), cplx(hilbert(xr))) < 1e-5
+        xc = torch.complex(randn(712, 25856), randn(713, 25856)).cuda()
+        assert rel(cplx(F.hilbert(xc)), cplx(hilbert(xc))) < 1e-5
+    with pytest.raises(NotImplementedError):
+        F.minimum_phase_version(hm[..., :4096])
     # get_loss: value and gradient w.r.t. x_hat, every supported normalisation and a hybrid of two
     x_hat = (x + 0.01 * randn(702, 2, NS).cuda())
     cfgs = [rh.AD(name=n, weight=w, compression_factor=0.667) for n, w in
@@ -285,7 +299,7 @@ def test_api_operator_remaining_methods_match_reference(rh):
         xo = x_hat.clone().requires_grad_(True)
         lo = our_fn(x, xo)
         (go,) = torch.autograd.grad(lo, xo)
-        print(f"\n[get_loss {cfg.name}] {float(lo):.6g} vs reference {float(lr):.6g}; gradient {rel(go, gr):.2e}")
+        print(f"\n[get_loss {cfg.name}] {lo.item():.6g} vs reference {lr.item():.6g}; gradient {rel(go, gr):.2e}")
         assert abs(float(lo) - float(lr)) < 1e-4 * abs(float(lr)) and rel(go, gr) < 1e-3
     assert F.get_loss(rh.AD(name="none")) is None
     with pytest.raises(NotImplementedError):
