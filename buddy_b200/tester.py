@@ -205,20 +205,22 @@ class BatchedDereverb:
         if restore is None:
             # one run seed for the whole call: utterance i keeps stream seed + first + i whatever bucket it lands in
             self.sampler.seed_base = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
-        for idx in length_buckets([y.shape[-1] for y in ys], self.max_batch):
-            y = torch.stack([ys[i].float() for i in idx])
-            m = max(rirs[i].shape[-1] for i in idx)
-            h = torch.zeros(len(idx), m, device=y.device)
-            for r, i in enumerate(idx):
-                h[r, :rirs[i].shape[-1]] = rirs[i].float()      # zero tail: the same convolution
-            op = RIROperator(time_kernel_size=m)
-            op.update_params(h)
-            self.sampler.utterance_ids = [first + i for i in idx]   # noise stream of utterance i = seed_base + first + i
-            out = self.sampler.predict_conditional(y, op, shape=tuple(y.shape))
-            for r, i in enumerate(idx):
-                preds[i] = out[r]
-        self.sampler.utterance_ids = None
-        self.sampler.seed_base = restore
+        try:
+            for idx in length_buckets([y.shape[-1] for y in ys], self.max_batch):
+                y = torch.stack([ys[i].float() for i in idx])
+                m = max(rirs[i].shape[-1] for i in idx)
+                h = torch.zeros(len(idx), m, device=y.device)
+                for r, i in enumerate(idx):
+                    h[r, :rirs[i].shape[-1]] = rirs[i].float()      # zero tail: the same convolution
+                op = RIROperator(time_kernel_size=m)
+                op.update_params(h)
+                self.sampler.utterance_ids = [first + i for i in idx]   # noise stream of utterance i = seed_base + first + i
+                out = self.sampler.predict_conditional(y, op, shape=tuple(y.shape))
+                for r, i in enumerate(idx):
+                    preds[i] = out[r]
+        finally:                                  # a failed bucket (NaN guard, bad input) must not leave the sampler pinned
+            self.sampler.utterance_ids = None
+            self.sampler.seed_base = restore
         return preds
 
     def test_dereverberation(self, test_set, out_dir, mode="informed_dereverberation", blind=False, device="cuda",
@@ -297,18 +299,20 @@ class BatchedDereverb:
         restore = self.sampler.seed_base
         if restore is None:
             self.sampler.seed_base = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
-        for idx in length_buckets([y.shape[-1] for y in ys], self.max_batch):
-            y = torch.stack([ys[i].float() for i in idx])
-            op = self.init_blind_operator(len(idx), y.device, generator)
-            self.sampler.utterance_ids = [first + i for i in idx]
-            out = self.sampler.predict_conditional(y, op, shape=tuple(y.shape), blind=True)
-            be = op._engine
-            Hr = torch.view_as_real(op.H_batch.contiguous()).contiguous()
-            be.init_state(len(idx), op.params_batch[0], op.params_batch[1], op.params_batch[2], op.H_batch)
-            be.select(slice(0, len(idx)))
-            rir = be.get_time_RIR(Hr)
-            for r, i in enumerate(idx):
-                preds[i], rirs[i] = out[r], rir[r]
-        self.sampler.utterance_ids = None
-        self.sampler.seed_base = restore
+        try:
+            for idx in length_buckets([y.shape[-1] for y in ys], self.max_batch):
+                y = torch.stack([ys[i].float() for i in idx])
+                op = self.init_blind_operator(len(idx), y.device, generator)
+                self.sampler.utterance_ids = [first + i for i in idx]
+                out = self.sampler.predict_conditional(y, op, shape=tuple(y.shape), blind=True)
+                be = op._engine
+                Hr = torch.view_as_real(op.H_batch.contiguous()).contiguous()
+                be.init_state(len(idx), op.params_batch[0], op.params_batch[1], op.params_batch[2], op.H_batch)
+                be.select(slice(0, len(idx)))
+                rir = be.get_time_RIR(Hr)
+                for r, i in enumerate(idx):
+                    preds[i], rirs[i] = out[r], rir[r]
+        finally:
+            self.sampler.utterance_ids = None
+            self.sampler.seed_base = restore
         return preds, rirs

@@ -405,3 +405,37 @@ def test_sampler_placeholders_and_function_mirrors_without_gpu():
         F.minimum_phase_version(torch.zeros(4096))
     with pytest.raises(NotImplementedError):
         F.hilbert(torch.zeros(2, 8192))
+
+
+def test_front_end_restores_the_sampler_after_a_failed_bucket():
+    """BatchedDereverb pins `seed_base` / `utterance_ids` for the duration of a call; a bucket that raises (NaN guard,
+    bad input) must hand the sampler back as it was."""
+    import torch
+    from buddy_b200.tester import BatchedDereverb
+    from oracle import ref_harness as rh
+
+    class _Sampler:
+        args = rh.make_args("informed", 3)
+        seed_base, utterance_ids, utterance_offset = None, None, 0
+        seen = []
+
+        def predict_conditional(self, y, op, shape=None, blind=False):
+            self.seen.append((self.seed_base, list(self.utterance_ids), tuple(y.shape), tuple(op.params.shape)))
+            if y.shape[1] == 24:
+                raise FloatingPointError("utterance 0 is NaN")
+            return y.clone()
+
+    s = _Sampler()
+    fe = BatchedDereverb(s, max_batch=2)
+    ys = [torch.zeros(16), torch.zeros(16), torch.zeros(16), torch.zeros(24)]
+    rirs = [torch.ones(3), torch.ones(5), torch.ones(4), torch.ones(2)]
+    with pytest.raises(FloatingPointError):
+        fe.informed(ys, rirs)
+    assert s.seed_base is None and s.utterance_ids is None
+    # buckets by exact length, chunks of max_batch, one run seed for the whole call, RIRs zero-padded per bucket
+    assert [(ids, ys_, hs) for _, ids, ys_, hs in s.seen] == [([0, 1], (2, 16), (2, 5)), ([2], (1, 16), (1, 4)),
+                                                             ([3], (1, 24), (1, 2))]
+    assert len({seed for seed, *_ in s.seen}) == 1 and s.seen[0][0] is not None
+    s.seed_base = 77
+    out = fe.informed(ys[:3], rirs[:3])
+    assert len(out) == 3 and s.seed_base == 77 and s.seen[-1][0] == 77
