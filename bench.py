@@ -455,8 +455,8 @@ def run_ours(args):
         line["config"]["step_definition"] = "one Euler sampler step over the batch = 1 network fwd+VJP + 10 operator updates"
         line["config"]["T"], line["config"]["order"], line["config"]["evals_per_utterance"] = 60, 1, 60
     if world == 1 and not args.no_cpu_baseline and not blind and not long_form:
-        line["cpu_baseline"] = cpu_baseline_subprocess(1, 0)
-        line["cpu_baseline"]["sample"] += "; ONE step, no warm-up"
+        line["cpu_baseline"] = cpu_baseline_subprocess(2, 1)
+        line["cpu_baseline"]["sample"] += "; mean of 2 steps after 1 warm-up step (about 10-15 s of CPU work)"
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
