@@ -100,7 +100,7 @@ def ola_gather(fr, hop, off, n_out, out, tab=None, scale_b=None):
     v = buf[:, off:off + n_out]
     if scale_b is not None:
         v = v * scale_b[:, None]
-    out.copy_(v)
+    out[:, :n_out].copy_(v)            # `out` may be a wider row (the kernel takes its leading dimension)
     return out
 
 
@@ -163,7 +163,7 @@ def fft_mixed(x, in_real, work, out, N1, sign, tw512):
 
 
 def minphase_pw(mode, B, N, T, c0=None, c1=None, r0=None, r1=None, oc=None, or0=None, or1=None, scale_inv_n=False):
-    """blind.cu `minphase_pw_kernel`, forward stages 0-3."""
+    """blind.cu `minphase_pw_kernel`: pointwise stages of minimum_phase_version (0-3) and of its backward (4-7)."""
     invN = 1.0 / N
     if mode == 0:      # m = |Hf|, Lc = (log(m + 1e-8), 0)
         m = torch.view_as_complex(c0).abs()
@@ -182,10 +182,111 @@ def minphase_pw(mode, B, N, T, c0=None, c1=None, r0=None, r1=None, oc=None, or0=
     elif mode == 3:    # hm = Re/N for k < T, sample 0 := r0[0]
         or0.copy_(c0[:, :T, 0] * invN)
         or0[:, 0] = r0[0]
+    elif mode == 4:    # backward start: G_z = dh2[k] for 1 <= k < T else 0
+        or0.zero_()
+        or0[:, 1:T] = r0[:, 1:T]
+    elif mode == 5:    # G_E = raw/N; t = e^{-j phi} G_E; g_m1 = Re t; G_c = (0, -m Im t)      (r0 = m, r1 = phi)
+        gx, gy = c0[..., 0] * invN, c0[..., 1] * invN
+        cs, sn = torch.cos(r1), torch.sin(r1)
+        tr, ti = cs * gx + sn * gy, cs * gy - sn * gx
+        or0.copy_(tr)
+        oc[..., 0] = 0
+        oc[..., 1] = -r0 * ti
+    elif mode == 6:    # G_L = Re(raw3); g_m = g_m1 + G_L/(m + 1e-8); G_Hf = g_m * Hf / m   (r0 = m, r1 = g_m1, c1 = Hf)
+        gm = r1 + c0[..., 0] / (r0 + 1e-8)
+        ok = r0 > 0
+        safe = torch.where(ok, r0, torch.ones_like(r0))
+        oc[..., 0] = torch.where(ok, gm * c1[..., 0] / safe, torch.zeros_like(gm))
+        oc[..., 1] = torch.where(ok, gm * c1[..., 1] / safe, torch.zeros_like(gm))
+    elif mode == 7:    # g_u = Re(raw4) -> [B][T]
+        or0.copy_(c0[:, :T, 0])
     else:
         raise NotImplementedError(mode)
 
 
+def _shift(Z, d):
+    """Z[..., t + d] with zeros outside the row."""
+    T = Z.shape[-1]
+    out = torch.zeros_like(Z)
+    if d >= 0:
+        if d < T:
+            out[..., :T - d] = Z[..., d:]
+    elif -d < T:
+        out[..., -d:] = Z[..., :T + d]
+    return out
+
+
+def subband_fir(a, h_or_dy, out, *, Nf, pre, mode, shared_h=False, accumulate=False):
+    """include/buddy_b200.h: mode 0 Y[t] = sum_n H[n] X[t+pre-n]; mode 1 dX[s] = sum_n conj(H[n]) dY[s-pre+n];
+    mode 2 dH[n] (+)= sum_t conj(X[t+pre-n]) dY[t].  Rows are [batch][F][T] complex (fp32 pairs)."""
+    A = torch.view_as_complex(a.contiguous()).to(torch.complex128)
+    Bc = torch.view_as_complex(h_or_dy.contiguous()).to(torch.complex128)
+    if mode in (0, 1):
+        acc = torch.zeros_like(A)
+        for n in range(Nf):
+            Hn = Bc[..., n][..., None]
+            acc += (Hn * _shift(A, pre - n)) if mode == 0 else (Hn.conj() * _shift(A, n - pre))
+        res = acc
+    else:
+        res = torch.stack([(_shift(A, pre - n).conj() * Bc).sum(-1) for n in range(Nf)], -1)
+    r = torch.view_as_real(res.to(torch.complex64))
+    if accumulate:
+        out += r
+    else:
+        out.copy_(r)
+    return out
+
+
+def _design(decays, weights, phases, tabs):
+    """(decays, weights, phases) -> (A [B][F][Nf], H0 = A e^{j phase} with a zero frame on each side), following
+    design_subband_filter / design_filter (subband_filtering.py:224-251) with the host-built tables."""
+    B, F, Nf = phases.shape
+    n = torch.arange(Nf, dtype=decays.dtype)
+    D = weights[:, :, None] * torch.exp(decays)[:, :, None] ** (-n[None, None, :])            # [B, 25, Nf]
+    D = torch.cat([torch.zeros(B, 1, Nf, dtype=D.dtype), D, torch.zeros(B, 1, Nf, dtype=D.dtype)], 1)  # 27 knots
+    L = torch.log(D + 1e-6)
+    k, fr = tabs["kidx"].long(), tabs["frac"].to(D.dtype)
+    A = torch.exp(L[:, k] + fr[None, :, None] * (L[:, k + 1] - L[:, k])) + 1e-6                # [B, F, Nf]
+    K = tabs["corr"].numel()
+    A = torch.cat([A[..., :K] / tabs["corr"].to(D.dtype), A[..., K:]], -1) + tabs["dpmag"].to(D.dtype)
+    H = torch.polar(A, phases.to(D.dtype))
+    H0 = torch.nn.functional.pad(torch.view_as_real(H), (0, 0, 1, 1))
+    return A, H0
+
+
+def blind_design_fwd(decays, weights, phases, tabs, A, H0):
+    a, h0 = _design(decays.double(), weights.double(), phases.double(), tabs)
+    A.copy_(a.float())
+    H0.copy_(h0.float())
+
+
+def blind_design_bwd(decays, weights, phases, A, tabs, G, dphases, ddecays, dweights):
+    """Gradients of <G, H0> w.r.t. the parameters (the analytic chain of blind.cu, here by autograd)."""
+    with torch.enable_grad():
+        d, w, p = (t.detach().double().requires_grad_(True) for t in (decays, weights, phases))
+        _, h0 = _design(d, w, p, tabs)
+        gd, gw, gp = torch.autograd.grad((h0 * G.double()).sum(), (d, w, p))
+    ddecays.copy_(gd.float())
+    dweights.copy_(gw.float())
+    dphases.copy_(gp.float())
+
+
+def adam_project(p, g, m, v, step, lr, beta1, beta2, eps, dmin, dmax, wmin, wmax):
+    """blind.cu `adam_project_kernel`: torch.optim.Adam (bias-corrected) + project_params clamps on the first 25
+    (decays) / next 25 (weights) entries of every row; NaN survives the clamp."""
+    bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+    m.copy_(m + (g - m) * (1.0 - beta1))
+    v.copy_(v * beta2 + (1.0 - beta2) * g * g)
+    new = p - (lr / bc1) * (m / (v.sqrt() / math.sqrt(bc2) + eps))
+    lo = torch.full_like(new, -float("inf"))
+    hi = torch.full_like(new, float("inf"))
+    lo[:, :25], hi[:, :25] = dmin, dmax
+    lo[:, 25:50], hi[:, 25:50] = wmin, wmax
+    p.copy_(torch.where(torch.isnan(new), new, torch.minimum(torch.maximum(new, lo), hi)))
+
+
 ALL = dict(pad_signal=pad_signal, reflect_fold=reflect_fold, dft_analysis=dft_analysis, dft_synthesis=dft_synthesis,
            fft_analysis=fft_analysis, fft_synthesis=fft_synthesis, ola_gather=ola_gather, lincomb3=lincomb3,
-           row_stats=row_stats, comp_loss=comp_loss, fftconv=fftconv, fft_mixed=fft_mixed, minphase_pw=minphase_pw)
+           row_stats=row_stats, comp_loss=comp_loss, fftconv=fftconv, fft_mixed=fft_mixed, minphase_pw=minphase_pw,
+           subband_fir=subband_fir, blind_design_fwd=blind_design_fwd, blind_design_bwd=blind_design_bwd,
+           adam_project=adam_project)

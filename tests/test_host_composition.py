@@ -33,6 +33,9 @@ def emu(monkeypatch):
     import emulated_kernels as ek          # tests/ is on sys.path (pytest rootdir import mode)
     for name, fn in ek.ALL.items():
         monkeypatch.setattr(ops, name, fn)
+    # BlindEngine keys its scratch buffers by (micro-batch size, CUDA stream): one "stream" here
+    import types
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=0))
     return ops
 
 
@@ -152,3 +155,190 @@ def test_rir_operator_and_function_mirrors(emu):
         assert rel(got[b], oop.minimum_phase(hm[b])) < 1e-5
     z = randn(14, 25856)
     assert rel(torch.view_as_real(F.hilbert(z)), torch.view_as_real(oop.hilbert(z))) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Sampler glue on the CPU: the product samplers with the spectral entry points replaced
+# as above and the network ENGINE replaced by a double that evaluates the oracle network (forward + data-gradient by
+# autograd) — everything else is the product's own host code: schedule, gamma, stochastic step, EDM scalars, STFT
+# adjoint chain around the engine, likelihood-score normalisation, Heun correction, magnitude constraint, what
+# predict*() returns.  Expected values: the fixtures written by the UNMODIFIED reference (oracle/make_golden*.py).
+# ------------------------------------------------------------------------------------------------------------------
+class _OracleEngine:
+    """Same call surface as buddy_b200.engine.Engine.forward / .vjp on [B, 256, frames, 2] spectrograms."""
+
+    def __init__(self, sd):
+        self.sd = sd
+
+    def forward(self, spec, time_cond, save=False, graph=False):
+        with torch.enable_grad():
+            s = spec.detach().clone().requires_grad_(bool(save))
+            out = onet.ncsnpp_forward(self.sd, torch.view_as_complex(s)[:, None], time_cond)
+            out = torch.view_as_real(out[:, 0].contiguous())
+        return out.detach(), ((s, out) if save else None)
+
+    def vjp(self, ctx, dspec):
+        s, out = ctx
+        (g,) = torch.autograd.grad(out, s, dspec)
+        return g
+
+
+@pytest.fixture(scope="module")
+def glue_net():
+    from buddy_b200.ncsnpp import NCSNppTime
+    from buddy_b200.spectral import NetSTFT
+    from oracle.weights import make_state_dict
+    sd = make_state_dict(0)
+
+    class _Net(NCSNppTime):
+        def engine(self):
+            return self._double
+
+        def stft_engine(self):
+            return self._cpu_stft
+
+    net = _Net(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    net._double, net._cpu_stft = _OracleEngine(sd), NetSTFT("cpu")
+    return net.eval()
+
+
+def _edm():
+    from buddy_b200.edm import EDM
+    return EDM("ve_karras", dict(sigma_data=0.05, sigma_min=1e-5, sigma_max=10, rho=10))
+
+
+def _gold(name):
+    import os
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", name), weights_only=False)
+
+
+def test_sampler_glue_unconditional_vs_reference_fixture(emu, glue_net):
+    from buddy_b200.samplers import EulerHeunSampler
+    from oracle import ref_harness as rh
+    g = _gold("sampler_uncond_T3.pt")
+    s = EulerHeunSampler(glue_net, _edm(), rh.make_args("unconditional", g["T"]))
+    s.noise_source = iter([randn(g["noise_seed0"] + i, 1, g["n"]) for i in range(g["T"] + 1)])
+    x = s.predict_unconditional((1, g["n"]), "cpu")
+    assert rel(x, g["x"]) < 1e-4
+    assert s.step_counter == g["T"] - 1
+
+
+@pytest.mark.parametrize("fixture,rescale", [("sampler_informed_T3.pt", False), ("sampler_informed_T2_rescale.pt", True)])
+def test_sampler_glue_informed_dps_vs_reference_fixture(emu, glue_net, fixture, rescale):
+    """Incl. order 2 + constraint_speech_magnitude (the rescale follows the FIRST evaluation of a step only,
+    EulerHeunSamplerDPS.py:128-129 vs :136-150)."""
+    from buddy_b200.operators import RIROperator
+    from buddy_b200.samplers import EulerHeunSamplerDPS
+    from oracle import ref_harness as rh
+    g = _gold(fixture)
+    s = EulerHeunSamplerDPS(glue_net, _edm(), rh.make_args("informed", g["T"], rescale=rescale))
+    s.noise_source = iter([randn(g["noise_seed0"] + i, 1, g["n"]) for i in range(g["T"] + 1)])
+    op = RIROperator()
+    op.update_params(g["h"])
+    with pytest.raises(RuntimeError):                     # the public entry point refuses CPU tensors: no fallback
+        s.predict_conditional(g["y"], op, shape=(1, g["n"]), blind=False)
+    # below the guard: exactly what predict_conditional does next (samplers.py, end of the class)
+    s.operator, s.y = op, g["y"].detach().float().contiguous()
+    s._bind_operator(op, s.y, False)
+    pred = s.predict((1, g["n"]), "cpu", False)
+    assert rel(pred, g["pred"]) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Blind operator host chain (SURVEY §8 a12-a17): buddy_b200.blind.BlindEngine — filter design -> consistency projection
+# (istft, minimum phase over 25 856-point FFTs, direct path, stft), sub-band degradation, both loss terms, the whole
+# backward chain, Adam + projection — over the stand-ins, against the oracle and the reference's own fixture.
+# ------------------------------------------------------------------------------------------------------------------
+def _blind_engine(g, n):
+    from buddy_b200.blind import BlindEngine
+    i = g["init"]
+    be = BlindEngine(n, "cpu")
+    be.init_state(1, i["decays"], i["weights"], i["phases"], i["H"])
+    be.select(slice(0, 1))
+    return be
+
+
+def test_blind_engine_forward_chain_vs_oracle(emu):
+    g = _gold("sampler_blind_T2.pt")
+    n, i = g["n"], g["init"]
+    be = _blind_engine(g, n)
+    H = torch.view_as_complex(be.update_H().contiguous())[0]
+    want = oop.design_H(i["decays"], i["weights"], i["phases"])
+    assert rel(torch.view_as_real(H), torch.view_as_real(want)) < 1e-4
+    assert rel(be.get_time_RIR()[0], oop.time_rir(want)) < 1e-4
+    x = g["s"][None] + 0.01 * randn(5, 1, n)
+    assert rel(be.degradation(x), oop.blind_degradation(x, want)) < 1e-4
+    # d rec / d x_den with the filter held fixed (EulerHeunSamplerDPS.py:61-69 through SubbandFiltering.degradation)
+    Y = be.loss_stft.forward(g["y"])
+    gx, loss = be.likelihood_grad(x, Y, 512.0, 0.667)
+    xr = x.clone().requires_grad_(True)
+    rec = oop.comp_loss(g["y"], oop.blind_degradation(xr, want.detach()), 512.0).sum()
+    (gw,) = torch.autograd.grad(rec, xr)
+    assert abs(float(loss[0]) - rec.item()) < 1e-4 * rec.item() and rel(gx, gw) < 1e-3
+
+
+def test_blind_operator_iteration_vs_reference_fixture(emu, monkeypatch):
+    """One operator iteration (update_H -> both losses -> backward chain -> Adam + projection): the loss values and
+    the gradients w.r.t. decays / weights / phases against the values the UNMODIFIED reference produced
+    (tests/golden/sampler_blind_T2.pt, `iter`), then the parameter update against torch.optim.Adam."""
+    g = _gold("sampler_blind_T2.pt")
+    n, it, i = g["n"], g["iter"], g["init"]
+    be = _blind_engine(g, n)
+    grads = []
+    inner = emu.adam_project
+    monkeypatch.setattr(emu, "adam_project", lambda p, gr, *a: (grads.append(gr.clone()), inner(p, gr, *a))[1])
+    x_probe = g["s"][None] + 0.01 * randn(it["x_probe_seed"], 1, n)
+    hp = dict(iters=1, lr=0.1, beta1=0.9, beta2=0.99, comp=0.667, w_rec=512.0, w_reg=2560.0, crop_max=1e9, crop_min=0.0)
+    be.optimize(x_probe, be.loss_stft.forward(g["y"]), float(it["t_op"]), lambda shape: randn(it["noise_seed"], *shape), hp)
+    rec, reg = (float(v[0]) for v in be.last_losses)
+    assert abs(rec - it["rec"].item()) < 1e-4 * it["rec"].item() and abs(reg - it["reg"].item()) < 1e-4 * it["reg"].item()
+    gd, gw, gp = grads
+    assert rel(gd, it["g_decays"]) < 1e-3 and rel(gw, it["g_weights"]) < 1e-3
+    assert rel(gp.reshape(513, 100), it["g_phases"]) < 1e-3
+    # the update itself: Adam's first step moves every element by lr * sign(g) (bias-corrected), then the clamps
+    ref = [i["decays"].clone().requires_grad_(True), i["weights"].clone().requires_grad_(True),
+           i["phases"].clone().requires_grad_(True)]
+    opt = torch.optim.Adam(ref, lr=0.1, betas=(0.9, 0.99))
+    for p_, g_ in zip(ref, (it["g_decays"], it["g_weights"], it["g_phases"])):
+        p_.grad = g_.clone()
+    opt.step()
+    d, w = oop.project_params(ref[0].detach(), ref[1].detach())
+    st = be.full
+    assert rel(st["decays"], d) < 1e-5 and rel(st["weights"], w) < 1e-5
+    # phases: elements whose gradient is at rounding level may step the other way (+-lr): compare where it is not
+    big = it["g_phases"].abs() > 1e-3 * it["g_phases"].abs().max()
+    assert (st["phases"][0][big] - ref[2].detach()[big]).abs().max() < 1e-4
+
+
+def test_sampler_glue_blind_dps_single_iteration_vs_oracle(emu, glue_net):
+    """T = 2 blind DPS through the product sampler (one operator update per step: no chaotic amplification, cf.
+    tests/test_gpu_blind.py) against the oracle's dps_blind; the estimated filter is written back into the operator."""
+    from buddy_b200.samplers import EulerHeunSamplerDPS
+    from oracle import ref_harness as rh
+    from oracle import sampler as osm
+    from oracle.weights import make_state_dict
+    g = _gold("sampler_blind_T2.pt")
+    T, n, i = 2, g["n"], g["init"]
+    step_noise = [randn(300 + k, 1, n) for k in range(T + 1)]
+    rir_noise = [randn(400 + k, 13824) for k in range(T)]
+    st = osm.BlindState(i["decays"], i["weights"], i["phases"], i["H"])
+    want = osm.dps_blind(make_state_dict(0), g["y"], st, T, step_noise, rir_noise, n_iter=1)
+    args = rh.make_args("blind", T)
+    args.tester.posterior_sampling.blind_hp["op_updates_per_step"] = 1
+    smp = EulerHeunSamplerDPS(glue_net, _edm(), args)
+    order = [step_noise[0]]
+    for k in range(T):
+        order += [step_noise[1 + k], rir_noise[k]]
+    smp.noise_source = iter(order)
+
+    class Op:
+        pass
+    op = Op()
+    op.params, op.params_phases, op.H = [i["decays"].clone(), i["weights"].clone()], [i["phases"].clone()], i["H"].clone()
+    smp.operator, smp.y = op, g["y"].detach().float().contiguous()
+    smp._bind_operator(op, smp.y, True)
+    pred = smp.predict((1, n), "cpu", True)
+    e, eH = rel(pred, want), rel(torch.view_as_real(op.H), torch.view_as_real(st.H.detach()))
+    print(f"\n[blind DPS T2, 1 op-iteration/step, host glue on CPU] pred {e:.2e} H {eH:.2e}")
+    assert e < 1e-3 and eH < 5e-3
+    assert rel(op.params[0], st.decays.detach()) < 1e-3 and rel(op.params[1], st.weights.detach()) < 1e-3
