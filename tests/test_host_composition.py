@@ -342,3 +342,33 @@ def test_sampler_glue_blind_dps_single_iteration_vs_oracle(emu, glue_net):
     print(f"\n[blind DPS T2, 1 op-iteration/step, host glue on CPU] pred {e:.2e} H {eH:.2e}")
     assert e < 1e-3 and eH < 5e-3
     assert rel(op.params[0], st.decays.detach()) < 1e-3 and rel(op.params[1], st.weights.detach()) < 1e-3
+
+
+def test_wpe_warm_start_host_side_vs_oracle(emu, monkeypatch):
+    """buddy_b200.wpe.WpeDereverb (EulerHeunSamplerDPS.py:32-54): the STFT pair around the solver — 512 / 128 periodic
+    Blackman window, `fading` padding, frame count, biorthogonal synthesis window — against oracle/wpe.py; the solver
+    entry point itself is stood in by the oracle's per-bin solver, so what is compared is the host composition."""
+    import numpy as np
+    from buddy_b200.wpe import WpeDereverb
+    from oracle import wpe as ow
+
+    def wpe_standin(Y, taps, delay, iterations, Z=None):
+        Yc = torch.view_as_complex(Y.contiguous()).to(torch.complex128).numpy()          # [B, F, T]
+        out = np.stack([ow.wpe(Yc[b], taps, delay, iterations) for b in range(Yc.shape[0])])
+        return torch.view_as_real(torch.from_numpy(out).to(torch.complex64)).contiguous()
+
+    monkeypatch.setattr(emu, "wpe", wpe_standin)
+    n = 4000                                   # not a multiple of the shift: the tail is padded to whole frames
+    rng = np.random.default_rng(1)
+    y = np.stack([np.convolve(rng.standard_normal(n), rng.standard_normal(600) * np.exp(-np.arange(600) / 100.0))[:n]
+                  for _ in range(2)])
+    w = WpeDereverb("cpu", taps=10, delay=2, iterations=2)
+    yt = torch.from_numpy(y).float()
+    Y = w.stft(yt)
+    want = ow.stft(y)                                                                     # (B, frames, 257)
+    assert Y.shape == (2, 257, want.shape[1], 2) and w.frames(n) == want.shape[1]
+    assert rel(Y, torch.view_as_real(torch.from_numpy(want).transpose(1, 2).to(torch.complex64))) < 1e-5
+    assert rel(w.istft(Y, n), yt) < 1e-5                                                   # perfect reconstruction
+    got = w(yt)
+    ref = np.stack([ow.wpe_dereverb(y[b], taps=10, delay=2, iterations=2)[:n] for b in range(2)])
+    assert got.shape == (2, n) and rel(got, torch.from_numpy(ref)) < 1e-4
