@@ -285,8 +285,285 @@ def adam_project(p, g, m, v, step, lr, beta1, beta2, eps, dmin, dmax, wmin, wmax
     p.copy_(torch.where(torch.isnan(new), new, torch.minimum(torch.maximum(new, lo), hi)))
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# Network-engine entry points (fp16 single-pass operand scheme only: no e4m3 pairs, passes == 1)
+# ----------------------------------------------------------------------------------------------------------------
+def pack_weights(src, T, N, K, *, off0=0, st=0, sn=(1, 0, 0), sk=(1, 0, 0), n_valid=None, k_valid=None, passes=1,
+                 e4m3=False):
+    """include/buddy_b200.h `buddy_pack_desc`: element (t, n, k) = src.flatten()[off0 + t*st + (n // ndiv)*sn_outer +
+    (n % ndiv)*sn_inner + (k // kdiv)*sk_outer + (k % kdiv)*sk_inner], zero for n >= n_valid or k >= k_valid."""
+    assert passes == 1 and not e4m3, "the stand-in covers the single-pass fp16 scheme"
+    ndiv, sno, sni = sn
+    kdiv, sko, ski = sk
+    t = torch.arange(T)[:, None, None]
+    n = torch.arange(N)[None, :, None]
+    k = torch.arange(K)[None, None, :]
+    idx = off0 + t * st + (n // ndiv) * sno + (n % ndiv) * sni + (k // kdiv) * sko + (k % kdiv) * ski
+    valid = (n < (N if n_valid is None else n_valid)) & (k < (K if k_valid is None else k_valid))
+    flat = src.flatten()
+    assert int(idx[valid.expand_as(idx)].min()) >= 0 and int(idx[valid.expand_as(idx)].max()) < flat.numel()
+    vals = torch.where(valid, flat[idx.clamp(0, flat.numel() - 1)], torch.zeros(()))
+    return vals.to(torch.float16).contiguous(), None
+
+
+def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=None, bias_b=None, resid=None,
+              scale=1.0, stats=None, b_batched=False, col_off=0, ldc=None, passes=1, a8=None, w8=None, a8_2=None,
+              w8_2=None, gnb=None, **tuning):
+    """out[b,h,w,n] = scale * (sum_{tap,k} a[b,h+dy,w+dx,k] w[tap,n,k] + sum_k a2[b,h,w,k] w2[n,k] + bias + bias_b +
+    resid), tap = 3*ky + kx, (dy, dx) = (ky-1, kx-1), zero padding; `stats` += per-4-channel-bundle (sum, sum of
+    squares) of the values written; b_batched: one weight matrix per batch entry (attention products)."""
+    assert a8 is None and w8 is None and a8_2 is None and passes == 1 and gnb is None
+    B, H, W, C = a.shape
+    assert w.shape[2] == C and w.shape[1] >= n_total
+    A = a.float()
+    if b_batched:
+        assert taps == 1 and w.shape[0] == B
+        acc = torch.einsum("bhwk,bnk->bhwn", A, w.float()[:, :n_total])
+    elif taps == 1:
+        acc = torch.einsum("bhwk,nk->bhwn", A, w.float()[0, :n_total])
+    else:
+        assert taps == 9 and w.shape[0] == 9
+        wt = w.float()[:, :n_total].reshape(3, 3, n_total, C).permute(2, 3, 0, 1)
+        acc = torch.nn.functional.conv2d(A.permute(0, 3, 1, 2), wt, padding=1).permute(0, 2, 3, 1)
+    if a2 is not None:
+        assert a2.shape[:3] == a.shape[:3] and w2.shape[1] == a2.shape[3]
+        acc = acc + torch.einsum("bhwk,nk->bhwn", a2.float(), w2.float()[:n_total])
+    if bias is not None:
+        acc = acc + bias[:n_total]
+    if bias_b is not None:
+        acc = acc + bias_b[:, None, None, :]
+    if resid is not None:
+        acc = acc + resid.reshape(B, H, W, -1)[..., :n_total]
+    acc = (acc * scale).to(out.dtype)
+    if stats is not None:
+        v = acc.double().reshape(B, H * W, n_total // 4, 4)
+        stats[..., 0] += v.sum(dim=(1, 3))
+        stats[..., 1] += (v * v).sum(dim=(1, 3))
+    ld = out.shape[-1] if ldc is None else ldc
+    out.view(B, H, W, ld)[..., col_off:col_off + n_total] = acc
+    return out
+
+
+def gn_stats(x, stats=None):
+    """Per-4-channel-bundle (sum, sum of squares) of x fp32 [B, .., C] -> fp64 [B, C/4, 2] (+=)."""
+    B, C = x.shape[0], x.shape[-1]
+    if stats is None:
+        stats = torch.zeros(B, C // 4, 2, dtype=torch.float64)
+    v = x.double().reshape(B, -1, C // 4, 4)
+    stats[..., 0] += v.sum(dim=(1, 3))
+    stats[..., 1] += (v * v).sum(dim=(1, 3))
+    return stats
+
+
+def _cat(xa, xb):
+    return xa if xb is None else torch.cat([xa, xb], -1)
+
+
+def _check_stats(xa, sa, xb, sb):
+    """The statistics a consumer is handed must be those of the tensor it is handed (catches mis-wired launches)."""
+    for x, s_ in ((xa, sa), (xb, sb)):
+        if x is not None:
+            want = gn_stats(x)
+            assert torch.allclose(s_, want, rtol=1e-4, atol=1e-6 * float(want.abs().max())), "GroupNorm statistics mismatch"
+
+
+def _gn(x, gamma, beta, groups, eps, silu):
+    B, H, W, C = x.shape
+    xg = x.reshape(B, H * W, groups, C // groups)
+    mean = xg.mean(dim=(1, 3), keepdim=True)
+    var = xg.var(dim=(1, 3), unbiased=False, keepdim=True)
+    y = ((xg - mean) / torch.sqrt(var + eps)).reshape(B, H, W, C) * gamma + beta
+    return y * torch.sigmoid(y) if silu else y
+
+
+def _resample(y, mode):
+    if mode == 1:      # nearest x2
+        return y.repeat_interleave(2, 1).repeat_interleave(2, 2)
+    if mode == 2:      # 2x2 mean
+        B, H, W, C = y.shape
+        return y.reshape(B, H // 2, 2, W // 2, 2, C).mean(dim=(2, 4))
+    return y
+
+
+def gn_apply(xa, sa, gamma, beta, out, *, xb=None, sb=None, groups=32, silu=True, mode=0, out_raw=None, eps=1e-6,
+             split=False, out8=None, out_raw8=None):
+    """out(fp16) = resample(act(GroupNorm([xa|xb]))); out_raw(fp16) = resample([xa|xb])."""
+    assert not split and out8 is None and out_raw8 is None
+    _check_stats(xa, sa, xb, sb)
+    x = _cat(xa, xb).double()
+    out.copy_(_resample(_gn(x, gamma.double(), beta.double(), groups, eps, silu), mode).to(out.dtype))
+    if out_raw is not None:
+        out_raw.copy_(_resample(x, mode).to(out_raw.dtype))
+    return out
+
+
+def gn_bwd(xa, sa, gamma, beta, da, gsum, *, xb=None, sb=None, groups=32, silu=True, mode=0, dskip=None, skip_scale=1.0,
+           extra_a=None, extra_b=None, dxa=None, dxb=None, g16a=None, g16b=None, g16_scale=1.0, eps=1e-6, split=False,
+           g8a=None, g8b=None, pass0_done=False):
+    """dx = d/dx <da, resample(act(GroupNorm(x)))> + R^T(dskip) * skip_scale + extra; fp32 (dxa, dxb) and / or the
+    producer's dgrad operand fp16(dx * g16_scale) (g16a, g16b).  Here by autograd over the forward definition."""
+    assert not split and g8a is None and g8b is None and not pass0_done
+    _check_stats(xa, sa, xb, sb)
+    with torch.enable_grad():
+        x = _cat(xa, xb).double().requires_grad_(True)
+        obj = (_resample(_gn(x, gamma.double(), beta.double(), groups, eps, silu), mode) * da.double()).sum()
+        if dskip is not None:
+            obj = obj + skip_scale * (_resample(x, mode) * dskip.double()).sum()
+        (dx,) = torch.autograd.grad(obj, x)
+    Ca = xa.shape[-1]
+    parts = [(dx[..., :Ca], extra_a, dxa, g16a), (dx[..., Ca:], extra_b, dxb, g16b)]
+    for d, extra, o32, o16 in parts[:1 if xb is None else 2]:
+        if extra is not None:
+            d = d + extra.double()
+        if o32 is not None:
+            o32.copy_(d.float())
+        if o16 is not None:
+            o16.copy_((d * g16_scale).to(torch.float16))
+
+
+_TAPS = [(t // 3 - 1, t % 3 - 1) for t in range(9)]
+
+
+def _shift2(x, dy, dx):
+    """x[b, h + dy, w + dx, :] with zeros outside the image."""
+    B, H, W, C = x.shape
+    out = torch.zeros_like(x)
+    hs, he = max(0, -dy), min(H, H - dy)
+    ws, we = max(0, -dx), min(W, W - dx)
+    if hs < he and ws < we:
+        out[:, hs:he, ws:we] = x[:, hs + dy:he + dy, ws + dx:we + dx]
+    return out
+
+
+def im2col_c2(x, col, split=False, col8=None, in_scale=1.0):
+    """x fp32 [B,H,W,2] -> fp16 [B,H,W,64], K index = tap*2 + ci (3x3, zero padded; 18 used, rest zero)."""
+    assert not split and col8 is None
+    col.zero_()
+    for t, (dy, dx) in enumerate(_TAPS):
+        col[..., 2 * t:2 * t + 2] = (_shift2(x, dy, dx) * in_scale).to(col.dtype)
+    return col
+
+
+def col2im_c2(dcol, dx, accumulate=False):
+    """dx[b,h,w,ci] (+)= sum_tap dcol[b, h-dy, w-dx, tap*2+ci]."""
+    acc = sum(_shift2(dcol[..., 2 * t:2 * t + 2], -dy, -dx_) for t, (dy, dx_) in enumerate(_TAPS))
+    dx.copy_(dx + acc if accumulate else acc)
+    return dx
+
+
+def resample_c2(x, mode, out, add=None, accumulate=False):
+    """mode 0: 2x2 mean; 1: nearest x2 (+ add); 2: adjoint of 0 (parent / 4); 3: adjoint of 1 (sum of 4)."""
+    B, H, W, C = x.shape
+    if mode in (0, 3):
+        r = x.reshape(B, H // 2, 2, W // 2, 2, C).sum(dim=(2, 4)) * (0.25 if mode == 0 else 1.0)
+    else:
+        r = x.repeat_interleave(2, 1).repeat_interleave(2, 2) * (0.25 if mode == 2 else 1.0)
+    if add is not None:
+        r = r + add
+    out.copy_(out + r if accumulate else r)
+    return out
+
+
+def combine_fwd(h, pyr, w, bias, out):
+    """Combine 'sum' (layerspp.py:52-59): out[p][c] = h[p][c] + w[c][0] pyr[p][0] + w[c][1] pyr[p][1] + bias[c]."""
+    out.copy_(h + pyr @ w.t() + bias)
+    return out
+
+
+def combine_bwd(dout, w, dpyr):
+    dpyr.copy_(dout @ w)
+    return dpyr
+
+
+def affine_c2(x, m4, b2, y):
+    """y[p] = M (2x2, row-major m4) x[p] + b2."""
+    M = torch.tensor([float(v) for v in m4]).reshape(2, 2)
+    y.copy_(x @ M.t() + torch.tensor([float(v) for v in b2]))
+    return y
+
+
+def softmax_fwd(s, p):
+    n = s.shape[-1]
+    p.view(-1, p.shape[-1])[:, :n] = torch.softmax(s.reshape(-1, n).double(), -1).to(p.dtype)
+    return p
+
+
+def softmax_bwd(p, dp, scale, ds):
+    """dS = P * (dP - <dP, P>) * scale per row."""
+    n = dp.shape[-1]
+    P = p.reshape(-1, p.shape[-1])[:, :n].double()
+    D = dp.reshape(-1, n).double()
+    ds.view(-1, ds.shape[-1])[:, :n] = (P * (D - (P * D).sum(-1, keepdim=True)) * scale).to(ds.dtype)
+    return ds
+
+
+def transpose_h(x, out):
+    out.copy_(x.transpose(1, 2))
+    return out
+
+
+def fourier_features(t, W, out):
+    """GaussianFourierProjection: out[b] = [sin(t W 2 pi) | cos(t W 2 pi)]."""
+    xp = t[:, None] * W[None, :] * 2 * math.pi
+    out.copy_(torch.cat([torch.sin(xp), torch.cos(xp)], -1))
+    return out
+
+
+def dense(x, W, bias, out, act_in=False, act_out=False):
+    v = torch.nn.functional.silu(x) if act_in else x
+    y = v @ W.t() + (bias if bias is not None else 0.0)
+    out.copy_(torch.nn.functional.silu(y) if act_out else y)
+    return out
+
+
+def dense_seg(x, W, bias, seg, out, act_in=False):
+    """Several dense layers in one launch: the layer with first row r0 and `rows` rows writes its own contiguous
+    [B][rows] slab at out + B * r0."""
+    B = x.shape[0]
+    y = (torch.nn.functional.silu(x) if act_in else x) @ W.t() + (bias if bias is not None else 0.0)
+    for r0, rows in sorted({(int(a), int(b)) for a, b in seg.tolist()}):
+        out[B * r0:B * (r0 + rows)] = y[:, r0:r0 + rows].reshape(-1)
+    return out
+
+
+def cast_operand(x, out16, out8=None, scale=1.0, upsample=False, split=0):
+    """fp32 [B,H,W,C] -> fp16 operand of scale * x, optionally through nearest-neighbour x2 first."""
+    assert not split and out8 is None
+    v = x * scale
+    out16.copy_((v.repeat_interleave(2, 1).repeat_interleave(2, 2) if upsample else v).to(out16.dtype))
+    return out16
+
+
+def gn_act32(x, stats, gamma, beta, out, groups=32, eps=1e-6, silu=True):
+    """GroupNorm (+SiLU) of one tensor written as fp32 (the activation the `fir` blocks hand to upfirdn2d)."""
+    _check_stats(x, stats, None, None)
+    out.copy_(_gn(x.double(), gamma.double(), beta.double(), groups, eps, silu).float())
+    return out
+
+
+def upfirdn2d_launch(x4, kernel, up, down, pad):
+    """buddy_upfirdn2d on [major, in_h, in_w, minor]: zero-insertion upsampling by (up_x, up_y), padding (x0, x1, y0, y1;
+    negative = crop), correlation with the flipped FIR, decimation by (down_x, down_y) — op/upfirdn2d.py:157-200."""
+    (ux, uy), (dx, dy), (px0, px1, py0, py1) = up, down, pad
+    M, H, W, C = x4.shape
+    z = x4.new_zeros(M, H * uy, W * ux, C)
+    z[:, ::uy, ::ux] = x4
+    z = torch.nn.functional.pad(z, [0, 0, max(px0, 0), max(px1, 0), max(py0, 0), max(py1, 0)])
+    z = z[:, max(-py0, 0):z.shape[1] - max(-py1, 0), max(-px0, 0):z.shape[2] - max(-px1, 0)]
+    kh, kw = kernel.shape
+    zz = z.permute(0, 3, 1, 2).reshape(M * C, 1, z.shape[1], z.shape[2])
+    y = torch.nn.functional.conv2d(zz, torch.flip(kernel, [0, 1]).view(1, 1, kh, kw).to(x4.dtype))
+    y = y[:, :, ::dy, ::dx]
+    return y.reshape(M, C, y.shape[2], y.shape[3]).permute(0, 2, 3, 1).contiguous()
+
+
 ALL = dict(pad_signal=pad_signal, reflect_fold=reflect_fold, dft_analysis=dft_analysis, dft_synthesis=dft_synthesis,
            fft_analysis=fft_analysis, fft_synthesis=fft_synthesis, ola_gather=ola_gather, lincomb3=lincomb3,
            row_stats=row_stats, comp_loss=comp_loss, fftconv=fftconv, fft_mixed=fft_mixed, minphase_pw=minphase_pw,
            subband_fir=subband_fir, blind_design_fwd=blind_design_fwd, blind_design_bwd=blind_design_bwd,
-           adam_project=adam_project)
+           adam_project=adam_project,
+           pack_weights=pack_weights, conv_gemm=conv_gemm, gn_stats=gn_stats, gn_apply=gn_apply, gn_bwd=gn_bwd,
+           im2col_c2=im2col_c2, col2im_c2=col2im_c2, resample_c2=resample_c2, combine_fwd=combine_fwd,
+           combine_bwd=combine_bwd, affine_c2=affine_c2, softmax_fwd=softmax_fwd, softmax_bwd=softmax_bwd,
+           transpose_h=transpose_h, fourier_features=fourier_features, dense=dense, dense_seg=dense_seg,
+           cast_operand=cast_operand, gn_act32=gn_act32)

@@ -8,6 +8,8 @@ hold the compositions to the oracle (`oracle/`, pinned to the reference) — so 
 up in the `-m "not gpu"` suite, not only on the GPU box.  The kernels themselves are covered by the `-m gpu` tests.
 """
 
+import math
+
 import pytest
 import torch
 
@@ -36,6 +38,8 @@ def emu(monkeypatch):
     # BlindEngine keys its scratch buffers by (micro-batch size, CUDA stream): one "stream" here
     import types
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=0))
+    from buddy_b200 import upfirdn2d
+    monkeypatch.setattr(upfirdn2d, "_launch", ek.upfirdn2d_launch)
     return ops
 
 
@@ -372,3 +376,68 @@ def test_wpe_warm_start_host_side_vs_oracle(emu, monkeypatch):
     got = w(yt)
     ref = np.stack([ow.wpe_dereverb(y[b], taps=10, delay=2, iterations=2)[:n] for b in range(2)])
     assert got.shape == (2, n) and rel(got, torch.from_numpy(ref)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Network engine: buddy_b200.engine.Engine is ~300 launches per evaluation wired together in Python —
+# weight repacking by element strides, virtual concatenation, statistics hand-over, the hand-scheduled data-gradient
+# walk with its partial-gradient bookkeeping.  Run over stand-ins (single-pass fp16 operand scheme) it must reproduce
+# the oracle network: a mis-wired launch is an O(1) error, the fp16 operand rounding ~1e-3.
+# ------------------------------------------------------------------------------------------------------------------
+def test_network_engine_wiring_forward_and_data_gradient_vs_oracle(emu):
+    from buddy_b200.engine import Engine
+    from oracle.weights import make_state_dict
+    sd = make_state_dict(0)
+    eng = Engine(sd, "cpu", precision="fp16")
+    B, W = 2, 16                                           # 2 utterances x 16 frames: the smallest legal spectrogram
+    spec = randn(900, B, 256, W, 2)
+    tc = torch.tensor([0.25 * math.log(0.3), 0.25 * math.log(0.02)])
+    dout = randn(901, B, 256, W, 2)
+    out, ctx = eng.forward(spec, tc, save=True, graph=False)
+    dx = eng.vjp(ctx, dout)
+    s = spec.clone().requires_grad_(True)
+    want = torch.view_as_real(onet.ncsnpp_forward(sd, torch.view_as_complex(s)[:, None], tc)[:, 0].contiguous())
+    (want_dx,) = torch.autograd.grad(want, s, dout)
+    e_f, e_b = rel(out, want.detach()), rel(dx, want_dx)
+    print(f"\n[engine wiring on CPU, fp16 single-pass operands] forward {e_f:.2e}, data-gradient {e_b:.2e}")
+    assert e_f < 5e-3 and e_b < 1e-2
+    # batch entries are independent problems (the stand-ins' fp32 sums depend on the batch shape in the last bit, and an
+    # fp16 operand rounding that flips on it moves the output by ~1e-4..1e-3; mixing utterances would be an O(1) error)
+    out2, _ = eng.forward(spec[1:], tc[1:], save=False, graph=False)
+    assert rel(out2, out[1:]) < 3e-3
+
+
+@pytest.mark.parametrize("variant", [
+    dict(resblock_type="ddpm"),
+    dict(progressive="residual", progressive_input="residual"),
+    dict(progressive="none", progressive_input="none"),
+    dict(progressive="output_skip", progressive_input="residual", resblock_type="ddpm"),
+    dict(fir=True),
+], ids=lambda v: "-".join(f"{k[:8]}={x}" for k, x in v.items()))
+def test_network_engine_wiring_of_the_graph_variants_vs_reference_network(emu, variant):
+    """The `resblock_type` / `progressive` / `progressive_input` / `fir` graphs (ncsnpp.py:127-150,196-274) — module plan
+    from netspec, general tape walk of engine_generic.py, ddpm Downsample / Upsample and FIR resampling through
+    upfirdn2d — against the UNMODIFIED reference network built with the same options (its own state_dict layout loaded
+    as is), at spectrogram level on the CPU."""
+    from buddy_b200.engine import Engine
+    from oracle import ref_harness as rh
+    from oracle.weights import make_state_dict
+    if not rh.available():
+        pytest.skip("unmodified reference not present (build container: /root/reference, GPU box: oracle/_ref)")
+    ref_net = rh.build_network(**variant)
+    spec_sd = [(k, tuple(v.shape)) for k, v in ref_net.state_dict().items()]
+    ref_net.load_state_dict(make_state_dict(3, spec=spec_sd))
+    eng = Engine(ref_net.state_dict(), "cpu", precision="fp16", **variant)
+    B, W = 1, 16
+    spec = randn(910, B, 256, W, 2)
+    tc = torch.tensor([0.25 * math.log(0.1)])
+    dout = randn(911, B, 256, W, 2)
+    out, ctx = eng.forward(spec, tc, save=True, graph=False)
+    dx = eng.vjp(ctx, dout)
+    from networks.ncsnpp import NCSNpp
+    s = spec.clone().requires_grad_(True)
+    want = torch.view_as_real(NCSNpp.forward(ref_net, torch.view_as_complex(s)[:, None], tc)[:, 0].contiguous())
+    (want_dx,) = torch.autograd.grad(want, s, dout)
+    e_f, e_b = rel(out, want.detach()), rel(dx, want_dx)
+    print(f"\n[engine wiring on CPU, {variant}] forward {e_f:.2e}, data-gradient {e_b:.2e}")
+    assert e_f < 5e-3 and e_b < 1e-2
