@@ -286,13 +286,36 @@ def adam_project(p, g, m, v, step, lr, beta1, beta2, eps, dmin, dmax, wmin, wmax
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# Network-engine entry points (fp16 single-pass operand scheme only: no e4m3 pairs, passes == 1)
+# Network-engine entry points: single-pass fp16 operands and the fp16 + e4m3-correction scheme (`fp16c8` / `mixed`:
+# operand pair [e4m3(2^9 (v - hi)) | e4m3(hi)], weight pair [e4m3(2^5 w_hi) | e4m3(2^14 w_lo)], corrections folded in
+# with 2^-14); the [hi | lo] fp16 split schemes (passes 2, 3) are not covered
 # ----------------------------------------------------------------------------------------------------------------
+def _e4m3(t):
+    """__nv_cvt_float_to_fp8(.., __NV_SATFINITE, __NV_E4M3) as uint8."""
+    return t.float().clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+
+
+def _from_e4m3(u8):
+    return u8.contiguous().view(torch.float8_e4m3fn).float()
+
+
+def _store_operand(v, out16, out8, split):
+    """elementwise.cu `store_op4` / `store_op8`: split 0 (or 2 without a pair buffer): fp16(v); split 2 with `out8`:
+    fp16 hi + [e4m3((v - hi) * 2^9) | e4m3(hi)]."""
+    assert split in (0, 2, False), "the [hi | lo] fp16 split is not covered by the stand-ins"
+    hi = v.to(torch.float16)
+    out16.copy_(hi)
+    if split == 2 and out8 is not None:
+        C = v.shape[-1]
+        out8[..., :C] = _e4m3((v.float() - hi.float()) * 512.0)
+        out8[..., C:] = _e4m3(hi.float())
+
+
 def pack_weights(src, T, N, K, *, off0=0, st=0, sn=(1, 0, 0), sk=(1, 0, 0), n_valid=None, k_valid=None, passes=1,
                  e4m3=False):
     """include/buddy_b200.h `buddy_pack_desc`: element (t, n, k) = src.flatten()[off0 + t*st + (n // ndiv)*sn_outer +
     (n % ndiv)*sn_inner + (k // kdiv)*sk_outer + (k % kdiv)*sk_inner], zero for n >= n_valid or k >= k_valid."""
-    assert passes == 1 and not e4m3, "the stand-in covers the single-pass fp16 scheme"
+    assert passes == 1, "the [hi | lo] fp16 split is not covered by the stand-ins"
     ndiv, sno, sni = sn
     kdiv, sko, ski = sk
     t = torch.arange(T)[:, None, None]
@@ -303,7 +326,11 @@ def pack_weights(src, T, N, K, *, off0=0, st=0, sn=(1, 0, 0), sk=(1, 0, 0), n_va
     flat = src.flatten()
     assert int(idx[valid.expand_as(idx)].min()) >= 0 and int(idx[valid.expand_as(idx)].max()) < flat.numel()
     vals = torch.where(valid, flat[idx.clamp(0, flat.numel() - 1)], torch.zeros(()))
-    return vals.to(torch.float16).contiguous(), None
+    w16 = vals.to(torch.float16).contiguous()
+    if not e4m3:
+        return w16, None
+    hi = w16.float()
+    return w16, torch.cat([_e4m3(hi * 32.0), _e4m3((vals - hi) * 16384.0)], -1).contiguous()
 
 
 def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=None, bias_b=None, resid=None,
@@ -312,22 +339,31 @@ def conv_gemm(a, w, out, *, taps, n_total, n_tile=None, a2=None, w2=None, bias=N
     """out[b,h,w,n] = scale * (sum_{tap,k} a[b,h+dy,w+dx,k] w[tap,n,k] + sum_k a2[b,h,w,k] w2[n,k] + bias + bias_b +
     resid), tap = 3*ky + kx, (dy, dx) = (ky-1, kx-1), zero padding; `stats` += per-4-channel-bundle (sum, sum of
     squares) of the values written; b_batched: one weight matrix per batch entry (attention products)."""
-    assert a8 is None and w8 is None and a8_2 is None and passes == 1 and gnb is None
+    assert passes == 1 and gnb is None and (a8 is None) == (w8 is None)
     B, H, W, C = a.shape
     assert w.shape[2] == C and w.shape[1] >= n_total
-    A = a.float()
-    if b_batched:
-        assert taps == 1 and w.shape[0] == B
-        acc = torch.einsum("bhwk,bnk->bhwn", A, w.float()[:, :n_total])
-    elif taps == 1:
-        acc = torch.einsum("bhwk,nk->bhwn", A, w.float()[0, :n_total])
-    else:
-        assert taps == 9 and w.shape[0] == 9
-        wt = w.float()[:, :n_total].reshape(3, 3, n_total, C).permute(2, 3, 0, 1)
-        acc = torch.nn.functional.conv2d(A.permute(0, 3, 1, 2), wt, padding=1).permute(0, 2, 3, 1)
+
+    def contract(A, Wt):
+        K = A.shape[-1]
+        if b_batched:
+            assert taps == 1 and Wt.shape[0] == B
+            return torch.einsum("bhwk,bnk->bhwn", A, Wt[:, :n_total])
+        if taps == 1:
+            return torch.einsum("bhwk,nk->bhwn", A, Wt[0, :n_total])
+        assert taps == 9 and Wt.shape[0] == 9
+        wt = Wt[:, :n_total].reshape(3, 3, n_total, K).permute(2, 3, 0, 1)
+        return torch.nn.functional.conv2d(A.permute(0, 3, 1, 2), wt, padding=1).permute(0, 2, 3, 1)
+
+    acc = contract(a.float(), w.float())
+    if a8 is not None:       # first-order corrections a_lo w_hi + a_hi w_lo as e4m3 products, scale 2^-14
+        assert a8.shape[-1] == 2 * C and w8.shape[-1] == 2 * C and w8.shape[:2] == w.shape[:2]
+        acc = acc + contract(_from_e4m3(a8), _from_e4m3(w8)) / 16384.0
     if a2 is not None:
         assert a2.shape[:3] == a.shape[:3] and w2.shape[1] == a2.shape[3]
         acc = acc + torch.einsum("bhwk,nk->bhwn", a2.float(), w2.float()[:n_total])
+        if a8 is not None:
+            assert a8_2 is not None and w8_2 is not None and w8_2.shape == (w2.shape[0], a8_2.shape[3])
+            acc = acc + torch.einsum("bhwk,nk->bhwn", _from_e4m3(a8_2), _from_e4m3(w8_2)[:n_total]) / 16384.0
     if bias is not None:
         acc = acc + bias[:n_total]
     if bias_b is not None:
@@ -388,12 +424,11 @@ def _resample(y, mode):
 def gn_apply(xa, sa, gamma, beta, out, *, xb=None, sb=None, groups=32, silu=True, mode=0, out_raw=None, eps=1e-6,
              split=False, out8=None, out_raw8=None):
     """out(fp16) = resample(act(GroupNorm([xa|xb]))); out_raw(fp16) = resample([xa|xb])."""
-    assert not split and out8 is None and out_raw8 is None
     _check_stats(xa, sa, xb, sb)
     x = _cat(xa, xb).double()
-    out.copy_(_resample(_gn(x, gamma.double(), beta.double(), groups, eps, silu), mode).to(out.dtype))
+    _store_operand(_resample(_gn(x, gamma.double(), beta.double(), groups, eps, silu), mode).float(), out, out8, split)
     if out_raw is not None:
-        out_raw.copy_(_resample(x, mode).to(out_raw.dtype))
+        _store_operand(_resample(x, mode).float(), out_raw, out_raw8, split)
     return out
 
 
@@ -402,7 +437,7 @@ def gn_bwd(xa, sa, gamma, beta, da, gsum, *, xb=None, sb=None, groups=32, silu=T
            g8a=None, g8b=None, pass0_done=False):
     """dx = d/dx <da, resample(act(GroupNorm(x)))> + R^T(dskip) * skip_scale + extra; fp32 (dxa, dxb) and / or the
     producer's dgrad operand fp16(dx * g16_scale) (g16a, g16b).  Here by autograd over the forward definition."""
-    assert not split and g8a is None and g8b is None and not pass0_done
+    assert not pass0_done
     _check_stats(xa, sa, xb, sb)
     with torch.enable_grad():
         x = _cat(xa, xb).double().requires_grad_(True)
@@ -411,14 +446,14 @@ def gn_bwd(xa, sa, gamma, beta, da, gsum, *, xb=None, sb=None, groups=32, silu=T
             obj = obj + skip_scale * (_resample(x, mode) * dskip.double()).sum()
         (dx,) = torch.autograd.grad(obj, x)
     Ca = xa.shape[-1]
-    parts = [(dx[..., :Ca], extra_a, dxa, g16a), (dx[..., Ca:], extra_b, dxb, g16b)]
-    for d, extra, o32, o16 in parts[:1 if xb is None else 2]:
+    parts = [(dx[..., :Ca], extra_a, dxa, g16a, g8a), (dx[..., Ca:], extra_b, dxb, g16b, g8b)]
+    for d, extra, o32, o16, o8 in parts[:1 if xb is None else 2]:
         if extra is not None:
             d = d + extra.double()
         if o32 is not None:
             o32.copy_(d.float())
         if o16 is not None:
-            o16.copy_((d * g16_scale).to(torch.float16))
+            _store_operand(d.float() * g16_scale, o16, o8, split)
 
 
 _TAPS = [(t // 3 - 1, t % 3 - 1) for t in range(9)]
@@ -437,10 +472,10 @@ def _shift2(x, dy, dx):
 
 def im2col_c2(x, col, split=False, col8=None, in_scale=1.0):
     """x fp32 [B,H,W,2] -> fp16 [B,H,W,64], K index = tap*2 + ci (3x3, zero padded; 18 used, rest zero)."""
-    assert not split and col8 is None
-    col.zero_()
+    v = torch.zeros(*x.shape[:3], 64)
     for t, (dy, dx) in enumerate(_TAPS):
-        col[..., 2 * t:2 * t + 2] = (_shift2(x, dy, dx) * in_scale).to(col.dtype)
+        v[..., 2 * t:2 * t + 2] = _shift2(x, dy, dx) * in_scale
+    _store_operand(v, col, col8, split)
     return col
 
 
@@ -528,9 +563,8 @@ def dense_seg(x, W, bias, seg, out, act_in=False):
 
 def cast_operand(x, out16, out8=None, scale=1.0, upsample=False, split=0):
     """fp32 [B,H,W,C] -> fp16 operand of scale * x, optionally through nearest-neighbour x2 first."""
-    assert not split and out8 is None
     v = x * scale
-    out16.copy_((v.repeat_interleave(2, 1).repeat_interleave(2, 2) if upsample else v).to(out16.dtype))
+    _store_operand(v.repeat_interleave(2, 1).repeat_interleave(2, 2) if upsample else v, out16, out8, split)
     return out16
 
 
