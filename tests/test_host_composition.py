@@ -445,3 +445,39 @@ def test_network_engine_wiring_of_the_graph_variants_vs_reference_network(emu, v
     e_f, e_b = rel(out, want.detach()), rel(dx, want_dx)
     print(f"\n[engine wiring on CPU, {variant}] forward {e_f:.2e}, data-gradient {e_b:.2e}")
     assert e_f < 5e-3 and e_b < 1e-2
+
+
+def test_full_host_stack_informed_dps_vs_reference_fixture(emu):
+    """Everything above together: the product sampler driving the product network ENGINE (default `mixed` operand
+    scheme) and the product spectral / operator code, every C-ABI entry point stood in, against the trajectory the
+    UNMODIFIED reference produced (tests/golden/sampler_informed_T3.pt) at the north-star tolerance."""
+    from buddy_b200.engine import Engine
+    from buddy_b200.ncsnpp import NCSNppTime
+    from buddy_b200.operators import RIROperator
+    from buddy_b200.samplers import EulerHeunSamplerDPS
+    from buddy_b200.spectral import NetSTFT
+    from oracle import ref_harness as rh
+    from oracle.weights import make_state_dict
+    sd = make_state_dict(0)
+
+    class _Net(NCSNppTime):
+        def engine(self):
+            return self._cpu_engine
+
+        def stft_engine(self):
+            return self._cpu_stft
+
+    net = _Net(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
+    net._cpu_engine, net._cpu_stft = Engine(sd, "cpu", precision="mixed"), NetSTFT("cpu")
+    g = _gold("sampler_informed_T3.pt")
+    s = EulerHeunSamplerDPS(net.eval(), _edm(), rh.make_args("informed", g["T"]))
+    s.use_graphs = False
+    s.noise_source = iter([randn(g["noise_seed0"] + i, 1, g["n"]) for i in range(g["T"] + 1)])
+    op = RIROperator()
+    op.update_params(g["h"])
+    s.operator, s.y = op, g["y"].detach().float().contiguous()
+    s._bind_operator(op, s.y, False)
+    pred = s.predict((1, g["n"]), "cpu", False)
+    e = rel(pred, g["pred"])
+    print(f"\n[full host stack on CPU, informed DPS T3, mixed operand scheme] rel-L2 vs the reference fixture {e:.2e}")
+    assert e < 1e-3
