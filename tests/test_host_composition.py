@@ -481,3 +481,27 @@ def test_full_host_stack_informed_dps_vs_reference_fixture(emu):
     e = rel(pred, g["pred"])
     print(f"\n[full host stack on CPU, informed DPS T3, mixed operand scheme] rel-L2 vs the reference fixture {e:.2e}")
     assert e < 1e-3
+
+
+def test_query_blocked_attention_host_logic_vs_dense_and_oracle(emu):
+    """Long utterances (30 s: 15 040 tokens) run the bottleneck attention over query blocks with recomputation in the
+    backward pass (engine.py `_attn_fwd_blocked` / `_attn_bwd_blocked`: per-block softmax, dK / dV accumulated across
+    blocks through the GEMM's residual input).  Forced here on a small spectrogram with ragged blocks (64 tokens in
+    blocks of 24): same forward and data-gradient as the dense path and as the oracle."""
+    from buddy_b200.engine import Engine
+    from oracle.weights import make_state_dict
+    sd = make_state_dict(0)
+    eng = Engine(sd, "cpu", precision="fp16c8")
+    spec, tc, dout = randn(920, 1, 256, 16, 2), torch.tensor([0.25 * math.log(0.1)]), randn(921, 1, 256, 16, 2)
+    out_d, ctx = eng.forward(spec, tc, save=True, graph=False)
+    assert ctx["attn"][3] is not None                       # dense: probabilities kept for the backward pass
+    dx_d = eng.vjp(ctx, dout)
+    eng.ATTN_DENSE_BYTES, eng.ATTN_QBLOCK = 0, 24
+    out_b, ctx = eng.forward(spec, tc, save=True, graph=False)
+    assert ctx["attn"][3] is None                           # blocked: nothing N x N is stored
+    dx_b = eng.vjp(ctx, dout)
+    assert rel(out_b, out_d) < 1e-3 and rel(dx_b, dx_d) < 1e-3
+    s = spec.clone().requires_grad_(True)
+    want = torch.view_as_real(onet.ncsnpp_forward(sd, torch.view_as_complex(s)[:, None], tc)[:, 0].contiguous())
+    (want_dx,) = torch.autograd.grad(want, s, dout)
+    assert rel(out_b, want.detach()) < 1e-3 and rel(dx_b, want_dx) < 1e-3
