@@ -8,8 +8,13 @@ function); none of them is a product code path: nothing under `buddy_b200/`, `be
 this module, and the CUDA kernels themselves are checked against the oracle by the `-m gpu` tests.
 """
 import math
+import sys
 
 import torch
+
+if "pytest" not in sys.modules:      # not a fallback: only the test suite may load these
+    raise ImportError("tests/emulated_kernels.py is test infrastructure (pytest only); the product runs on the CUDA "
+                      "library buddy_b200/libbuddy_b200.so and has no CPU path")
 
 
 def pad_signal(x, left, total, mode, out, tab=None, scale_b=None):
