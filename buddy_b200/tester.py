@@ -230,8 +230,7 @@ class BatchedDereverb:
         <out_dir>/{original, degraded, reconstructed, true_rir[, estimated_rir]}/<name>.wav (tester.py:167-203) through an
         `AsyncWavWriter`.  Returns the list of reconstructed-file paths in set order."""
         sr = self.sampler.args.exp.sample_rate
-        own = writer is None
-        writer = AsyncWavWriter() if own else writer
+        writer = AsyncWavWriter() if writer is None else writer
         items = [test_set[i] for i in range(len(test_set))]
         segs, ys, rirs = [], [], []
         for x, h, _ in items:
@@ -255,8 +254,7 @@ class BatchedDereverb:
             paths.append(writer.write(preds[k], sr, stem, sub("reconstructed")))
             if blind:
                 writer.write(est[k], sr, stem, sub("estimated_rir"))
-        if own:
-            writer.close()
+        writer.close()        # wait for every file of this call (the writer itself stays usable): the paths exist on return
         return paths
 
     def init_blind_operator(self, B, device, generator=None):

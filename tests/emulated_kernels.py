@@ -596,6 +596,15 @@ def upfirdn2d_launch(x4, kernel, up, down, pad):
     return y.reshape(M, C, y.shape[2], y.shape[3]).permute(0, 2, 3, 1).contiguous()
 
 
+def philox_normal(seeds, draw, out):
+    """One N(0,1) stream per utterance (seed[b]), `draw` = running draw index: what the stand-in keeps of the Philox
+    kernel is exactly that contract (values depend on (seed, draw) only), not its bit pattern."""
+    for b in range(out.shape[0]):
+        g = torch.Generator().manual_seed((int(seeds[b]) * 1000003 + int(draw)) % (2 ** 63 - 1))
+        out[b] = torch.randn(out.shape[1], generator=g)
+    return out
+
+
 ALL = dict(pad_signal=pad_signal, reflect_fold=reflect_fold, dft_analysis=dft_analysis, dft_synthesis=dft_synthesis,
            fft_analysis=fft_analysis, fft_synthesis=fft_synthesis, ola_gather=ola_gather, lincomb3=lincomb3,
            row_stats=row_stats, comp_loss=comp_loss, fftconv=fftconv, fft_mixed=fft_mixed, minphase_pw=minphase_pw,
@@ -605,4 +614,4 @@ ALL = dict(pad_signal=pad_signal, reflect_fold=reflect_fold, dft_analysis=dft_an
            im2col_c2=im2col_c2, col2im_c2=col2im_c2, resample_c2=resample_c2, combine_fwd=combine_fwd,
            combine_bwd=combine_bwd, affine_c2=affine_c2, softmax_fwd=softmax_fwd, softmax_bwd=softmax_bwd,
            transpose_h=transpose_h, fourier_features=fourier_features, dense=dense, dense_seg=dense_seg,
-           cast_operand=cast_operand, gn_act32=gn_act32)
+           cast_operand=cast_operand, gn_act32=gn_act32, philox_normal=philox_normal)
