@@ -235,6 +235,7 @@ def test_sampler_glue_unconditional_vs_reference_fixture(emu, glue_net):
     s = EulerHeunSampler(glue_net, _edm(), rh.make_args("unconditional", g["T"]))
     s.noise_source = iter([randn(g["noise_seed0"] + i, 1, g["n"]) for i in range(g["T"] + 1)])
     x = s.predict_unconditional((1, g["n"]), "cpu")
+    print(f"\n[sampler glue on CPU, unconditional T3] rel-L2 vs the reference fixture {rel(x, g['x']):.2e}")
     assert rel(x, g["x"]) < 1e-4
     assert s.step_counter == g["T"] - 1
 
@@ -257,6 +258,7 @@ def test_sampler_glue_informed_dps_vs_reference_fixture(emu, glue_net, fixture, 
     s.operator, s.y = op, g["y"].detach().float().contiguous()
     s._bind_operator(op, s.y, False)
     pred = s.predict((1, g["n"]), "cpu", False)
+    print(f"\n[sampler glue on CPU, {fixture}] rel-L2 vs the reference fixture {rel(pred, g['pred']):.2e}")
     assert rel(pred, g["pred"]) < 1e-3
 
 
