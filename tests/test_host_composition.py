@@ -650,3 +650,21 @@ def test_front_end_blind_batched_equals_single_runs(emu, glue_net64):
             print(f"[front-end blind, utterance {i}] batched vs alone {rel(preds[i], alone):.1e}")
             assert rel(preds[i], alone) < 1e-2, (i, rel(preds[i], alone))          # measured 2e-7; see the informed test
             assert rel(rirs[i], s1._blind.get_time_RIR()[0]) < 1e-2
+
+
+def test_nan_guard_names_the_utterance(emu, glue_net):
+    """The reference asserts on NaN inside the loop (EulerHeunSamplerDPS.py:90,103); here NaN propagates through the
+    launches and ONE finiteness check per call raises, naming the utterance — or not at all with `nan_guard = False`."""
+    from buddy_b200.operators import RIROperator
+    n = 2048
+    y = randn(990, 2, n) * 0.05
+    y[1, 100] = float("nan")
+    op = RIROperator()
+    op.update_params(randn(991, 300) * torch.exp(-torch.arange(300) / 60.0))
+    smp = _cpu_sampler(glue_net, "informed", 2)
+    smp.seed_base = 1
+    with pytest.raises(FloatingPointError, match=r"utterance\(s\) \[1\]"):
+        smp.predict_conditional(y, op, shape=(2, n))
+    smp.nan_guard = False
+    out = smp.predict_conditional(y, op, shape=(2, n))
+    assert torch.isfinite(out[0]).all() and not torch.isfinite(out[1]).all()      # utterances do not contaminate each other
