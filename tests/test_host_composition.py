@@ -668,3 +668,69 @@ def test_nan_guard_names_the_utterance(emu, glue_net):
     smp.nan_guard = False
     out = smp.predict_conditional(y, op, shape=(2, n))
     assert torch.isfinite(out[0]).all() and not torch.isfinite(out[1]).all()      # utterances do not contaminate each other
+
+
+_SHARD_WORKER = r'''
+import os, sys, types
+import pytest                                   # the stand-ins load under pytest only; this worker is part of a test
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import emulated_kernels as ek
+import test_host_composition as thc
+from buddy_b200 import ops
+from buddy_b200.dist import gather_utterances, shard_range, world_info
+from buddy_b200.operators import RIROperator
+for k, v in ek.ALL.items():
+    setattr(ops, k, v)
+rank, world, _ = world_info()
+dist.init_process_group("gloo", rank=rank, world_size=world)
+total, n = 3, 4096
+ys = torch.stack([thc.randn(960 + i, n) * 0.05 for i in range(total)])
+hs = torch.stack([thc.randn(970 + i, 600) * torch.exp(-torch.arange(600) / 120.0) for i in range(total)])
+lo, hi = shard_range(rank, world, total)
+smp = thc._cpu_sampler(thc._glue_net(True), "informed", 2)
+smp.seed_base, smp.utterance_offset = 5000, lo          # noise stream of utterance i = seed_base + GLOBAL index i
+op = RIROperator()
+op.update_params(hs[lo:hi])
+local = smp.predict_conditional(ys[lo:hi], op, shape=(hi - lo, n))
+full = gather_utterances(local, total)
+if rank == 0:
+    torch.save(full, sys.argv[2])
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank, lo, hi)
+'''
+
+
+def test_two_rank_gloo_utterance_shards_equal_the_single_process_batch(emu, glue_net64, tmp_path):
+    """SURVEY §8e on the CPU: two processes (gloo), contiguous block shards of a 3-utterance batch (2 + 1), per-utterance
+    RIRs, noise streams keyed by the GLOBAL utterance index, no collective inside the sampler, results gathered in
+    global order == the same batch run by one process."""
+    import os
+    import subprocess
+    import sys
+    from buddy_b200.operators import RIROperator
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script, out = tmp_path / "worker.py", tmp_path / "full.pt"
+    script.write_text(_SHARD_WORKER)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT="29541", OMP_NUM_THREADS="4")
+        procs.append(subprocess.Popen([sys.executable, str(script), root, str(out)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        log, _ = p.communicate(timeout=600)
+        assert p.returncode == 0 and "ok" in log, log
+    total, n = 3, 4096
+    ys = torch.stack([randn(960 + i, n) * 0.05 for i in range(total)])
+    hs = torch.stack([randn(970 + i, 600) * torch.exp(-torch.arange(600) / 120.0) for i in range(total)])
+    smp = _cpu_sampler(glue_net64, "informed", 2)
+    smp.seed_base = 5000
+    op = RIROperator()
+    op.update_params(hs)
+    want = smp.predict_conditional(ys, op, shape=(total, n))
+    got = torch.load(out)
+    assert got.shape == want.shape
+    for i in range(total):          # measured 0.0e+00; the bound is that of the front-end tests above
+        assert rel(got[i], want[i]) < 1e-2, (i, rel(got[i], want[i]))
