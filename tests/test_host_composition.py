@@ -734,3 +734,37 @@ def test_two_rank_gloo_utterance_shards_equal_the_single_process_batch(emu, glue
     assert got.shape == want.shape
     for i in range(total):          # measured 0.0e+00; the bound is that of the front-end tests above
         assert rel(got[i], want[i]) < 1e-2, (i, rel(got[i], want[i]))
+
+
+@pytest.mark.parametrize("blind", [False, True], ids=["informed", "blind"])
+def test_micro_batch_slicing_is_invisible(emu, glue_net64, blind):
+    """`sampler.micro_batch` only bounds the activation memory of a network evaluation: 3 utterances in micro-batches of
+    2 + 1 == one micro-batch of 3 — per-utterance RIRs follow the slice offset (`RirConv.forward(first=...)`), the blind
+    operator / Adam state is sliced in place (`BlindEngine.select`), noise draws are keyed by utterance, not by slice."""
+    from buddy_b200.operators import RIROperator
+    B, n = 3, 2048
+    y = torch.stack([randn(980 + i, n) * 0.05 for i in range(B)])
+    outs = []
+    for mb in (32, 2):
+        smp = _cpu_sampler(glue_net64, "blind" if blind else "informed", 2)
+        smp.seed_base, smp.micro_batch = 6000, mb
+        if blind:
+            smp.args.tester.posterior_sampling.blind_hp["op_updates_per_step"] = 2
+            g = _gold("sampler_blind_T2.pt")["init"]
+
+            class Op:
+                pass
+            op = Op()
+            op.params = [torch.stack([g["decays"][0] * (1 + 0.1 * b) for b in range(B)]),
+                         torch.stack([g["weights"][0] * (1 + 0.2 * b) for b in range(B)])]
+            op.params_phases = [torch.stack([g["phases"].roll(b, 1) for b in range(B)])]
+            op.H = torch.stack([g["H"].roll(b, 1) for b in range(B)])
+        else:
+            op = RIROperator()
+            op.update_params(torch.stack([randn(985 + i, 500) * torch.exp(-torch.arange(500) / 100.0) for i in range(B)]))
+        outs.append((smp.predict_conditional(y, op, shape=(B, n), blind=blind),
+                     torch.view_as_real(op.H_batch).clone() if blind else None))
+    for b in range(B):          # measured bit-identical; bound as in the front-end tests
+        assert rel(outs[1][0][b], outs[0][0][b]) < 1e-2, (b, rel(outs[1][0][b], outs[0][0][b]))
+        if blind:
+            assert rel(outs[1][1][b], outs[0][1][b]) < 1e-2
