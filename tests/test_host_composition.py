@@ -190,6 +190,18 @@ class _OracleEngine:
         return g.float()
 
 
+class _ToyEngine:
+    """A linear stand-in network with the engine's call surface: per utterance, out = 0.5 spec + 0.1 flip_time(spec).
+    For the bookkeeping tests below (batching, sharding, slicing), which compare runs of the SAME map and only need it
+    cheap and exactly independent of the batch it is evaluated in; the real network is exercised by the tests above."""
+
+    def forward(self, spec, time_cond, save=False, graph=False):
+        return 0.5 * spec + 0.1 * spec.flip(2), (True if save else None)
+
+    def vjp(self, ctx, dspec):
+        return 0.5 * dspec + 0.1 * dspec.flip(2)
+
+
 def _glue_net(double):
     from buddy_b200.ncsnpp import NCSNppTime
     from buddy_b200.spectral import NetSTFT
@@ -204,7 +216,8 @@ def _glue_net(double):
             return self._cpu_stft
 
     net = _Net(stft=dict(n_fft=510, hop_length=128, center=True), nf=128, ch_mult=[1, 2, 2, 2])
-    net._double, net._cpu_stft = _OracleEngine(sd, double), NetSTFT("cpu")
+    net._double = _ToyEngine() if double == "toy" else _OracleEngine(sd, double)
+    net._cpu_stft = NetSTFT("cpu")
     return net.eval()
 
 
@@ -216,6 +229,11 @@ def glue_net():
 @pytest.fixture(scope="module")
 def glue_net64():
     return _glue_net(True)
+
+
+@pytest.fixture(scope="module")
+def glue_net_toy():
+    return _glue_net("toy")
 
 
 def _edm():
@@ -574,8 +592,8 @@ def _cpu_sampler(glue_net, mode, T):
     return _S(glue_net, _edm(), rh.make_args(mode, T))
 
 
-def test_front_end_informed_batched_equals_single_runs_and_file_loop(emu, glue_net64, tmp_path):
-    glue_net = glue_net64
+def test_front_end_informed_batched_equals_single_runs_and_file_loop(emu, glue_net_toy, tmp_path):
+    glue_net = glue_net_toy
     import os
     from buddy_b200.operators import RIROperator
     from buddy_b200.tester import AsyncWavWriter, BatchedDereverb, PairedWavSet, read_wav
@@ -609,15 +627,12 @@ def test_front_end_informed_batched_equals_single_runs_and_file_loop(emu, glue_n
         op.update_params(h)
         alone = s1.predict_conditional(y[None], op, shape=(1, lens[i]))[0]
         got, _ = read_wav(paths[i])
-        # bit-identical here (0.0e+00); the bound leaves room for CPUs whose fp64 convolutions depend on the batch shape in
-        # the last bit — this random-init trajectory amplifies such a bit to ~4e-4 (seen at 2048 samples) — while a wrong
-        # RIR / noise stream / bucket assignment is an O(1) difference
         print(f"[front-end informed, utterance {i}] batched vs alone {rel(got, alone):.1e}")
-        assert got.shape[0] == lens[i] and rel(got, alone) < 1e-2, (i, rel(got, alone))
+        assert got.shape[0] == lens[i] and rel(got, alone) < 1e-3, (i, rel(got, alone))
 
 
-def test_front_end_blind_batched_equals_single_runs(emu, glue_net64):
-    glue_net = glue_net64
+def test_front_end_blind_batched_equals_single_runs(emu, glue_net_toy):
+    glue_net = glue_net_toy
     from buddy_b200.tester import BatchedDereverb
     lens = [4096, 3000, 4096]
     ys = [randn(950 + i, n) * 0.05 for i, n in enumerate(lens)]
@@ -648,8 +663,8 @@ def test_front_end_blind_batched_equals_single_runs(emu, glue_net64):
             op.params, op.params_phases, op.H = [d0[r:r + 1].clone(), w0[r:r + 1].clone()], [ph0[r].clone()], H0[r].clone()
             alone = s1.predict_conditional(ys[i][None], op, shape=(1, lens[i]), blind=True)[0]
             print(f"[front-end blind, utterance {i}] batched vs alone {rel(preds[i], alone):.1e}")
-            assert rel(preds[i], alone) < 1e-2, (i, rel(preds[i], alone))          # measured 2e-7; see the informed test
-            assert rel(rirs[i], s1._blind.get_time_RIR()[0]) < 1e-2
+            assert rel(preds[i], alone) < 1e-3, (i, rel(preds[i], alone))
+            assert rel(rirs[i], s1._blind.get_time_RIR()[0]) < 1e-3
 
 
 def test_nan_guard_names_the_utterance(emu, glue_net):
@@ -688,7 +703,7 @@ total, n = 3, 4096
 ys = torch.stack([thc.randn(960 + i, n) * 0.05 for i in range(total)])
 hs = torch.stack([thc.randn(970 + i, 600) * torch.exp(-torch.arange(600) / 120.0) for i in range(total)])
 lo, hi = shard_range(rank, world, total)
-smp = thc._cpu_sampler(thc._glue_net(True), "informed", 2)
+smp = thc._cpu_sampler(thc._glue_net("toy"), "informed", 2)
 smp.seed_base, smp.utterance_offset = 5000, lo          # noise stream of utterance i = seed_base + GLOBAL index i
 op = RIROperator()
 op.update_params(hs[lo:hi])
@@ -702,7 +717,7 @@ print("ok", rank, lo, hi)
 '''
 
 
-def test_two_rank_gloo_utterance_shards_equal_the_single_process_batch(emu, glue_net64, tmp_path):
+def test_two_rank_gloo_utterance_shards_equal_the_single_process_batch(emu, glue_net_toy, tmp_path):
     """SURVEY §8e on the CPU: two processes (gloo), contiguous block shards of a 3-utterance batch (2 + 1), per-utterance
     RIRs, noise streams keyed by the GLOBAL utterance index, no collective inside the sampler, results gathered in
     global order == the same batch run by one process."""
@@ -725,19 +740,19 @@ def test_two_rank_gloo_utterance_shards_equal_the_single_process_batch(emu, glue
     total, n = 3, 4096
     ys = torch.stack([randn(960 + i, n) * 0.05 for i in range(total)])
     hs = torch.stack([randn(970 + i, 600) * torch.exp(-torch.arange(600) / 120.0) for i in range(total)])
-    smp = _cpu_sampler(glue_net64, "informed", 2)
+    smp = _cpu_sampler(glue_net_toy, "informed", 2)
     smp.seed_base = 5000
     op = RIROperator()
     op.update_params(hs)
     want = smp.predict_conditional(ys, op, shape=(total, n))
     got = torch.load(out)
     assert got.shape == want.shape
-    for i in range(total):          # measured 0.0e+00; the bound is that of the front-end tests above
-        assert rel(got[i], want[i]) < 1e-2, (i, rel(got[i], want[i]))
+    for i in range(total):      # other processes, other thread counts: the stand-ins' sums differ in the last bits (measured 2e-5)
+        assert rel(got[i], want[i]) < 1e-3, (i, rel(got[i], want[i]))
 
 
 @pytest.mark.parametrize("blind", [False, True], ids=["informed", "blind"])
-def test_micro_batch_slicing_is_invisible(emu, glue_net64, blind):
+def test_micro_batch_slicing_is_invisible(emu, glue_net_toy, blind):
     """`sampler.micro_batch` only bounds the activation memory of a network evaluation: 3 utterances in micro-batches of
     2 + 1 == one micro-batch of 3 — per-utterance RIRs follow the slice offset (`RirConv.forward(first=...)`), the blind
     operator / Adam state is sliced in place (`BlindEngine.select`), noise draws are keyed by utterance, not by slice."""
@@ -746,7 +761,7 @@ def test_micro_batch_slicing_is_invisible(emu, glue_net64, blind):
     y = torch.stack([randn(980 + i, n) * 0.05 for i in range(B)])
     outs = []
     for mb in (32, 2):
-        smp = _cpu_sampler(glue_net64, "blind" if blind else "informed", 2)
+        smp = _cpu_sampler(glue_net_toy, "blind" if blind else "informed", 2)
         smp.seed_base, smp.micro_batch = 6000, mb
         if blind:
             smp.args.tester.posterior_sampling.blind_hp["op_updates_per_step"] = 2
@@ -764,7 +779,8 @@ def test_micro_batch_slicing_is_invisible(emu, glue_net64, blind):
             op.update_params(torch.stack([randn(985 + i, 500) * torch.exp(-torch.arange(500) / 100.0) for i in range(B)]))
         outs.append((smp.predict_conditional(y, op, shape=(B, n), blind=blind),
                      torch.view_as_real(op.H_batch).clone() if blind else None))
-    for b in range(B):          # measured bit-identical; bound as in the front-end tests
-        assert rel(outs[1][0][b], outs[0][0][b]) < 1e-2, (b, rel(outs[1][0][b], outs[0][0][b]))
+    for b in range(B):      # the stand-ins' fp32 sums depend on the batch shape in the last bits (measured <= 1.3e-5 after
+        # amplification by this expansive toy trajectory); wrong bookkeeping is an O(1) difference
+        assert rel(outs[1][0][b], outs[0][0][b]) < 1e-3, (b, rel(outs[1][0][b], outs[0][0][b]))
         if blind:
-            assert rel(outs[1][1][b], outs[0][1][b]) < 1e-2
+            assert rel(outs[1][1][b], outs[0][1][b]) < 1e-3
